@@ -192,7 +192,7 @@ def test_resize_saturated_and_random():
     y, gx = run_with_grad(lambda t: O.resize(t, 0.8), T("xsat"), T("g32"), torch.float64)
     assert maxdiff(y, T("resize/bicubic/r0.8/xsat/y")) <= 5e-6
     ratio = float(GOLD["resize/random/ratio"])
-    assert maxdiff(O.resize(T("x32").double(), ratio), T("resize/random/x32/y")) <= 2e-6
+    assert maxdiff(O.resize(T("x32").double(), ratio), T("resize/random/x32/y")) <= 5e-6
 
 
 @pytest.mark.parametrize("mode", ("bicubic", "bilinear"))
