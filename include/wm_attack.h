@@ -1,0 +1,182 @@
+/* libwmattack — C ABI of the B200-native "tailored attacking layer".
+ *
+ * Drop-in scope: the differentiable distortion pipeline of
+ * yingqichao/video-watermarking-forgery-detection (noise_layers/ and utils/JPEG.py::DiffJPEG).
+ * The reference has no FFI: its boundary is Python nn.Modules.  Each entry point below is
+ * the device-side replacement of the torch op graph behind ONE reference forward (cited as
+ * reference file:line); the Python host layer (wmattack/) re-creates the nn.Module surface
+ * on top of these calls through ctypes.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - Images are float32 [B, C, H, W]; the innermost (W) stride is 1.  Inputs carry element
+ *     strides (sb, sc, sh) so that slices such as x[:, :, t] of a [B,3,T,H,W] clip are read
+ *     in place; outputs are written densely (NCHW contiguous).
+ *   - `stream` is a cudaStream_t passed as void*.  Every call is asynchronous on that
+ *     stream, allocates nothing, and never synchronises.
+ *   - Return value: 0 = ok; < 0 = WM_E_* invalid-argument code; > 0 = cudaError_t.
+ *     wm_last_error() returns a thread-local human-readable message for the last failure.
+ *   - There is no CPU path.
+ */
+#ifndef WM_ATTACK_H
+#define WM_ATTACK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WM_ABI_VERSION 1
+
+#define WM_OK 0
+#define WM_E_NULL (-1)      /* required pointer is NULL */
+#define WM_E_SHAPE (-2)     /* unsupported shape (e.g. H,W not multiples of 16 for DiffJPEG) */
+#define WM_E_ALIGN (-3)     /* pointer / stride alignment not met (see each call) */
+#define WM_E_ARG (-4)       /* enum / scalar argument out of range */
+
+/* rounding surrogates of the JPEG quantiser */
+#define WM_ROUND_ONLY_AT_0 0 /* utils/JPEG.py:482 round_only_at_0 (== JpegSS.round_ss, noise_layers/jpeg.py:255) */
+#define WM_ROUND_CUBIC 1     /* utils/JPEG.py:472 diff_round */
+#define WM_ROUND_HARD 2      /* torch.round (half to even) */
+#define WM_ROUND_FOURIER 3   /* utils/JPEG_utils.py:36 diff_round (9-term Fourier series) */
+
+int wm_version(void);
+const char* wm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * DiffJPEG  —  utils/JPEG.py:501-540 (compress_jpeg :256-291, decompress_jpeg :431-469)
+ *   x: [B,3,H,W] in [0,1], strides (x_sb, x_sc, x_sh) in elements, multiples of 8, base
+ *      pointer 32-byte aligned; H, W multiples of 16.
+ *   factor: quality_to_factor(quality) (utils/JPEG.py:487); if factor_per_sample != NULL it
+ *      is a device array [B] that overrides `factor` per image (quality sweep extension).
+ * ------------------------------------------------------------------------------------------ */
+int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                    float* y, int B, int H, int W,
+                    float factor, const float* factor_per_sample, int rounding, void* stream);
+
+/* gx = d<gy, DiffJPEG(x)>/dx, recomputed from x (nothing saved by the forward).
+ * Replaces autograd over the ~30 saved activations of the reference graph. */
+int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                    const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
+                    float* gx, int B, int H, int W,
+                    float factor, const float* factor_per_sample, int rounding, void* stream);
+
+/* compress_jpeg.forward (utils/JPEG.py:279-291): rounded quantised coefficients,
+ * coef_y [B, H*W/64, 8, 8], coef_cb / coef_cr [B, H*W/256, 8, 8] (block raster order). */
+int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                         float* coef_y, float* coef_cb, float* coef_cr, int B, int H, int W,
+                         float factor, const float* factor_per_sample, int rounding, void* stream);
+
+/* decompress_jpeg.forward (utils/JPEG.py:452-469) */
+int wm_diffjpeg_decompress(const float* coef_y, const float* coef_cb, const float* coef_cr,
+                           float* y, int B, int H, int W,
+                           float factor, const float* factor_per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 8x8-unit 4:4:4 JPEG simulators — Jpeg / JpegSS / JpegMask (noise_layers/jpeg.py:214-306)
+ * and HiDDeN JpegCompression (noise_layers/jpeg_compression.py:65-159) share one kernel:
+ *   yuv = fwd_color * rgb ; zero-pad to x8 ; [subsample] ; C = D X D^T ;
+ *   HARD: rint(C/T)*T   SS: ss(C/T)*T   MASK: C*T (T in {0,1}) ; X' = D^T C' D ;
+ *   rgb' = inv_color * yuv' ; un-pad.   No clamp.
+ * params_host: host pointer to wm_jpeg8_params (copied into the launch).
+ * Any H, W >= 1 (the reference is correct for square inputs only, jpeg.py:123-127).
+ * ------------------------------------------------------------------------------------------ */
+#define WM_JPEG8_HARD 0
+#define WM_JPEG8_SS 1
+#define WM_JPEG8_MASK 2
+
+typedef struct wm_jpeg8_params {
+    float fwd_color[9];   /* row-major 3x3, includes the x255 of jpeg.py:168 where applicable */
+    float inv_color[9];   /* row-major 3x3, includes the /255 of jpeg.py:200 where applicable */
+    float table[3][64];   /* per channel, [u*8+v], u = vertical frequency: quant steps or keep mask */
+    int variant;          /* WM_JPEG8_* */
+    int subsample;        /* 0, or 2 = in-block chroma decimation of jpeg.py:202-211 */
+} wm_jpeg8_params;
+
+int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                 float* y, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                 const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
+                 float* gx, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+/* std_quantization output (noise_layers/jpeg.py:52-82) as a [B,3,Hp,Wp] coefficient image,
+ * Hp/Wp = H/W rounded up to x8: the integer-exact parity target for Jpeg. */
+int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                       float* coef, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Separable Gaussian blur, depth-wise over N = B*C planes.
+ *   border 0 = zero padding  (GaussianBlur, noise_layers/gaussian_blur.py:44-56)
+ *   border 1 = reflect       (GF -> kornia GaussianBlur2d, noise_layers/gaussian_filter.py:9)
+ * taps_host: k normalised 1-D taps (k odd, k <= 31).  x plane stride = x_sp elements, row
+ * stride x_sh.  `adjoint` != 0 applies the transpose operator (== backward); for border 0
+ * it is the same filter.
+ * ------------------------------------------------------------------------------------------ */
+int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
+                 const float* taps_host, int k, int border, int adjoint, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * k x k median, zero padding, k in {3,5}  (MiddleBlur, noise_layers/middle_filter.py:5-13 ->
+ * kornia MedianBlur).  idx (optional, uint8 [N,H,W]) receives the raster position inside
+ * the window of the FIRST element equal to the median; wm_median_bwd routes gy through it.
+ * ------------------------------------------------------------------------------------------ */
+int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
+                  int N, int H, int W, int k, void* stream);
+int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise attacks over n contiguous floats.  Randomness: Philox4x32-10 keyed by `seed`,
+ * counter = element index / 4 + `offset`; if `inject` != NULL that device array [n] is used
+ * instead (parity tests inject the reference's random tensor).
+ * ------------------------------------------------------------------------------------------ */
+/* Gaussian (noise_layers/gaussian.py:10-17, clamp=1) and GN (noise_layers/gaussian_noise.py:13-16, clamp=0) */
+int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
+                      uint64_t seed, uint64_t offset, const float* inject, void* stream);
+int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
+                      int clamp, uint64_t seed, uint64_t offset, const float* inject, void* stream);
+/* SaltPepper (noise_layers/salt_pepper_noise.py:11-19) */
+int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob,
+                      uint64_t seed, uint64_t offset, const float* inject, void* stream);
+int wm_saltpepper_bwd(const float* gy, float* gx, int64_t n, float prob,
+                      uint64_t seed, uint64_t offset, const float* inject, void* stream);
+/* crop.Dropout (noise_layers/crop.py:142-147): y = rdn > prob ? cover : image */
+int wm_dropout_elem_fwd(const float* image, const float* cover, float* y, int64_t n, float prob,
+                        uint64_t seed, uint64_t offset, const float* inject, void* stream);
+int wm_dropout_elem_bwd(const float* gy, float* g_image, float* g_cover, int64_t n, float prob,
+                        uint64_t seed, uint64_t offset, const float* inject, void* stream);
+/* dropout.Dropout (noise_layers/dropout.py:14-27): mask [H*W] in {0,1} shared by all planes */
+int wm_dropout_mask_fwd(const float* noised, const float* cover, const float* mask_hw, float* y,
+                        int64_t planes, int64_t hw, void* stream);
+int wm_dropout_mask_bwd(const float* gy, const float* mask_hw, float* g_noised, float* g_cover,
+                        int64_t planes, int64_t hw, void* stream);
+/* Fill mask_hw[hw] with Bernoulli(keep) in {0,1} from Philox (fast path of dropout.py:21) */
+int wm_bernoulli_mask(float* mask_hw, int64_t hw, float keep, uint64_t seed, uint64_t offset, void* stream);
+/* Quantization (models/modules/Quantization.py:7-10): rint(x*255)/255; clamp01 != 0 applies
+ * the utils/JPEG_utils.py:48 variant (clamp to [0,1] first). */
+int wm_quantize8_fwd(const float* x, float* y, int64_t n, int clamp01, void* stream);
+/* Cropout (noise_layers/crop.py:128-134): y = cover with image pasted inside the box */
+int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t planes, int H, int W,
+                   int h0, int h1, int w0, int w1, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Interpolation (F.interpolate(size=..., align_corners=False) semantics, ATen
+ * upsample_bilinear2d / upsample_bicubic2d A=-0.75) over N = B*C planes.
+ *   mode 0 = bilinear, 1 = bicubic.  The source window (h0, w0, Hin, Win) addresses a crop of
+ *   a [N, Hsrc, Wsrc] plane stack (plane stride x_sp, row stride x_sh) so that
+ *   Crop (noise_layers/crop.py:48-53) needs no copy.  clamp01: clamp the result to [0,1]
+ *   (Resize, noise_layers/resize.py:53).
+ * wm_interp_bwd is the exact transpose (two separable deterministic gather passes, no
+ * atomics): gx is the dense [N, Hsrc, Wsrc] gradient (zero outside the source window); if
+ * `pre` != NULL (same shape as gy) gy is first masked by 0 <= pre <= 1 (torch.clamp backward).
+ * workspace: caller-provided device scratch of N * Hin * Wout floats.
+ * ------------------------------------------------------------------------------------------ */
+int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0, int w0, int Hin, int Win,
+                  float* y, int N, int Hout, int Wout, int mode, int clamp01, void* stream);
+int wm_interp_bwd(const float* gy, const float* pre, int N, int Hout, int Wout,
+                  float* gx, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
+                  int mode, float* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WM_ATTACK_H */

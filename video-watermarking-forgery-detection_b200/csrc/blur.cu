@@ -1,0 +1,139 @@
+// Separable Gaussian blur over N = B*C planes (depth-wise), zero or reflect border.
+//
+// Replaces: GaussianBlur.forward (noise_layers/gaussian_blur.py:53-56), which builds a fresh
+// nn.Conv2d and uploads its weights on EVERY call, and GF / kornia GaussianBlur2d
+// (noise_layers/gaussian_filter.py:9-13).  The 2-D kernel of the reference is the outer product
+// of normalised 1-D taps, so one CTA stages a (TH+2r) x (TW+2r) halo tile in shared memory,
+// runs the horizontal pass into a second shared buffer and the vertical pass straight to
+// global memory: x is read once (+halo) and y written once.
+// Backward: the filter is symmetric, so with zero padding the adjoint is the same operator.
+// For the reflect border the adjoint folds the out-of-range part of the zero-extended
+// response back onto the interior (gather form, deterministic).
+#include "wm_common.cuh"
+
+namespace wm {
+
+constexpr int BL_TW = 128, BL_TH = 32, BL_THREADS = 256, BL_MAXK = 31;
+
+struct BlurArgs {
+    const float* x; int64_t x_sp, x_sh;
+    float* y; int N, H, W, k, r, border;
+    float taps[BL_MAXK + 1];
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // kornia / F.pad(mode='reflect'): -i -> i, n-1+i -> n-1-i   (requires r < n)
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(BL_THREADS) gaussblur_kernel(const BlurArgs a) {
+    extern __shared__ float sm[];
+    const int r = a.r, k = a.k;
+    const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;
+    float* tin = sm;                       // [IH][IW]
+    float* tmp = sm + IH * IW;             // [IH][BL_TW]
+    const int tiles_x = (a.W + BL_TW - 1) / BL_TW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int n = blockIdx.y;
+    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    const float* src = a.x + int64_t(n) * a.x_sp;
+    for (int i = threadIdx.x; i < IH * IW; i += BL_THREADS) {
+        const int ly = i / IW, lx = i - ly * IW;
+        int gy = y0 + ly - r, gx = x0 + lx - r;
+        float v = 0.f;
+        if (a.border == 1) {
+            // rows/cols beyond the reflected range of this (possibly partial) tile are unused
+            gy = reflect_idx(gy, a.H); gx = reflect_idx(gx, a.W);
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = __ldg(src + int64_t(gy) * a.x_sh + gx);
+        } else if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+            v = __ldg(src + int64_t(gy) * a.x_sh + gx);
+        }
+        tin[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IH * BL_TW; i += BL_THREADS) {
+        const int ly = i / BL_TW, lx = i - ly * BL_TW;
+        const float* p = tin + ly * IW + lx;
+        float acc = 0.f;
+        for (int t = 0; t < k; ++t) acc = fmaf(a.taps[t], p[t], acc);
+        tmp[i] = acc;
+    }
+    __syncthreads();
+    float* dst = a.y + int64_t(n) * a.H * a.W;
+    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_THREADS) {
+        const int ly = i / BL_TW, lx = i - ly * BL_TW;
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (gy < a.H && gx < a.W) {
+            const float* p = tmp + ly * BL_TW + lx;
+            float acc = 0.f;
+            for (int t = 0; t < k; ++t) acc = fmaf(a.taps[t], p[t * BL_TW], acc);
+            dst[int64_t(gy) * a.W + gx] = acc;
+        }
+    }
+}
+
+// adjoint of the reflect-border blur, direct gather (GF is never instantiated by the
+// reference's trainers; this path favours clarity over speed)
+__global__ void __launch_bounds__(256) gaussblur_reflect_adjoint_kernel(const BlurArgs a) {
+    const int64_t total = int64_t(a.N) * a.H * a.W;
+    const int r = a.r;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int w = int(i % a.W), h = int((i / a.W) % a.H), n = int(i / (int64_t(a.W) * a.H));
+        const float* g = a.x + int64_t(n) * a.x_sp;
+        // positions of the zero-extended response that fold onto (h, w)
+        int ys[3], xs[3], ny = 0, nx = 0;
+        ys[ny++] = h; if (h >= 1 && h <= r) ys[ny++] = -h; if (h <= a.H - 2 && h >= a.H - 1 - r) ys[ny++] = 2 * (a.H - 1) - h;
+        xs[nx++] = w; if (w >= 1 && w <= r) xs[nx++] = -w; if (w <= a.W - 2 && w >= a.W - 1 - r) xs[nx++] = 2 * (a.W - 1) - w;
+        float acc = 0.f;
+        for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix)
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int sy = ys[iy] + dy;
+                    if (sy < 0 || sy >= a.H) continue;
+                    float row = 0.f;
+                    for (int dx = -r; dx <= r; ++dx) {
+                        const int sx = xs[ix] + dx;
+                        if (sx >= 0 && sx < a.W) row = fmaf(a.taps[dx + r], __ldg(g + int64_t(sy) * a.x_sh + sx), row);
+                    }
+                    acc = fmaf(a.taps[dy + r], row, acc);
+                }
+        a.y[i] = acc;
+    }
+}
+
+}  // namespace wm
+
+using namespace wm;
+
+extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
+                            const float* taps_host, int k, int border, int adjoint, void* stream) {
+    WM_REQUIRE(x && y && taps_host, WM_E_NULL, "wm_gaussblur: null pointer");
+    WM_REQUIRE(k >= 1 && k <= BL_MAXK && (k & 1), WM_E_ARG, "wm_gaussblur: kernel size must be odd and <= %d (got %d)", BL_MAXK, k);
+    WM_REQUIRE(border == 0 || border == 1, WM_E_ARG, "wm_gaussblur: border must be 0 (zero) or 1 (reflect)");
+    WM_REQUIRE(N >= 0 && H > 0 && W > 0, WM_E_SHAPE, "wm_gaussblur: bad shape N=%d H=%d W=%d", N, H, W);
+    const int r = (k - 1) / 2;
+    WM_REQUIRE(border == 0 || (r < H && r < W), WM_E_SHAPE, "wm_gaussblur: reflect border needs k/2 < H, W");
+    if (N == 0) return WM_OK;
+    BlurArgs a{};
+    a.x = x; a.x_sp = x_sp; a.x_sh = x_sh; a.y = y; a.N = N; a.H = H; a.W = W; a.k = k; a.r = r; a.border = border;
+    for (int i = 0; i < k; ++i) a.taps[i] = taps_host[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (border == 1 && adjoint) {
+        const int64_t total = int64_t(N) * H * W;
+        const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 16;
+        gaussblur_reflect_adjoint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a);
+        WM_LAUNCH_CHECK("wm_gaussblur(reflect adjoint)");
+        return WM_OK;
+    }
+    const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;
+    const size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * BL_TW);
+    cudaError_t e = cudaFuncSetAttribute(gaussblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
+    const int tiles = ((W + BL_TW - 1) / BL_TW) * ((H + BL_TH - 1) / BL_TH);
+    WM_REQUIRE(N <= 65535, WM_E_SHAPE, "wm_gaussblur: at most 65535 planes per call (got %d)", N);
+    gaussblur_kernel<<<dim3(tiles, N), BL_THREADS, smem, st>>>(a);
+    WM_LAUNCH_CHECK("wm_gaussblur");
+    return WM_OK;
+}

@@ -1,0 +1,315 @@
+// Elementwise attacks: Gaussian / GN noise, salt-and-pepper, both Dropout flavours, Cropout,
+// 8-bit Quantization.  All are single-pass float4 streaming kernels; per-element randomness is
+// Philox4x32-10 generated in registers (the reference draws full-size random tensors on the
+// HOST and copies them over PCIe: noise_layers/salt_pepper_noise.py:14, crop.py:145,
+// gaussian_noise.py:14, dropout.py:21), with an `inject` pointer so that parity tests can feed
+// the very tensor the reference drew.
+#include "wm_common.cuh"
+
+namespace wm {
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (idx_lo, idx_hi, 0, 0), key = seed -------
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t ctr) const {
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+// uniform in [0,1) with 24 bits (same support as torch.rand float32)
+__device__ __forceinline__ float u01(uint32_t r) { return (r >> 8) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ float4 uniform4(const Philox& ph, uint64_t ctr) {
+    const uint4 r = ph(ctr);
+    return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+__device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t ctr) {
+    const uint4 r = ph(ctr);
+    // Box-Muller on (0,1] x [0,1)
+    const float u1 = ((r.x >> 8) + 1) * (1.0f / 16777216.0f), u2 = u01(r.y);
+    const float u3 = ((r.z >> 8) + 1) * (1.0f / 16777216.0f), u4 = u01(r.w);
+    const float ra = sqrtf(-2.f * __logf(u1)), rb = sqrtf(-2.f * __logf(u3));
+    float s1, c1, s2, c2;
+    __sincosf(6.283185307179586f * u2, &s1, &c1);
+    __sincosf(6.283185307179586f * u4, &s2, &c2);
+    return make_float4(ra * c1, ra * s1, rb * c2, rb * s2);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i, int64_t n) {
+    if (i + 3 < n) return *reinterpret_cast<const float4*>(p + i);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) r.x = p[i];
+    if (i + 1 < n) r.y = p[i + 1];
+    if (i + 2 < n) r.z = p[i + 2];
+    return r;
+}
+__device__ __forceinline__ void st4(float* p, int64_t i, int64_t n, float4 v) {
+    if (i + 3 < n) { *reinterpret_cast<float4*>(p + i) = v; return; }
+    if (i < n) p[i] = v.x;
+    if (i + 1 < n) p[i + 1] = v.y;
+    if (i + 2 < n) p[i + 2] = v.z;
+}
+
+#define WM_EW_LOOP(i)                                                                         \
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;             \
+         i += int64_t(gridDim.x) * blockDim.x * 4)
+
+// ---- Gaussian / GN ---------------------------------------------------------------------------
+// fwd: y = [clamp01](x + mean + std * N);  bwd: gx = gy * 1[0 <= x + noise <= 1] (torch.clamp is
+// inclusive) or gy when not clamped.
+template <bool BWD>
+__global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                         float* __restrict__ out, int64_t n, float mean, float std,
+                                                         int clamp, uint64_t seed, uint64_t offset,
+                                                         const float* __restrict__ inject) {
+    const Philox ph(seed);
+    WM_EW_LOOP(i) {
+        float4 nz;
+        if (inject) nz = ld4(inject, i, n);
+        else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
+               nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
+        const float4 xv = ld4(x, i, n);
+        float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
+        if (!BWD) {
+            if (clamp) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
+                         v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
+            st4(out, i, n, v);
+        } else {
+            float4 g = ld4(gy, i, n);
+            if (clamp) { g.x = (v.x >= 0.f && v.x <= 1.f) ? g.x : 0.f; g.y = (v.y >= 0.f && v.y <= 1.f) ? g.y : 0.f;
+                         g.z = (v.z >= 0.f && v.z <= 1.f) ? g.z : 0.f; g.w = (v.w >= 0.f && v.w <= 1.f) ? g.w : 0.f; }
+            st4(out, i, n, g);
+        }
+    }
+}
+
+// ---- SaltPepper (noise_layers/salt_pepper_noise.py:11-19) ------------------------------------
+__device__ __forceinline__ float sp_one(float x, float r, float p0, float p1) {
+    float o = r > p1 ? 0.f : x;
+    return r < p0 ? 1.f : o;
+}
+template <bool BWD>
+__global__ void __launch_bounds__(256) saltpepper_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n,
+                                                         float p0, float p1, uint64_t seed, uint64_t offset,
+                                                         const float* __restrict__ inject) {
+    const Philox ph(seed);
+    WM_EW_LOOP(i) {
+        const float4 r = inject ? ld4(inject, i, n) : uniform4(ph, (uint64_t)(i >> 2) + offset);
+        const float4 v = ld4(x, i, n);   // x (fwd) or gy (bwd)
+        float4 o;
+        if (!BWD) { o.x = sp_one(v.x, r.x, p0, p1); o.y = sp_one(v.y, r.y, p0, p1);
+                    o.z = sp_one(v.z, r.z, p0, p1); o.w = sp_one(v.w, r.w, p0, p1); }
+        else { o.x = (r.x > p1 || r.x < p0) ? 0.f : v.x; o.y = (r.y > p1 || r.y < p0) ? 0.f : v.y;
+               o.z = (r.z > p1 || r.z < p0) ? 0.f : v.z; o.w = (r.w > p1 || r.w < p0) ? 0.f : v.w; }
+        st4(out, i, n, o);
+    }
+}
+
+// ---- crop.Dropout (noise_layers/crop.py:142-147): y = rdn > prob ? cover : image ---------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) dropout_elem_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           float* __restrict__ o1, float* __restrict__ o2, int64_t n,
+                                                           float prob, uint64_t seed, uint64_t offset,
+                                                           const float* __restrict__ inject) {
+    const Philox ph(seed);
+    WM_EW_LOOP(i) {
+        const float4 r = inject ? ld4(inject, i, n) : uniform4(ph, (uint64_t)(i >> 2) + offset);
+        if (!BWD) {
+            const float4 im = ld4(a, i, n), cv = ld4(b, i, n);
+            st4(o1, i, n, make_float4(r.x > prob ? cv.x : im.x, r.y > prob ? cv.y : im.y,
+                                      r.z > prob ? cv.z : im.z, r.w > prob ? cv.w : im.w));
+        } else {
+            const float4 g = ld4(a, i, n);
+            if (o1) st4(o1, i, n, make_float4(r.x > prob ? 0.f : g.x, r.y > prob ? 0.f : g.y,
+                                              r.z > prob ? 0.f : g.z, r.w > prob ? 0.f : g.w));
+            if (o2) st4(o2, i, n, make_float4(r.x > prob ? g.x : 0.f, r.y > prob ? g.y : 0.f,
+                                              r.z > prob ? g.z : 0.f, r.w > prob ? g.w : 0.f));
+        }
+    }
+}
+
+// ---- dropout.Dropout (noise_layers/dropout.py:14-27): y = noised*m + cover*(1-m), m[H*W] -------
+template <bool BWD>
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           const float* __restrict__ mask, float* __restrict__ o1,
+                                                           float* __restrict__ o2, int64_t hw) {
+    const int64_t base = int64_t(blockIdx.y) * hw;
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < hw; i += int64_t(gridDim.x) * blockDim.x * 4) {
+        const float4 m = ld4(mask, i, hw);
+        if (!BWD) {
+            const float4 nz = ld4(a + base, i, hw), cv = ld4(b + base, i, hw);
+            st4(o1 + base, i, hw, make_float4(nz.x * m.x + cv.x * (1.f - m.x), nz.y * m.y + cv.y * (1.f - m.y),
+                                              nz.z * m.z + cv.z * (1.f - m.z), nz.w * m.w + cv.w * (1.f - m.w)));
+        } else {
+            const float4 g = ld4(a + base, i, hw);
+            if (o1) st4(o1 + base, i, hw, make_float4(g.x * m.x, g.y * m.y, g.z * m.z, g.w * m.w));
+            if (o2) st4(o2 + base, i, hw, make_float4(g.x * (1.f - m.x), g.y * (1.f - m.y), g.z * (1.f - m.z), g.w * (1.f - m.w)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bernoulli_kernel(float* __restrict__ mask, int64_t n, float keep,
+                                                        uint64_t seed, uint64_t offset) {
+    const Philox ph(seed);
+    WM_EW_LOOP(i) {
+        const float4 r = uniform4(ph, (uint64_t)(i >> 2) + offset);
+        st4(mask, i, n, make_float4(r.x < keep ? 1.f : 0.f, r.y < keep ? 1.f : 0.f, r.z < keep ? 1.f : 0.f, r.w < keep ? 1.f : 0.f));
+    }
+}
+
+// ---- Quantization (models/modules/Quantization.py:7-10; utils/JPEG_utils.py:46-50 with clamp) --
+__global__ void __launch_bounds__(256) quantize8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int clamp01) {
+    WM_EW_LOOP(i) {
+        float4 v = ld4(x, i, n);
+        if (clamp01) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
+                       v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
+        // true division by 255 keeps bit-parity with torch's `/ 255.`
+        st4(y, i, n, make_float4(__fdiv_rn(rintf(v.x * 255.f), 255.f), __fdiv_rn(rintf(v.y * 255.f), 255.f),
+                                 __fdiv_rn(rintf(v.z * 255.f), 255.f), __fdiv_rn(rintf(v.w * 255.f), 255.f)));
+    }
+}
+
+// ---- Cropout (noise_layers/crop.py:128-134) ----------------------------------------------------
+__global__ void __launch_bounds__(256) cropout_kernel(const float* __restrict__ image, const float* __restrict__ cover,
+                                                      float* __restrict__ y, int64_t total, int H, int W,
+                                                      int h0, int h1, int w0, int w1) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int w = int(i % W), h = int((i / W) % H);
+        const bool in = h >= h0 && h < h1 && w >= w0 && w < w1;
+        y[i] = in ? image[i] : cover[i];
+    }
+}
+
+static inline unsigned ew_grid(int64_t n_vec) {
+    const int64_t want = (n_vec + 255) / 256;
+    const int64_t cap = int64_t(sm_count()) * 16;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace wm
+
+using namespace wm;
+
+#define EW_ALIGN_CHECK(who, ...)                                                                \
+    do { const void* ps__[] = {__VA_ARGS__};                                                    \
+         for (const void* p__ : ps__) WM_REQUIRE(p__ == nullptr || aligned(p__, 16), WM_E_ALIGN, \
+             "%s: pointers must be 16-byte aligned", who); } while (0)
+
+extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
+                                 uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
+    EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
+    if (n <= 0) return WM_OK;
+    gaussnoise_kernel<false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_gaussnoise_fwd");
+    return WM_OK;
+}
+extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
+                                 int clamp, uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    WM_REQUIRE(gy && gx && (x || !clamp), WM_E_NULL, "wm_gaussnoise_bwd: null pointer");
+    EW_ALIGN_CHECK("wm_gaussnoise_bwd", x, gy, gx, inject);
+    if (n <= 0) return WM_OK;
+    if (!clamp) {   // GN: identity gradient
+        cudaError_t e = cudaMemcpyAsync(gx, gy, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        return e == cudaSuccess ? WM_OK : cuda_fail(e, "wm_gaussnoise_bwd");
+    }
+    gaussnoise_kernel<true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, mean, std, clamp, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_gaussnoise_bwd");
+    return WM_OK;
+}
+extern "C" int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob, uint64_t seed, uint64_t offset,
+                                 const float* inject, void* stream) {
+    WM_REQUIRE(x && y, WM_E_NULL, "wm_saltpepper_fwd: null pointer");
+    EW_ALIGN_CHECK("wm_saltpepper_fwd", x, y, inject);
+    if (n <= 0) return WM_OK;
+    // thresholds in the reference's arithmetic: python doubles prob/2 and 1 - prob/2 compared
+    // against a float32 tensor (promoted scalar -> float32)
+    const float p0 = (float)((double)prob / 2.0), p1 = (float)(1.0 - (double)prob / 2.0);
+    saltpepper_kernel<false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p0, p1, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_saltpepper_fwd");
+    return WM_OK;
+}
+extern "C" int wm_saltpepper_bwd(const float* gy, float* gx, int64_t n, float prob, uint64_t seed, uint64_t offset,
+                                 const float* inject, void* stream) {
+    WM_REQUIRE(gy && gx, WM_E_NULL, "wm_saltpepper_bwd: null pointer");
+    EW_ALIGN_CHECK("wm_saltpepper_bwd", gy, gx, inject);
+    if (n <= 0) return WM_OK;
+    const float p0 = (float)((double)prob / 2.0), p1 = (float)(1.0 - (double)prob / 2.0);
+    saltpepper_kernel<true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, gx, n, p0, p1, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_saltpepper_bwd");
+    return WM_OK;
+}
+extern "C" int wm_dropout_elem_fwd(const float* image, const float* cover, float* y, int64_t n, float prob,
+                                   uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    WM_REQUIRE(image && cover && y, WM_E_NULL, "wm_dropout_elem_fwd: null pointer");
+    EW_ALIGN_CHECK("wm_dropout_elem_fwd", image, cover, y, inject);
+    if (n <= 0) return WM_OK;
+    dropout_elem_kernel<false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(image, cover, y, nullptr, n, prob, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_dropout_elem_fwd");
+    return WM_OK;
+}
+extern "C" int wm_dropout_elem_bwd(const float* gy, float* g_image, float* g_cover, int64_t n, float prob,
+                                   uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    WM_REQUIRE(gy && (g_image || g_cover), WM_E_NULL, "wm_dropout_elem_bwd: null pointer");
+    EW_ALIGN_CHECK("wm_dropout_elem_bwd", gy, g_image, g_cover, inject);
+    if (n <= 0) return WM_OK;
+    dropout_elem_kernel<true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, g_image, g_cover, n, prob, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_dropout_elem_bwd");
+    return WM_OK;
+}
+extern "C" int wm_dropout_mask_fwd(const float* noised, const float* cover, const float* mask_hw, float* y,
+                                   int64_t planes, int64_t hw, void* stream) {
+    WM_REQUIRE(noised && cover && mask_hw && y, WM_E_NULL, "wm_dropout_mask_fwd: null pointer");
+    WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_fwd: H*W must be a multiple of 4");
+    EW_ALIGN_CHECK("wm_dropout_mask_fwd", noised, cover, mask_hw, y);
+    if (planes <= 0 || hw <= 0) return WM_OK;
+    dim3 grid(ew_grid((hw + 3) / 4), (unsigned)planes);
+    dropout_mask_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(noised, cover, mask_hw, y, nullptr, hw);
+    WM_LAUNCH_CHECK("wm_dropout_mask_fwd");
+    return WM_OK;
+}
+extern "C" int wm_dropout_mask_bwd(const float* gy, const float* mask_hw, float* g_noised, float* g_cover,
+                                   int64_t planes, int64_t hw, void* stream) {
+    WM_REQUIRE(gy && mask_hw && (g_noised || g_cover), WM_E_NULL, "wm_dropout_mask_bwd: null pointer");
+    WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_bwd: H*W must be a multiple of 4");
+    EW_ALIGN_CHECK("wm_dropout_mask_bwd", gy, mask_hw, g_noised, g_cover);
+    if (planes <= 0 || hw <= 0) return WM_OK;
+    dim3 grid(ew_grid((hw + 3) / 4), (unsigned)planes);
+    dropout_mask_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask_hw, g_noised, g_cover, hw);
+    WM_LAUNCH_CHECK("wm_dropout_mask_bwd");
+    return WM_OK;
+}
+extern "C" int wm_bernoulli_mask(float* mask_hw, int64_t hw, float keep, uint64_t seed, uint64_t offset, void* stream) {
+    WM_REQUIRE(mask_hw, WM_E_NULL, "wm_bernoulli_mask: null pointer");
+    EW_ALIGN_CHECK("wm_bernoulli_mask", mask_hw);
+    if (hw <= 0) return WM_OK;
+    bernoulli_kernel<<<ew_grid((hw + 3) / 4), 256, 0, (cudaStream_t)stream>>>(mask_hw, hw, keep, seed, offset);
+    WM_LAUNCH_CHECK("wm_bernoulli_mask");
+    return WM_OK;
+}
+extern "C" int wm_quantize8_fwd(const float* x, float* y, int64_t n, int clamp01, void* stream) {
+    WM_REQUIRE(x && y, WM_E_NULL, "wm_quantize8_fwd: null pointer");
+    EW_ALIGN_CHECK("wm_quantize8_fwd", x, y);
+    if (n <= 0) return WM_OK;
+    quantize8_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, clamp01);
+    WM_LAUNCH_CHECK("wm_quantize8_fwd");
+    return WM_OK;
+}
+extern "C" int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t planes, int H, int W,
+                              int h0, int h1, int w0, int w1, void* stream) {
+    WM_REQUIRE(image && cover && y, WM_E_NULL, "wm_cropout_fwd: null pointer");
+    const int64_t total = planes * H * W;
+    if (total <= 0) return WM_OK;
+    cropout_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, cover, y, total, H, W, h0, h1, w0, w1);
+    WM_LAUNCH_CHECK("wm_cropout_fwd");
+    return WM_OK;
+}

@@ -1,0 +1,574 @@
+"""torch.autograd.Function wrappers over the C ABI (include/wm_attack.h).
+
+Every function here launches hand-written sm_100a kernels from libwmattack.so on the current
+CUDA stream; PyTorch is used only to own device memory and to hook into autograd.
+There is deliberately NO CPU implementation: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Jpeg8Params
+
+ROUND_ONLY_AT_0, ROUND_CUBIC, ROUND_HARD, ROUND_FOURIER = 0, 1, 2, 3
+JPEG8_HARD, JPEG8_SS, JPEG8_MASK = 0, 1, 2
+BILINEAR, BICUBIC = 0, 1
+_MODES = {"bilinear": BILINEAR, "bicubic": BICUBIC}
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(t: torch.Tensor, who: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{who}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: expected a CUDA tensor — this package has no CPU fallback "
+                           f"(got device {t.device})")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _image(t: torch.Tensor, who: str, align_elems: int = 8) -> Tuple[torch.Tensor, int, int, int]:
+    """Return (tensor, sb, sc, sh) of a [B,C,H,W] float32 CUDA tensor readable in place by the
+    vector kernels (unit W stride, aligned strides/base); otherwise a contiguous copy."""
+    _check_cuda(t, who)
+    if t.dim() != 4:
+        raise ValueError(f"{who}: expected a 4-D [B,C,H,W] tensor, got shape {tuple(t.shape)}")
+    t = _f32(t)
+    sb, sc, sh, sw = t.stride()
+    ok = (sw == 1 and sb % align_elems == 0 and sc % align_elems == 0 and sh % align_elems == 0
+          and t.data_ptr() % (4 * align_elems) == 0 and min(sb, sc, sh) >= 0)
+    if not ok:
+        t = t.contiguous()
+        sb, sc, sh, sw = t.stride()
+    return t, sb, sc, sh
+
+
+def _planes(t: torch.Tensor, who: str) -> Tuple[torch.Tensor, int, int]:
+    """[B,C,H,W] viewed as N = B*C planes with one plane stride (needs sb == C*sc)."""
+    _check_cuda(t, who)
+    if t.dim() != 4:
+        raise ValueError(f"{who}: expected a 4-D [B,C,H,W] tensor, got shape {tuple(t.shape)}")
+    t = _f32(t)
+    b, c, h, w = t.shape
+    sb, sc, sh, sw = t.stride()
+    if not (sw == 1 and (b == 1 or sb == c * sc) and sh >= w and sc >= 0):
+        t = t.contiguous()
+        sb, sc, sh, sw = t.stride()
+    return t, sc, sh
+
+
+def _flat(t: torch.Tensor, who: str) -> torch.Tensor:
+    _check_cuda(t, who)
+    return _f32(t).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+_rng_lock = threading.Lock()
+_rng_calls = 0
+
+
+def next_philox_stream(n_elems: int) -> Tuple[int, int]:
+    """(seed, offset) for an in-kernel Philox draw of n_elems values: seeded by
+    torch.initial_seed(), advanced per call so that successive layers decorrelate.
+    Per-rank decorrelation under DDP comes from each rank's own call sequence + rank offset."""
+    global _rng_calls
+    with _rng_lock:
+        off = _rng_calls
+        _rng_calls += (n_elems + 3) // 4 + 1
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, (off + (rank << 44)) & 0xFFFFFFFFFFFFFFFF
+
+
+# --------------------------------------------------------------------------------------
+# DiffJPEG
+# --------------------------------------------------------------------------------------
+
+def quality_to_factor(quality: float) -> float:
+    """utils/JPEG.py:487-498 (quality == 100 gives 0 and divides by zero downstream, as upstream)."""
+    q = 5000.0 / quality if quality < 50 else 200.0 - quality * 2
+    return q / 100.0
+
+
+def _factor_args(factor, batch: int, device) -> Tuple[float, Optional[torch.Tensor]]:
+    if torch.is_tensor(factor):
+        f = factor.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        if f.numel() == 1:
+            return float(f.item()), None
+        if f.numel() != batch:
+            raise ValueError(f"per-sample factor must have {batch} entries, got {f.numel()}")
+        return 0.0, f
+    return float(factor), None
+
+
+class _DiffJPEGFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, factor, rounding):
+        x, sb, sc, sh = _image(x, "DiffJPEG")
+        b, c, h, w = x.shape
+        if c != 3:
+            raise ValueError(f"DiffJPEG expects 3 channels, got {c}")
+        if h % 16 or w % 16:
+            raise ValueError(f"DiffJPEG needs H and W to be multiples of 16 (got {h}x{w}); the reference's "
+                             "block_merging views require it (utils/JPEG.py:371-376)")
+        fs, fps = _factor_args(factor, b, x.device)
+        y = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
+        _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+        ctx.save_for_backward(x, fps if fps is not None else torch.empty(0, device=x.device))
+        ctx.meta = (fs, fps is not None, rounding)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, fps_t = ctx.saved_tensors
+        fs, has_fps, rounding = ctx.meta
+        b, _, h, w = x.shape
+        if rounding == ROUND_HARD:
+            return torch.zeros_like(x), None, None
+        gy, gsb, gsc, gsh = _image(gy, "DiffJPEG.backward")
+        sb, sc, sh, _ = x.stride()
+        gx = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
+        _lib.call("wm_diffjpeg_bwd", x.data_ptr(), sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(),
+                  b, h, w, fs, _ptr(fps_t) if has_fps else None, rounding, _stream())
+        return gx, None, None
+
+
+def diffjpeg(x: torch.Tensor, factor, rounding: int = ROUND_ONLY_AT_0) -> torch.Tensor:
+    """Fused DiffJPEG (utils/JPEG.py:535-540).  `factor` = quality_to_factor(quality), a python
+    float or a per-sample tensor [B]."""
+    return _DiffJPEGFn.apply(x, factor, rounding)
+
+
+def diffjpeg_compress(x: torch.Tensor, factor, rounding: int = ROUND_HARD):
+    """compress_jpeg.forward (utils/JPEG.py:279-291) -> (y, cb, cr) as [B, nblk, 8, 8]. No autograd."""
+    x, sb, sc, sh = _image(x.detach(), "DiffJPEG.compress")
+    b, c, h, w = x.shape
+    if c != 3 or h % 16 or w % 16:
+        raise ValueError(f"compress expects [B,3,H,W] with H,W multiples of 16, got {tuple(x.shape)}")
+    fs, fps = _factor_args(factor, b, x.device)
+    cy = torch.empty((b, h * w // 64, 8, 8), device=x.device, dtype=torch.float32)
+    ccb = torch.empty((b, h * w // 256, 8, 8), device=x.device, dtype=torch.float32)
+    ccr = torch.empty_like(ccb)
+    _lib.call("wm_diffjpeg_compress", x.data_ptr(), sb, sc, sh, cy.data_ptr(), ccb.data_ptr(), ccr.data_ptr(),
+              b, h, w, fs, _ptr(fps), rounding, _stream())
+    return cy, ccb, ccr
+
+
+def diffjpeg_decompress(y, cb, cr, height: int, width: int, factor) -> torch.Tensor:
+    """decompress_jpeg.forward (utils/JPEG.py:452-469). No autograd."""
+    for t in (y, cb, cr):
+        _check_cuda(t, "DiffJPEG.decompress")
+    y, cb, cr = (_f32(t.detach()).contiguous() for t in (y, cb, cr))
+    b = y.shape[0]
+    if height % 16 or width % 16 or y.numel() != b * height * width or cb.numel() != y.numel() // 4:
+        raise ValueError("decompress: coefficient tensors do not match height/width")
+    fs, fps = _factor_args(factor, b, y.device)
+    out = torch.empty((b, 3, height, width), device=y.device, dtype=torch.float32)
+    _lib.call("wm_diffjpeg_decompress", y.data_ptr(), cb.data_ptr(), cr.data_ptr(), out.data_ptr(),
+              b, height, width, fs, _ptr(fps), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# 8x8-unit JPEG family
+# --------------------------------------------------------------------------------------
+
+def make_jpeg8_params(fwd_color: Sequence[float], inv_color: Sequence[float], table: np.ndarray,
+                      variant: int, subsample: int) -> Jpeg8Params:
+    p = Jpeg8Params()
+    for i in range(9):
+        p.fwd_color[i] = float(fwd_color[i])
+        p.inv_color[i] = float(inv_color[i])
+    tab = np.asarray(table, dtype=np.float32).reshape(3, 64)
+    for c in range(3):
+        for i in range(64):
+            p.table[c][i] = float(tab[c, i])
+    p.variant, p.subsample = int(variant), int(subsample)
+    return p
+
+
+class _Jpeg8Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, params):
+        x, sb, sc, sh = _image(x, "jpeg8")
+        b, c, h, w = x.shape
+        if c != 3:
+            raise ValueError(f"JPEG layers expect 3 channels, got {c}")
+        y = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
+        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), _stream())
+        ctx.params = params
+        if params.variant == JPEG8_SS:
+            ctx.save_for_backward(x)
+        else:
+            ctx.shape = (b, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        p = ctx.params
+        if p.variant == JPEG8_SS:
+            (x,) = ctx.saved_tensors
+            b, _, h, w = x.shape
+            sb, sc, sh, _ = x.stride()
+            xp = x.data_ptr()
+        else:
+            b, h, w = ctx.shape
+            sb = sc = sh = 0
+            xp = None
+        gy, gsb, gsc, gsh = _image(gy, "jpeg8.backward")
+        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
+        _lib.call("wm_jpeg8_bwd", xp, sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(), b, h, w,
+                  C.byref(p), _stream())
+        return gx, None
+
+
+def jpeg8(x: torch.Tensor, params: Jpeg8Params) -> torch.Tensor:
+    return _Jpeg8Fn.apply(x, params)
+
+
+def jpeg8_quantised(x: torch.Tensor, params: Jpeg8Params) -> torch.Tensor:
+    """std_quantization output (noise_layers/jpeg.py:52-82) as [B,3,Hp,Wp]. No autograd."""
+    x, sb, sc, sh = _image(x.detach(), "jpeg8_quantised")
+    b, c, h, w = x.shape
+    hp, wp = (h + 7) // 8 * 8, (w + 7) // 8 * 8
+    coef = torch.empty((b, 3, hp, wp), device=x.device, dtype=torch.float32)
+    _lib.call("wm_jpeg8_quantised", x.data_ptr(), sb, sc, sh, coef.data_ptr(), b, h, w, C.byref(params), _stream())
+    return coef
+
+
+# --------------------------------------------------------------------------------------
+# Gaussian blur / median
+# --------------------------------------------------------------------------------------
+
+def _taps_array(taps: Sequence[float]):
+    arr = (C.c_float * len(taps))(*[float(t) for t in taps])
+    return arr
+
+
+class _BlurFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, taps, border):
+        x, sp, sh = _planes(x, "gaussian blur")
+        b, c, h, w = x.shape
+        y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+        arr = _taps_array(taps)
+        _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, y.data_ptr(), b * c, h, w, arr, len(taps), border, 0, _stream())
+        ctx.meta = (tuple(taps), border)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        taps, border = ctx.meta
+        gy, sp, sh = _planes(gy, "gaussian blur backward")
+        b, c, h, w = gy.shape
+        gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
+        _lib.call("wm_gaussblur", gy.data_ptr(), sp, sh, gx.data_ptr(), b * c, h, w, _taps_array(taps), len(taps),
+                  border, 1, _stream())
+        return gx, None, None
+
+
+def gaussian_blur(x: torch.Tensor, taps: Sequence[float], border: int = 0) -> torch.Tensor:
+    """Separable blur with normalised 1-D `taps`; border 0 = zero pad, 1 = reflect."""
+    return _BlurFn.apply(x, tuple(float(t) for t in taps), border)
+
+
+class _MedianFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        need_idx = bool(ctx.needs_input_grad[0])
+        x, sp, sh = _planes(x, "median blur")
+        b, c, h, w = x.shape
+        y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+        idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8) if need_idx else None
+        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), b * c, h, w, k, _stream())
+        ctx.k = k
+        if need_idx:
+            ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        gy = _flat(gy, "median blur backward")
+        b, c, h, w = gy.shape
+        gx = torch.empty_like(gy)
+        _lib.call("wm_median_bwd", gy.data_ptr(), idx.data_ptr(), gx.data_ptr(), b * c, h, w, ctx.k, _stream())
+        return gx, None
+
+
+def median_blur(x: torch.Tensor, k: int) -> torch.Tensor:
+    if k not in (3, 5):
+        raise ValueError(f"median_blur supports kernel sizes 3 and 5, got {k}")
+    return _MedianFn.apply(x, k)
+
+
+def median_blur_with_index(x: torch.Tensor, k: int):
+    """(values, uint8 arg-median index plane) — test/inspection helper, no autograd."""
+    x, sp, sh = _planes(x.detach(), "median blur")
+    b, c, h, w = x.shape
+    y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8)
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), idx.data_ptr(), b * c, h, w, k, _stream())
+    return y, idx
+
+
+# --------------------------------------------------------------------------------------
+# Elementwise attacks
+# --------------------------------------------------------------------------------------
+
+class _GaussNoiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, std, clamp, noise, seed, offset):
+        x = _flat(x, "gaussian noise")
+        inj = _flat(noise, "gaussian noise (injected)") if noise is not None else None
+        if inj is not None and inj.shape != x.shape:
+            raise ValueError("injected noise must have the input's shape")
+        y = torch.empty_like(x)
+        _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, offset,
+                  _ptr(inj), _stream())
+        ctx.meta = (mean, std, int(clamp), seed, offset)
+        if clamp:
+            ctx.save_for_backward(x, inj if inj is not None else torch.empty(0, device=x.device))
+        ctx.has_inj = inj is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        mean, std, clamp, seed, offset = ctx.meta
+        gy = _flat(gy, "gaussian noise backward")
+        if not clamp:
+            return gy, None, None, None, None, None, None
+        x, inj = ctx.saved_tensors
+        gx = torch.empty_like(gy)
+        _lib.call("wm_gaussnoise_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), gy.numel(), mean, std, clamp,
+                  seed, offset, inj.data_ptr() if ctx.has_inj else None, _stream())
+        return gx, None, None, None, None, None, None
+
+
+def gaussian_noise(x, mean: float = 0.0, std: float = 0.05, clamp: bool = True, noise=None):
+    seed, offset = next_philox_stream(x.numel()) if noise is None else (0, 0)
+    return _GaussNoiseFn.apply(x, float(mean), float(std), clamp, noise, seed, offset)
+
+
+class _SaltPepperFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, prob, rdn, seed, offset):
+        x = _flat(x, "salt & pepper")
+        inj = _flat(rdn, "salt & pepper (injected)") if rdn is not None else None
+        y = torch.empty_like(x)
+        _lib.call("wm_saltpepper_fwd", x.data_ptr(), y.data_ptr(), x.numel(), prob, seed, offset, _ptr(inj), _stream())
+        ctx.meta = (prob, seed, offset)
+        ctx.inj = inj
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        prob, seed, offset = ctx.meta
+        gy = _flat(gy, "salt & pepper backward")
+        gx = torch.empty_like(gy)
+        _lib.call("wm_saltpepper_bwd", gy.data_ptr(), gx.data_ptr(), gy.numel(), prob, seed, offset, _ptr(ctx.inj), _stream())
+        return gx, None, None, None, None
+
+
+def salt_pepper(x, prob: float, rdn=None):
+    seed, offset = next_philox_stream(x.numel()) if rdn is None else (0, 0)
+    return _SaltPepperFn.apply(x, float(prob), rdn, seed, offset)
+
+
+class _DropoutElemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, cover, prob, rdn, seed, offset):
+        image = _flat(image, "dropout")
+        cover = _flat(cover, "dropout")
+        if image.shape != cover.shape:
+            raise ValueError("image and cover must have the same shape")
+        inj = _flat(rdn, "dropout (injected)") if rdn is not None else None
+        y = torch.empty_like(image)
+        _lib.call("wm_dropout_elem_fwd", image.data_ptr(), cover.data_ptr(), y.data_ptr(), image.numel(), prob,
+                  seed, offset, _ptr(inj), _stream())
+        ctx.meta = (prob, seed, offset)
+        ctx.inj = inj
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        prob, seed, offset = ctx.meta
+        gy = _flat(gy, "dropout backward")
+        gi = torch.empty_like(gy) if ctx.needs_input_grad[0] else None
+        gc = torch.empty_like(gy) if ctx.needs_input_grad[1] else None
+        if gi is not None or gc is not None:
+            _lib.call("wm_dropout_elem_bwd", gy.data_ptr(), _ptr(gi), _ptr(gc), gy.numel(), prob, seed, offset,
+                      _ptr(ctx.inj), _stream())
+        return gi, gc, None, None, None, None
+
+
+def dropout_elementwise(image, cover, prob: float, rdn=None):
+    seed, offset = next_philox_stream(image.numel()) if rdn is None else (0, 0)
+    return _DropoutElemFn.apply(image, cover, float(prob), rdn, seed, offset)
+
+
+class _DropoutMaskFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, noised, cover, mask_hw):
+        noised = _flat(noised, "dropout")
+        cover = _flat(cover, "dropout")
+        mask_hw = _flat(mask_hw, "dropout mask")
+        b, c, h, w = noised.shape
+        if mask_hw.numel() != h * w or cover.shape != noised.shape:
+            raise ValueError("mask must be [H,W] and cover must match the noised image")
+        y = torch.empty_like(noised)
+        _lib.call("wm_dropout_mask_fwd", noised.data_ptr(), cover.data_ptr(), mask_hw.data_ptr(), y.data_ptr(),
+                  b * c, h * w, _stream())
+        ctx.save_for_backward(mask_hw)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (mask_hw,) = ctx.saved_tensors
+        gy = _flat(gy, "dropout backward")
+        b, c, h, w = gy.shape
+        gn = torch.empty_like(gy) if ctx.needs_input_grad[0] else None
+        gc = torch.empty_like(gy) if ctx.needs_input_grad[1] else None
+        if gn is not None or gc is not None:
+            _lib.call("wm_dropout_mask_bwd", gy.data_ptr(), mask_hw.data_ptr(), _ptr(gn), _ptr(gc), b * c, h * w, _stream())
+        return gn, gc, None
+
+
+def dropout_mask(noised, cover, mask_hw):
+    return _DropoutMaskFn.apply(noised, cover, mask_hw)
+
+
+def bernoulli_mask(h: int, w: int, keep: float, device) -> torch.Tensor:
+    m = torch.empty((h, w), device=device, dtype=torch.float32)
+    seed, offset = next_philox_stream(h * w)
+    _lib.call("wm_bernoulli_mask", m.data_ptr(), h * w, float(keep), seed, offset, _stream())
+    return m
+
+
+class _Quantize8Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, clamp01):
+        x = _flat(x, "quantization")
+        y = torch.empty_like(x)
+        _lib.call("wm_quantize8_fwd", x.data_ptr(), y.data_ptr(), x.numel(), int(clamp01), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy, None      # straight-through (models/modules/Quantization.py:13-14)
+
+
+def quantize8(x, clamp01: bool = False):
+    return _Quantize8Fn.apply(x, clamp01)
+
+
+class _CropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, cover, box):
+        image = _flat(image, "cropout")
+        cover = _flat(cover, "cropout")
+        b, c, h, w = image.shape
+        y = torch.empty_like(image)
+        _lib.call("wm_cropout_fwd", image.data_ptr(), cover.data_ptr(), y.data_ptr(), b * c, h, w, *[int(v) for v in box], _stream())
+        ctx.box = box
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = _flat(gy, "cropout backward")
+        b, c, h, w = gy.shape
+        z = torch.zeros_like(gy)
+        gi = torch.empty_like(gy)
+        gc = torch.empty_like(gy)
+        box = [int(v) for v in ctx.box]
+        _lib.call("wm_cropout_fwd", gy.data_ptr(), z.data_ptr(), gi.data_ptr(), b * c, h, w, *box, _stream())
+        _lib.call("wm_cropout_fwd", z.data_ptr(), gy.data_ptr(), gc.data_ptr(), b * c, h, w, *box, _stream())
+        return gi, gc, None
+
+
+def cropout(image, cover, box):
+    return _CropoutFn.apply(image, cover, tuple(box))
+
+
+# --------------------------------------------------------------------------------------
+# interpolation: Resize / Crop
+# --------------------------------------------------------------------------------------
+
+def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp):
+    h0, w0, hin, win = window
+    y = torch.empty((n, out_hw[0], out_hw[1]), device=x.device, dtype=torch.float32)
+    _lib.call("wm_interp_fwd", x.data_ptr(), sp, sh, h0, w0, hin, win, y.data_ptr(), n, out_hw[0], out_hw[1],
+              mode, int(clamp), _stream())
+    return y
+
+
+def _interp_bwd(gy, pre, n, out_hw, src_hw, window, mode):
+    h0, w0, hin, win = window
+    gx = torch.empty((n, src_hw[0], src_hw[1]), device=gy.device, dtype=torch.float32)
+    ws = torch.empty((n, hin, out_hw[1]), device=gy.device, dtype=torch.float32)
+    _lib.call("wm_interp_bwd", gy.data_ptr(), _ptr(pre), n, out_hw[0], out_hw[1], gx.data_ptr(), src_hw[0], src_hw[1],
+              h0, w0, hin, win, mode, ws.data_ptr(), _stream())
+    return gx
+
+
+class _InterpFn(torch.autograd.Function):
+    """y = interpolate(x[:, :, h0:h0+hin, w0:w0+win], size=out_hw) [clamped to 0..1]."""
+
+    @staticmethod
+    def forward(ctx, x, window, out_hw, mode, clamp):
+        x, sp, sh = _planes(x, "interpolate")
+        b, c, h, w = x.shape
+        n = b * c
+        y = _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp)
+        ctx.meta = (window, tuple(out_hw), mode, clamp, (b, c, h, w))
+        if clamp:
+            ctx.save_for_backward(x)
+        return y.view(b, c, out_hw[0], out_hw[1])
+
+    @staticmethod
+    def backward(ctx, gy):
+        window, out_hw, mode, clamp, (b, c, h, w) = ctx.meta
+        n = b * c
+        gy = _flat(gy, "interpolate backward")
+        pre = None
+        if clamp:
+            (x,) = ctx.saved_tensors
+            sp, sh = x.stride(1), x.stride(2)
+            pre = _interp_fwd(x, sp, sh, n, window, out_hw, mode, False)
+        gx = _interp_bwd(gy, pre, n, out_hw, (h, w), window, mode)
+        return gx.view(b, c, h, w), None, None, None, None
+
+
+def interpolate(x, size, mode: str = "bilinear", window=None, clamp: bool = False):
+    """F.interpolate(x[window], size=size, mode=mode, align_corners=False) on our kernels."""
+    h, w = x.shape[2:]
+    if window is None:
+        window = (0, 0, h, w)
+    return _InterpFn.apply(x, tuple(int(v) for v in window), (int(size[0]), int(size[1])), _MODES[mode], clamp)
+
+
+def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
+    """Resize.forward arithmetic (noise_layers/resize.py:38-53)."""
+    h, w = x.shape[2:]
+    mid = interpolate(x, mid_hw, mode)
+    return interpolate(mid, (h, w), mode, clamp=True)
