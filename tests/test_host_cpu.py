@@ -37,7 +37,7 @@ def test_library_exports_every_header_symbol(lib):
     assert {"wm_version", "wm_last_error", "wm_diffjpeg_fwd", "wm_diffjpeg_bwd"} <= names
     for n in names:
         assert hasattr(lib, n), f"libwmattack.so does not export {n}"
-    assert set(_lib.SIGNATURES) == names - {"wm_version", "wm_last_error"}
+    assert set(_lib.SIGNATURES) | set(_lib.HELPERS) == names - {"wm_version", "wm_last_error"}
     assert lib.wm_version() == 1
     assert isinstance(lib.wm_last_error(), bytes)
 
@@ -56,7 +56,8 @@ def test_invalid_arguments_fail_loudly_without_a_gpu(lib):
         taps = (_lib.f32 * 4)(0.25, 0.25, 0.25, 0.25)
         _lib.call("wm_gaussblur", 256, 64, 8, 256, 1, 8, 8, taps, 4, 0, 0, None)
     with pytest.raises(_lib.WMAttackError, match="mode"):
-        _lib.call("wm_interp_fwd", 256, 64, 8, 0, 0, 8, 8, 256, 1, 4, 4, 7, 0, None)
+        _lib.call("wm_interp_fwd", 256, 64, 8, 0, 0, 8, 8, 256, 1, 4, 4, 7, 0, None, None)
+    assert lib.wm_interp_is_tiled(512, 512, 256, 256, 192) == 1 and lib.wm_interp_is_tiled(512, 512, 64, 64, 3) == 0
 
 
 def test_no_cpu_fallback():

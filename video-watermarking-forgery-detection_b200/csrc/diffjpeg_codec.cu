@@ -12,44 +12,44 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_compress_kernel(const 
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
     const float f = a.factor_ps ? __ldg(a.factor_ps + t.b) : a.factor;
-    float cb[4][4], cr[4][4], dummy[4][4];
-    dj_load_block(a, t, scr, cb, cr);
-    dj_luma_columns<ROUND, true, false>(scr, nullptr, f);
+    dj_load_block<DJ_THREADS>(a, t, scr);
+    dj_luma_columns<ROUND, true, false, DJ_THREADS>(scr, f);
     QuadCoef qx, qy;
     quad_coef_init(qx, t.bx);
     quad_coef_init(qy, t.by);
-    dj_chroma_roundtrip<ROUND, true, false>(cb, dummy, qx, qy, t.bx, t.by, f);
-    dj_chroma_roundtrip<ROUND, true, false>(cr, dummy, qx, qy, t.bx, t.by, f);
+    dj_chroma_planes<ROUND, true, false, DJ_THREADS>(scr, qx, qy, t.bx, t.by, f);
     if (!t.active) return;
     // luminance block index (utils/JPEG.py:176-181): raster over (H/8, W/8)
     const int64_t yblk = (int64_t(t.b) * (a.H / 8) + t.row0 / 8) * (a.W / 8) + t.col0 / 8;
     float* py = a.coef_y + yblk * 64;
-#pragma unroll
+#pragma unroll 1
     for (int u = 0; u < 8; ++u) {
         float v[8];
-        scr_load_row(scr, u, v);
+        scr_load_row<DJ_THREADS>(scr, u, v);
         f8 o;
 #pragma unroll
         for (int c = 0; c < 8; ++c) o.v[c] = v[c];
         stg256(py + u * 8, o);
     }
     const int64_t cblk = (int64_t(t.b) * (a.H / 16) + t.mcu_y) * (a.W / 16) + t.mcu_x;
-    float* pb = a.coef_cb + cblk * 64;
-    float* pr = a.coef_cr + cblk * 64;
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        float* pc = (pl ? a.coef_cr : a.coef_cb) + cblk * 64;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            float v[4];
+            f4_to(v, scr[(SC_CB + 4 * pl + i) * DJ_THREADS]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = (2 * i + t.by) * 8 + 2 * j + t.bx;
-            pb[o] = cb[i][j];
-            pr[o] = cr[i][j];
+            for (int j = 0; j < 4; ++j) pc[(2 * i + t.by) * 8 + 2 * j + t.bx] = v[j];
         }
+    }
 }
 
 // =============================================================================================
 // decompress: coefficients -> image (utils/JPEG.py:452-469)
 // =============================================================================================
 __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_decompress_kernel(const DJArgs a) {
+    constexpr int NT = DJ_THREADS;
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_decompress_kernel(cons
     const int64_t yblk = (int64_t(t.b) * (a.H / 8) + t.row0 / 8) * (a.W / 8) + t.col0 / 8;
     const int64_t cblk = (int64_t(t.b) * (a.H / 16) + t.mcu_y) * (a.W / 16) + t.mcu_x;
     // luminance: dequantise, column IDCT per 4-column group via scratch, then row IDCT
-#pragma unroll
+#pragma unroll 1
     for (int u = 0; u < 8; ++u) {
         float v[8];
         if (t.active) {
@@ -68,62 +68,39 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_decompress_kernel(cons
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = 0.f;
         }
-        scr_store_row(scr, u, v);
+        scr_store_row<NT>(scr, u, v);
     }
-#pragma unroll
+#pragma unroll 1
     for (int cg = 0; cg < 2; ++cg) {
         float v[8][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float4 t4 = scr[(2 * r + cg) * DJ_THREADS];
-            v[r][0] = t4.x; v[r][1] = t4.y; v[r][2] = t4.z; v[r][3] = t4.w;
-        }
+        for (int r = 0; r < 8; ++r) f4_to(v[r], scr[(SC_Y + 2 * r + cg) * NT]);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             idct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            scr[(2 * r + cg) * DJ_THREADS] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        for (int r = 0; r < 8; ++r) scr[(SC_Y + 2 * r + cg) * NT] = to_f4(v[r]);
     }
-    float cb[4][4], cr[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = (2 * i + t.by) * 8 + 2 * j + t.bx;
-            const float tf = cTC[o] * f;
-            cb[i][j] = t.active ? a.coef_cb[cblk * 64 + o] * tf : 0.f;
-            cr[i][j] = t.active ? a.coef_cr[cblk * 64 + o] * tf : 0.f;
-        }
     QuadCoef qx, qy;
     quad_coef_init(qx, t.bx);
     quad_coef_init(qy, t.by);
-    quad_idct_cols(cb, qy, 16); quad_idct_rows(cb, qx, 1);
-    quad_idct_cols(cr, qy, 16); quad_idct_rows(cr, qx, 1);
-
-    float* yo = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
-    const int64_t plane = int64_t(a.H) * a.W;
-    float tR[4], tG[4], tB[4];
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        const float* pc = (pl ? a.coef_cr : a.coef_cb) + cblk * 64;
+        float p[4][4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float yv[8];
-        scr_load_row(scr, r, yv);
-        idct8(yv);
-        if ((r & 1) == 0) dj_chroma_terms(cb[r >> 1], cr[r >> 1], tR, tG, tB);
-        f8 oR, oG, oB;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            oR.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tR[c >> 1]));
-            oG.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tG[c >> 1]));
-            oB.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tB[c >> 1]));
-        }
-        if (t.active) {
-            float* p = yo + int64_t(r) * a.W;
-            stg256(p, oR);
-            stg256(p + plane, oG);
-            stg256(p + 2 * plane, oB);
-        }
+            for (int j = 0; j < 4; ++j) {
+                const int o = (2 * i + t.by) * 8 + 2 * j + t.bx;
+                p[i][j] = t.active ? __ldg(pc + o) * (cTC[o] * f) : 0.f;
+            }
+        quad_idct_cols(p, qy, 16);
+        quad_idct_rows(p, qx, 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) scr[(SC_CB + 4 * pl + i) * NT] = to_f4(p[i]);
     }
+    dj_emit_rgb<NT>(a, t, scr);
 }
 
 }  // namespace wm
@@ -139,8 +116,8 @@ extern "C" int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, 
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
     a.coef_y = coef_y; a.coef_cb = coef_cb; a.coef_cr = coef_cr;
-    const size_t smem = 16 * DJ_THREADS * sizeof(float4);
-    DJ_DISPATCH_ROUND(diffjpeg_compress_kernel, a, smem, (cudaStream_t)stream, "wm_diffjpeg_compress")
+    const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
+    DJ_DISPATCH_ROUND(diffjpeg_compress_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_compress")
 }
 
 extern "C" int wm_diffjpeg_decompress(const float* coef_y, const float* coef_cb, const float* coef_cr,
@@ -153,6 +130,6 @@ extern "C" int wm_diffjpeg_decompress(const float* coef_y, const float* coef_cb,
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
     a.coef_y = const_cast<float*>(coef_y); a.coef_cb = const_cast<float*>(coef_cb);
     a.coef_cr = const_cast<float*>(coef_cr); a.out = y;
-    const size_t smem = 16 * DJ_THREADS * sizeof(float4);
-    return dj_launch(diffjpeg_decompress_kernel, a, smem, (cudaStream_t)stream, "wm_diffjpeg_decompress");
+    const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
+    return dj_launch(diffjpeg_decompress_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_decompress");
 }

@@ -15,7 +15,10 @@
 //   * the 2-D DCT of the luminance block streams through a thread-private shared-memory
 //     scratch (row pass in registers as rows arrive -> scratch -> 4-column groups -> scratch
 //     -> row pass as rows leave), which keeps the register footprint at ~100 instead of the
-//     192 a register-resident RGB block would need;
+//     192 a register-resident RGB block would need; the chroma quadrants park there too, so
+//     every phase is a ROLLED loop over row pairs / column groups / planes: the whole kernel
+//     stays inside the instruction cache (the first, fully unrolled version was 150 KB of SASS
+//     and spent half its cycles on instruction fetch — profiles/ncu_r1_diffjpeg_unrolled.txt);
 //   * the chroma block uses the divergence-free 4-lane split transform of dct8.cuh
 //     (__shfl_xor with lane^1 / lane^16).
 #pragma once
@@ -46,7 +49,17 @@ static __constant__ float cTC[64] = {
     99, 99, 99, 99, 99, 99, 99, 99,
     99, 99, 99, 99, 99, 99, 99, 99};
 
-constexpr int DJ_THREADS = 128;
+constexpr int DJ_THREADS = 128;    // forward / compress / decompress CTA
+constexpr int DJB_THREADS = 96;    // backward CTA (48 scratch chunks per thread -> 3 CTAs per SM)
+
+// Thread-private scratch layout, in float4 chunks (chunk c of thread t at [c * NT + t], so
+// consecutive lanes touch consecutive 16-byte words: conflict-free LDS.128 / STS.128):
+constexpr int SC_Y = 0;      // 16 chunks: luminance block, row r = chunks 2r, 2r+1
+constexpr int SC_CB = 16;    //  4 chunks: Cb quadrant rows   (backward: later the Cb cotangent)
+constexpr int SC_CR = 20;    //  4 chunks: Cr quadrant rows
+constexpr int SC_DY = 24;    // 16 chunks: round'(q) of the luminance block      (backward only)
+constexpr int SC_DC = 40;    //  8 chunks: round'(q) of the Cb, Cr quadrants     (backward only)
+constexpr int SC_FWD_CHUNKS = 24, SC_BWD_CHUNKS = 48;
 
 // ---- rounding surrogates (utils/JPEG.py:472-484, utils/JPEG_utils.py:36-41) -----------------
 template <int MODE>
@@ -112,78 +125,101 @@ __device__ __forceinline__ DJThread dj_locate(const DJArgs& a) {
     return t;
 }
 
-// scratch: 16 float4 chunks per thread, chunk c of thread t at [c * DJ_THREADS + t]
-// (consecutive lanes -> consecutive 16-byte words: conflict-free LDS.128/STS.128)
-__device__ __forceinline__ void scr_store_row(float4* scr, int r, const float (&v)[8]) {
-    scr[(2 * r) * DJ_THREADS] = make_float4(v[0], v[1], v[2], v[3]);
-    scr[(2 * r + 1) * DJ_THREADS] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void scr_load_row(const float4* scr, int r, float (&v)[8]) {
-    float4 a = scr[(2 * r) * DJ_THREADS], b = scr[(2 * r + 1) * DJ_THREADS];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// Phase 1: stream the RGB rows of the thread's 8x8 block: luminance rows are level-shifted,
-// row-transformed and parked in scratch; chroma is reduced to the 4x4 quadrant (2x2 mean).
-__device__ __forceinline__ void dj_load_block(const DJArgs& a, const DJThread& t, float4* scr,
-                                              float (&cb)[4][4], float (&cr)[4][4]) {
-    const float* xr = a.x + int64_t(t.b) * a.x_sb + int64_t(t.row0) * a.x_sh + t.col0;
+template <int NT>
+__device__ __forceinline__ void scr_store_row(float4* scr, int r, const float (&v)[8]) {
+    scr[(SC_Y + 2 * r) * NT] = make_float4(v[0], v[1], v[2], v[3]);
+    scr[(SC_Y + 2 * r + 1) * NT] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <int NT>
+__device__ __forceinline__ void scr_load_row(const float4* scr, int r, float (&v)[8]) {
+    const float4 a = scr[(SC_Y + 2 * r) * NT], b = scr[(SC_Y + 2 * r + 1) * NT];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void f4_to(float (&v)[4], const float4 a) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+__device__ __forceinline__ float4 to_f4(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+
+struct RowPair { f8 R[2], G[2], B[2]; };
+
+__device__ __forceinline__ void dj_load_pair(RowPair& p, const float* xr, int64_t sh, int64_t sc, bool active) {
 #pragma unroll
-    for (int rp = 0; rp < 4; ++rp) {
-        f8 R[2], G[2], Bl[2];
+    for (int rr = 0; rr < 2; ++rr) {
+        const float* q = xr + int64_t(rr) * sh;
+        if (active) {
+            p.R[rr] = ldg256_stream(q);
+            p.G[rr] = ldg256_stream(q + sc);
+            p.B[rr] = ldg256_stream(q + 2 * sc);
+        } else {
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const float* p = xr + int64_t(2 * rp + rr) * a.x_sh;
-            if (t.active) {
-                R[rr] = ldg256_stream(p);
-                G[rr] = ldg256_stream(p + a.x_sc);
-                Bl[rr] = ldg256_stream(p + 2 * a.x_sc);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) R[rr].v[c] = G[rr].v[c] = Bl[rr].v[c] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            float yv[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                yv[c] = fmaf(R[rr].v[c], DJ_YR, fmaf(G[rr].v[c], DJ_YG, fmaf(Bl[rr].v[c], DJ_YB, -128.f)));
-            dct8(yv);
-            scr_store_row(scr, 2 * rp + rr, yv);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float sr = (R[0].v[2 * j] + R[0].v[2 * j + 1]) + (R[1].v[2 * j] + R[1].v[2 * j + 1]);
-            const float sg = (G[0].v[2 * j] + G[0].v[2 * j + 1]) + (G[1].v[2 * j] + G[1].v[2 * j + 1]);
-            const float sb = (Bl[0].v[2 * j] + Bl[0].v[2 * j + 1]) + (Bl[1].v[2 * j] + Bl[1].v[2 * j + 1]);
-            cb[rp][j] = fmaf(sr, DJ_CBR, fmaf(sg, DJ_CBG, sb * DJ_CBB));   // (Cb + 128) - 128
-            cr[rp][j] = fmaf(sr, DJ_CRR, fmaf(sg, DJ_CRG, sb * DJ_CRB));
+            for (int c = 0; c < 8; ++c) p.R[rr].v[c] = p.G[rr].v[c] = p.B[rr].v[c] = 0.f;
         }
     }
 }
 
-// Phase 2: luminance column stage on 4-column groups.
+// luminance rows are level-shifted, row-transformed and parked; chroma is 2x2-averaged
+template <int NT>
+__device__ __forceinline__ void dj_consume_pair(const RowPair& p, int rp, float4* scr) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        float yv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            yv[c] = fmaf(p.R[rr].v[c], DJ_YR, fmaf(p.G[rr].v[c], DJ_YG, fmaf(p.B[rr].v[c], DJ_YB, -128.f)));
+        dct8(yv);
+        scr_store_row<NT>(scr, 2 * rp + rr, yv);
+    }
+    float cb[4], cr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float sr = (p.R[0].v[2 * j] + p.R[0].v[2 * j + 1]) + (p.R[1].v[2 * j] + p.R[1].v[2 * j + 1]);
+        const float sg = (p.G[0].v[2 * j] + p.G[0].v[2 * j + 1]) + (p.G[1].v[2 * j] + p.G[1].v[2 * j + 1]);
+        const float sb = (p.B[0].v[2 * j] + p.B[0].v[2 * j + 1]) + (p.B[1].v[2 * j] + p.B[1].v[2 * j + 1]);
+        cb[j] = fmaf(sr, DJ_CBR, fmaf(sg, DJ_CBG, sb * DJ_CBB));   // (Cb + 128) - 128
+        cr[j] = fmaf(sr, DJ_CRR, fmaf(sg, DJ_CRG, sb * DJ_CRB));
+    }
+    scr[(SC_CB + rp) * NT] = to_f4(cb);
+    scr[(SC_CR + rp) * NT] = to_f4(cr);
+}
+
+// Phase 1: stream the 8 RGB rows of the thread's block, two rows at a time, always one pair
+// of loads (6 x LDG.E.256) in flight ahead of the arithmetic.  Rolled (2 iterations) to keep
+// the kernel inside the instruction cache.
+template <int NT>
+__device__ __forceinline__ void dj_load_block(const DJArgs& a, const DJThread& t, float4* scr) {
+    const float* xr = a.x + int64_t(t.b) * a.x_sb + int64_t(t.row0) * a.x_sh + t.col0;
+    RowPair A, B;
+    dj_load_pair(A, xr, a.x_sh, a.x_sc, t.active);
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        dj_load_pair(B, xr + int64_t(4 * it + 2) * a.x_sh, a.x_sh, a.x_sc, t.active);
+        dj_consume_pair<NT>(A, 2 * it, scr);
+        if (it == 0) dj_load_pair(A, xr + int64_t(4) * a.x_sh, a.x_sh, a.x_sc, t.active);
+        dj_consume_pair<NT>(B, 2 * it + 1, scr);
+    }
+}
+
+// Phase 2: luminance column stage on 4-column groups (rolled over the two groups).
 //   KEEP_Q : write the rounded quantised coefficient back (compress) instead of the
 //            dequantised, column-inverse-transformed value (forward / backward recompute)
-//   GRAD   : also park d round / dq in scratch region `dscr`
-template <int ROUND, bool KEEP_Q, bool GRAD>
-__device__ __forceinline__ void dj_luma_columns(float4* scr, float4* dscr, float f) {
-#pragma unroll
+//   GRAD   : also park d round / dq in the SC_DY chunks
+template <int ROUND, bool KEEP_Q, bool GRAD, int NT>
+__device__ __forceinline__ void dj_luma_columns(float4* scr, float f) {
+#pragma unroll 1
     for (int cg = 0; cg < 2; ++cg) {
         float v[8][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float4 t4 = scr[(2 * r + cg) * DJ_THREADS];
-            v[r][0] = t4.x; v[r][1] = t4.y; v[r][2] = t4.z; v[r][3] = t4.w;
-        }
+        for (int r = 0; r < 8; ++r) f4_to(v[r], scr[(SC_Y + 2 * r + cg) * NT]);
         float d[8][4];
+        const float* tab = cTY + 4 * cg;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const float tf = cTY[u * 8 + 4 * cg + j] * f;
+                const float tf = tab[u * 8 + j] * f;
                 const float q = div_by_recip(v[u][j], tf, fast_rcp(tf));
                 if (GRAD) d[u][j] = round_grad<ROUND>(q);
                 const float rq = round_fwd<ROUND>(q);
@@ -194,32 +230,43 @@ __device__ __forceinline__ void dj_luma_columns(float4* scr, float4* dscr, float
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            scr[(2 * r + cg) * DJ_THREADS] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-            if (GRAD) dscr[(2 * r + cg) * DJ_THREADS] = make_float4(d[r][0], d[r][1], d[r][2], d[r][3]);
+            scr[(SC_Y + 2 * r + cg) * NT] = to_f4(v[r]);
+            if (GRAD) scr[(SC_DY + 2 * r + cg) * NT] = to_f4(d[r]);
         }
     }
 }
 
-// Phase 3: chroma quadrant -> split DCT -> quantise/round/dequantise -> split IDCT.
-template <int ROUND, bool KEEP_Q, bool GRAD>
-__device__ __forceinline__ void dj_chroma_roundtrip(float (&p)[4][4], float (&d)[4][4],
-                                                    const QuadCoef& qx, const QuadCoef& qy,
-                                                    int bx, int by, float f) {
-    quad_dct_rows(p, qx, 1);
-    quad_dct_cols(p, qy, 16);
+// Phase 3: chroma quadrants (rolled over the two planes): split DCT -> quantise / round /
+// dequantise -> split IDCT, in place in the SC_CB / SC_CR chunks.
+template <int ROUND, bool KEEP_Q, bool GRAD, int NT>
+__device__ __forceinline__ void dj_chroma_planes(float4* scr, const QuadCoef& qx, const QuadCoef& qy,
+                                                 int bx, int by, float f) {
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        float p[4][4], d[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) f4_to(p[i], scr[(SC_CB + 4 * pl + i) * NT]);
+        quad_dct_rows(p, qx, 1);
+        quad_dct_cols(p, qy, 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float tf = cTC[(16 * i + 2 * j) + (8 * by + bx)] * f;   // [u=2i+by][v=2j+bx]
-            const float q = div_by_recip(p[i][j], tf, fast_rcp(tf));
-            if (GRAD) d[i][j] = round_grad<ROUND>(q);
-            const float rq = round_fwd<ROUND>(q);
-            p[i][j] = KEEP_Q ? rq : rq * tf;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float tf = cTC[(16 * i + 2 * j) + (8 * by + bx)] * f;   // [u=2i+by][v=2j+bx]
+                const float q = div_by_recip(p[i][j], tf, fast_rcp(tf));
+                if (GRAD) d[i][j] = round_grad<ROUND>(q);
+                const float rq = round_fwd<ROUND>(q);
+                p[i][j] = KEEP_Q ? rq : rq * tf;
+            }
+        if (!KEEP_Q) {
+            quad_idct_cols(p, qy, 16);
+            quad_idct_rows(p, qx, 1);
         }
-    if (!KEEP_Q) {
-        quad_idct_cols(p, qy, 16);
-        quad_idct_rows(p, qx, 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            scr[(SC_CB + 4 * pl + i) * NT] = to_f4(p[i]);
+            if (GRAD) scr[(SC_DC + 4 * pl + i) * NT] = to_f4(d[i]);
+        }
     }
 }
 
@@ -231,6 +278,41 @@ __device__ __forceinline__ void dj_chroma_terms(const float (&cb)[4], const floa
         tR[j] = fmaf(cr[j], 1.402f * DJ_I255, 128.f * DJ_I255);
         tG[j] = fmaf(cb[j], -0.344136f * DJ_I255, fmaf(cr[j], -0.714136f * DJ_I255, 128.f * DJ_I255));
         tB[j] = fmaf(cb[j], 1.772f * DJ_I255, 128.f * DJ_I255);
+    }
+}
+
+// Final phase of forward / decompress: row IDCT, upsampled chroma, colour transform, clamp.
+template <int NT>
+__device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, const float4* scr) {
+    float* yo = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
+    const int64_t plane = int64_t(a.H) * a.W;
+#pragma unroll 1
+    for (int rp = 0; rp < 4; ++rp) {
+        float cb[4], cr[4], tR[4], tG[4], tB[4];
+        f4_to(cb, scr[(SC_CB + rp) * NT]);
+        f4_to(cr, scr[(SC_CR + rp) * NT]);
+        dj_chroma_terms(cb, cr, tR, tG, tB);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * rp + rr;
+            float yv[8];
+            scr_load_row<NT>(scr, r, yv);
+            idct8(yv);
+            f8 oR, oG, oB;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                // min(255, max(0, v)) / 255  (utils/JPEG.py:467-469) == saturate(v / 255)
+                oR.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tR[c >> 1]));
+                oG.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tG[c >> 1]));
+                oB.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tB[c >> 1]));
+            }
+            if (t.active) {
+                float* p = yo + int64_t(r) * a.W;
+                stg256(p, oR);
+                stg256(p + plane, oG);
+                stg256(p + 2 * plane, oB);
+            }
+        }
     }
 }
 
@@ -256,13 +338,13 @@ static inline DJArgs dj_args(int B, int H, int W, float factor, const float* ps)
 }
 
 template <typename K>
-static inline int dj_launch(K kernel, const DJArgs& a, size_t smem, cudaStream_t st, const char* who) {
+static inline int dj_launch(K kernel, const DJArgs& a, int threads, size_t smem, cudaStream_t st, const char* who) {
     if (a.n_mcu == 0) return WM_OK;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
     const int64_t warps = (a.n_mcu + 7) / 8;
-    const int64_t blocks = (warps * 32 + DJ_THREADS - 1) / DJ_THREADS;
-    kernel<<<(unsigned)blocks, DJ_THREADS, smem, st>>>(a);
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    kernel<<<(unsigned)blocks, threads, smem, st>>>(a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
 }

@@ -50,13 +50,14 @@ SIGNATURES = {
     "wm_bernoulli_mask": [c_f32p, i64, f32, u64, u64, vp],
     "wm_quantize8_fwd": [c_f32p, c_f32p, i64, i32, vp],
     "wm_cropout_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, i32, i32, vp],
-    "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp],
-    "wm_interp_bwd": [c_f32p, c_f32p, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
+    "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
+    "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
 }
 
 # kernels launched by one successful call (wm_interp_bwd runs its two gather passes)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
-KERNELS_PER_CALL["wm_interp_bwd"] = 2
+# plain (non-status) helpers: name -> (restype, argtypes)
+HELPERS = {"wm_interp_is_tiled": (C.c_int, [i32, i32, i32, i32, i32])}
 
 _lock = threading.Lock()
 _lib = None
@@ -88,6 +89,10 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)          # AttributeError if the library is stale
             fn.argtypes = argtypes
             fn.restype = C.c_int
+        for name, (restype, argtypes) in HELPERS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
         _lib = lib
     return _lib
 

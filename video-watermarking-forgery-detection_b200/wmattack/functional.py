@@ -514,48 +514,50 @@ def cropout(image, cover, box):
 # interpolation: Resize / Crop
 # --------------------------------------------------------------------------------------
 
-def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp):
+def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp, want_mask=False):
     h0, w0, hin, win = window
     y = torch.empty((n, out_hw[0], out_hw[1]), device=x.device, dtype=torch.float32)
+    mask = None
+    if want_mask:
+        mask = torch.empty((n, out_hw[0], (out_hw[1] + 31) // 32), device=x.device, dtype=torch.int32)
     _lib.call("wm_interp_fwd", x.data_ptr(), sp, sh, h0, w0, hin, win, y.data_ptr(), n, out_hw[0], out_hw[1],
-              mode, int(clamp), _stream())
-    return y
+              mode, int(clamp), _ptr(mask), _stream())
+    return y, mask
 
 
-def _interp_bwd(gy, pre, n, out_hw, src_hw, window, mode):
+def _interp_bwd(gy, mask, n, out_hw, src_hw, window, mode):
     h0, w0, hin, win = window
     gx = torch.empty((n, src_hw[0], src_hw[1]), device=gy.device, dtype=torch.float32)
-    ws = torch.empty((n, hin, out_hw[1]), device=gy.device, dtype=torch.float32)
-    _lib.call("wm_interp_bwd", gy.data_ptr(), _ptr(pre), n, out_hw[0], out_hw[1], gx.data_ptr(), src_hw[0], src_hw[1],
-              h0, w0, hin, win, mode, ws.data_ptr(), _stream())
+    ws = None
+    if not _lib.load().wm_interp_is_tiled(hin, win, out_hw[0], out_hw[1], n):
+        ws = torch.empty((n, hin, out_hw[1]), device=gy.device, dtype=torch.float32)
+    _lib.call("wm_interp_bwd", gy.data_ptr(), None, _ptr(mask), n, out_hw[0], out_hw[1], gx.data_ptr(),
+              src_hw[0], src_hw[1], h0, w0, hin, win, mode, _ptr(ws), _stream())
     return gx
 
 
 class _InterpFn(torch.autograd.Function):
-    """y = interpolate(x[:, :, h0:h0+hin, w0:w0+win], size=out_hw) [clamped to 0..1]."""
+    """y = interpolate(x[:, :, h0:h0+hin, w0:w0+win], size=out_hw) [clamped to 0..1].
+    Linear apart from the clamp, whose pass-through mask is saved as 1 bit per value."""
 
     @staticmethod
     def forward(ctx, x, window, out_hw, mode, clamp):
+        need_grad = bool(ctx.needs_input_grad[0])
         x, sp, sh = _planes(x, "interpolate")
         b, c, h, w = x.shape
         n = b * c
-        y = _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp)
-        ctx.meta = (window, tuple(out_hw), mode, clamp, (b, c, h, w))
-        if clamp:
-            ctx.save_for_backward(x)
+        y, mask = _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp, want_mask=clamp and need_grad)
+        ctx.meta = (window, tuple(out_hw), mode, (b, c, h, w))
+        ctx.save_for_backward(mask if mask is not None else torch.empty(0, device=x.device))
+        ctx.has_mask = mask is not None
         return y.view(b, c, out_hw[0], out_hw[1])
 
     @staticmethod
     def backward(ctx, gy):
-        window, out_hw, mode, clamp, (b, c, h, w) = ctx.meta
-        n = b * c
+        window, out_hw, mode, (b, c, h, w) = ctx.meta
+        (mask,) = ctx.saved_tensors
         gy = _flat(gy, "interpolate backward")
-        pre = None
-        if clamp:
-            (x,) = ctx.saved_tensors
-            sp, sh = x.stride(1), x.stride(2)
-            pre = _interp_fwd(x, sp, sh, n, window, out_hw, mode, False)
-        gx = _interp_bwd(gy, pre, n, out_hw, (h, w), window, mode)
+        gx = _interp_bwd(gy, mask if ctx.has_mask else None, b * c, out_hw, (h, w), window, mode)
         return gx.view(b, c, h, w), None, None, None, None
 
 
