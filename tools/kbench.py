@@ -1,0 +1,126 @@
+"""Per-kernel device timing + quick torch-on-GPU cross-check (developer tool, GPU box only).
+
+    python tools/kbench.py [blur] [median] [resize] [diffjpeg] [jpeg8] [noise] [--shape B H W]
+
+Prints, per kernel: us/launch, algorithmic GB/s, fraction of the measured HBM peak, max-abs error
+against a plain torch implementation on the same device (NOT the parity gate — that is tests/).
+"""
+import json, os, sys
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "video-watermarking-forgery-detection_b200"))
+sys.path.insert(0, ROOT)
+import wmattack
+from wmattack import functional as WF
+
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+args = [a for a in sys.argv[1:]]
+shape = (64, 512, 512)
+if "--shape" in args:
+    i = args.index("--shape")
+    shape = tuple(int(v) for v in args[i + 1:i + 4])
+    del args[i:i + 4]
+which = set(args) or {"blur", "median", "resize", "diffjpeg", "jpeg8", "noise"}
+B, H, W = shape
+dev = "cuda"
+torch.manual_seed(0)
+x = torch.rand(B, 3, H, W, device=dev)
+g = torch.rand(B, 3, H, W, device=dev)
+px = B * H * W
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def report(name, us, bpp, err=None):
+    gbs = px * bpp / us / 1e3
+    e = "" if err is None else f"  err={err:.2e}"
+    print(f"{name:28s} {us:9.1f} us  {gbs:8.0f} GB/s  {gbs / PEAK * 100:5.1f}% of measured peak{e}", flush=True)
+
+
+def fwd_bwd(name, f, bpp_f, bpp_b, ref=None):
+    xx = x.clone().requires_grad_(True)
+    y = f(xx)
+    err = None
+    if ref is not None:
+        err = float((y.detach() - ref(x)).abs().max())
+    report(name + ".fwd(nograd)", timeit(lambda: f(x)), bpp_f, err)
+    report(name + ".fwd", timeit(lambda: f(xx)), bpp_f)
+    y = f(xx)
+    errb = None
+    if ref is not None:
+        xr = x.clone().requires_grad_(True)
+        ref(xr).backward(g)
+        y.backward(g, retain_graph=True)
+        errb = float((xx.grad - xr.grad).abs().max())
+        xx.grad = None
+
+    def step():
+        xx.grad = None
+        y.backward(g, retain_graph=True)
+    report(name + ".bwd", timeit(step), bpp_b, errb)
+
+
+def taps(k, sigma=2.0):
+    t = torch.arange(k, dtype=torch.float64) - (k - 1) / 2
+    w = torch.exp(-t * t / (2 * sigma * sigma))
+    return (w / w.sum()).tolist()
+
+
+if "blur" in which:
+    for k in (3, 5, 7):
+        tp = taps(k)
+        w2 = torch.tensor(tp, device=dev, dtype=torch.float32)
+        w2 = (w2[:, None] * w2[None, :]).expand(3, 1, k, k).contiguous()
+        fwd_bwd(f"gaussblur k{k}", lambda t: WF.gaussian_blur(t, tp, 0), 24, 24,
+                lambda t: F.conv2d(t, w2, padding=k // 2, groups=3))
+
+if "median" in which:
+    def med_ref(k):
+        def f(t):
+            b, c, h, w = t.shape
+            u = F.unfold(t.reshape(b * c, 1, h, w), k, padding=k // 2).view(b, c, k * k, h, w)
+            return u.median(dim=2)[0]
+        return f
+    for k in (3, 5):
+        small = B * H * W <= 8 * 512 * 512
+        fwd_bwd(f"median k{k}", lambda t: WF.median_blur(t, k), 27, 27, med_ref(k) if small else None)
+
+if "resize" in which:
+    for r in (0.5, 0.75, 1.25, 1.5):
+        mid = (int(r * H), int(r * W))
+        def ref(t, mid=mid):
+            m = F.interpolate(t, size=mid, mode="bicubic")
+            return torch.clamp(F.interpolate(m, size=(H, W), mode="bicubic"), 0, 1)
+        fwd_bwd(f"resize r{r}", lambda t, mid=mid: WF.resize_roundtrip(t, mid, "bicubic"), 24, 36, ref)
+
+if "diffjpeg" in which:
+    m = wmattack.DiffJPEG(True, H, W, quality=50)
+    fwd_bwd("diffjpeg q50", lambda t: m(t), 24, 36)
+
+if "jpeg8" in which:
+    for nm, mod, bb in (("jpegcompression", wmattack.JpegCompression(dev), 24), ("jpegss50", wmattack.JpegSS(50), 36),
+                        ("jpegmask50", wmattack.JpegMask(50), 24)):
+        fwd_bwd(nm, lambda t, mod=mod: mod(t), 24, bb)
+
+if "noise" in which:
+    gn = wmattack.Gaussian()
+    fwd_bwd("gaussian", lambda t: gn(t), 24, 36)
+    sp = wmattack.SaltPepper(0.01)
+    fwd_bwd("saltpepper", lambda t: sp(t), 24, 24)

@@ -9,6 +9,7 @@
 // Backward: the filter is symmetric, so with zero padding the adjoint is the same operator.
 // For the reflect border the adjoint folds the out-of-range part of the zero-extended
 // response back onto the interior (gather form, deterministic).
+#include "tma.cuh"
 #include "wm_common.cuh"
 
 namespace wm {
@@ -74,6 +75,129 @@ __global__ void __launch_bounds__(BL_THREADS) gaussblur_kernel(const BlurArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Zero-border fast path (k = 3, 5, 7; 16-byte aligned rows): persistent CTAs, a ring of
+// TMA-staged halo tiles (out-of-bounds box elements arrive as zeros == the zero padding), one
+// warp per 8-row strip, one lane per 4 adjacent columns.  A lane walks down its strip keeping
+// the last K horizontally filtered rows in registers; every output row costs one LDS.128 (+2R
+// scalar neighbours) and one coalesced STG.128 — x is read from HBM once, y written once.
+// ---------------------------------------------------------------------------------------------
+constexpr int BT_TW = 128, BT_TH = 64, BT_HALO = 4, BT_BW = BT_TW + 2 * BT_HALO, BT_THREADS = 256, BT_ROWS = 8;
+
+struct BlurTArgs {
+    float* y; int N, H, W, tiles_x, tiles_y; int64_t total;
+    float taps[8];
+};
+
+template <int K> constexpr int bt_stages() { return K <= 5 ? 3 : 2; }
+template <int K> constexpr int bt_stage_floats() { return ((BT_BW * (BT_TH + K - 1) + 31) / 32) * 32; }
+
+template <int K>
+__global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BlurTArgs a) {
+    constexpr int R = K / 2, BH = BT_TH + 2 * R, S = bt_stages<K>(), STRIDE = bt_stage_floats<K>();
+    extern __shared__ __align__(128) float bufs[];
+    __shared__ uint64_t full[S];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int per_plane = a.tiles_x * a.tiles_y;
+    auto issue = [&](int64_t t, int s) {
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        mbar_expect_tx(&full[s], BT_BW * BH * sizeof(float));
+        tma_load_3d(bufs + s * STRIDE, &tmap, tx * BT_TW - BT_HALO, ty * BT_TH - R, n, &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
+            if (t < a.total) issue(t, s);
+        }
+    }
+    float w[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) w[j] = a.taps[j];
+    const int cg = tid & 31, strip = tid >> 5;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
+        const int s = it % S;
+        mbar_wait(&full[s], (it / S) & 1);
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int gx = tx * BT_TW + 4 * cg, gy0 = ty * BT_TH + strip * BT_ROWS;
+        const float* col = bufs + s * STRIDE + (strip * BT_ROWS) * BT_BW + BT_HALO + 4 * cg;
+        auto hpass = [&](int row, float (&o)[4]) {
+            const float* p = col + row * BT_BW;
+            float win[4 + 2 * R];
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            win[R] = c.x; win[R + 1] = c.y; win[R + 2] = c.z; win[R + 3] = c.w;
+#pragma unroll
+            for (int i = 0; i < R; ++i) { win[R - 1 - i] = p[-1 - i]; win[R + 4 + i] = p[4 + i]; }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float acc = w[0] * win[c4];
+#pragma unroll
+                for (int j = 1; j < K; ++j) acc = fmaf(w[j], win[c4 + j], acc);
+                o[c4] = acc;
+            }
+        };
+        float h[K][4];
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) hpass(j, h[j]);
+        float* dst = a.y + (int64_t(n) * a.H + gy0) * a.W + gx;
+        const bool col_ok = gx < a.W;
+#pragma unroll
+        for (int r = 0; r < BT_ROWS; ++r) {
+            hpass(r + K - 1, h[(r + K - 1) % K]);
+            float4 o;
+            float* op = &o.x;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float acc = w[0] * h[r % K][c4];
+#pragma unroll
+                for (int j = 1; j < K; ++j) acc = fmaf(w[j], h[(r + j) % K][c4], acc);
+                op[c4] = acc;
+            }
+            if (col_ok && gy0 + r < a.H) stg128(dst + int64_t(r) * a.W, o);
+        }
+        __syncthreads();                      // every lane is done with stage s
+        if (tid == 0) {
+            const int64_t t2 = t + int64_t(S) * gridDim.x;
+            if (t2 < a.total) issue(t2, s);
+        }
+    }
+}
+
+template <int K>
+static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
+                           const float* taps_host, cudaStream_t st) {
+    constexpr int R = K / 2, S = bt_stages<K>();
+    CUtensorMap tm;
+    if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, BT_BW, BT_TH + 2 * R)) {
+        set_error("wm_gaussblur: cuTensorMapEncodeTiled failed (%d)", rc);
+        return WM_E_ARG;
+    }
+    BlurTArgs a{};
+    a.y = y; a.N = N; a.H = H; a.W = W;
+    a.tiles_x = (W + BT_TW - 1) / BT_TW; a.tiles_y = (H + BT_TH - 1) / BT_TH;
+    a.total = int64_t(N) * a.tiles_x * a.tiles_y;
+    for (int i = 0; i < K; ++i) a.taps[i] = taps_host[i];
+    const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
+    cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    const unsigned grid = (unsigned)(a.total < cap ? a.total : cap);
+    gaussblur_tma_kernel<K><<<grid, BT_THREADS, smem, st>>>(tm, a);
+    WM_LAUNCH_CHECK("wm_gaussblur(tma)");
+    return WM_OK;
+}
+
 // adjoint of the reflect-border blur, direct gather (GF is never instantiated by the
 // reference's trainers; this path favours clarity over speed)
 __global__ void __launch_bounds__(256) gaussblur_reflect_adjoint_kernel(const BlurArgs a) {
@@ -126,6 +250,11 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
         gaussblur_reflect_adjoint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a);
         WM_LAUNCH_CHECK("wm_gaussblur(reflect adjoint)");
         return WM_OK;
+    }
+    if (border == 0 && (k == 3 || k == 5 || k == 7) && W % 4 == 0 && aligned(y, 16) && tmap_ok(x, x_sp, x_sh, 4)) {
+        if (k == 3) return launch_blur_tma<3>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
+        if (k == 5) return launch_blur_tma<5>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
+        return launch_blur_tma<7>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
     }
     const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;
     const size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * BL_TW);

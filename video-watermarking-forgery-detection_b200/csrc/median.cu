@@ -9,6 +9,7 @@
 // forward is bit-exact.  Optionally it records, per output, the raster position of the FIRST
 // window element equal to the median (uint8); the backward is a deterministic gather through it.
 #include "median_net.cuh"
+#include "tma.cuh"
 #include "wm_common.cuh"
 
 namespace wm {
@@ -105,6 +106,203 @@ __global__ void __launch_bounds__(MD_THREADS) median_fwd_kernel(const MedArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 fast path (16-byte aligned rows): persistent CTAs fed by a ring of TMA-staged halo tiles
+// (out-of-bounds elements arrive as zeros == kornia's zero padding).  One warp per 8-row strip,
+// one lane per 4 adjacent columns: per tile row a lane reads 6 values (LDS.128 + 2 LDS.32), sorts
+// the 4 horizontal triples (FMNMX3 + XOR mid) and keeps the last 3 rows of sorted triples and raw
+// values in registers; an output is max3(mins), med3(mids), min3(maxes) -> med3.  The arg-median
+// plane is found by comparing the 9 raw values with the median (first match in raster order) and
+// leaves as one 32-bit store per lane.
+// ---------------------------------------------------------------------------------------------
+constexpr int MT_TW = 128, MT_TH = 64, MT_HALO = 4, MT_BW = MT_TW + 2 * MT_HALO, MT_BH = MT_TH + 2,
+              MT_THREADS = 256, MT_ROWS = 8, MT_STAGES = 3, MT_STRIDE = ((MT_BW * MT_BH + 31) / 32) * 32;
+
+struct MedTArgs {
+    float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
+};
+
+template <bool WANT_IDX>
+__global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
+    extern __shared__ __align__(128) float bufs[];
+    __shared__ uint64_t full[MT_STAGES];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < MT_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int per_plane = a.tiles_x * a.tiles_y;
+    auto issue = [&](int64_t t, int s) {
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float));
+        tma_load_3d(bufs + s * MT_STRIDE, &tmap, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < MT_STAGES; ++s) {
+            const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
+            if (t < a.total) issue(t, s);
+        }
+    }
+    const int cg = tid & 31, strip = tid >> 5;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
+        const int s = it % MT_STAGES;
+        mbar_wait(&full[s], (it / MT_STAGES) & 1);
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
+        const float* col = bufs + s * MT_STRIDE + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
+        float raw[3][6], lo[3][4], mi[3][4], hi[3][4];
+        auto load_row = [&](int row, int slot) {
+            const float* p = col + row * MT_BW;
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            raw[slot][0] = p[-1]; raw[slot][1] = c.x; raw[slot][2] = c.y; raw[slot][3] = c.z; raw[slot][4] = c.w;
+            raw[slot][5] = p[4];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float u = raw[slot][c4], v = raw[slot][c4 + 1], w = raw[slot][c4 + 2];
+                const float l = fmin3(u, v, w), h = fmax3(u, v, w);
+                lo[slot][c4] = l; hi[slot][c4] = h; mi[slot][c4] = mid3(u, v, w, l, h);
+            }
+        };
+        load_row(0, 0);
+        load_row(1, 1);
+        const bool col_ok = gx < a.W;
+        const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
+#pragma unroll
+        for (int r = 0; r < MT_ROWS; ++r) {
+            load_row(r + 2, (r + 2) % 3);
+            float4 o;
+            float* op = &o.x;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float med = med3(fmax3(lo[0][c4], lo[1][c4], lo[2][c4]),
+                                       med3(mi[0][c4], mi[1][c4], mi[2][c4]),
+                                       fmin3(hi[0][c4], hi[1][c4], hi[2][c4]));
+                op[c4] = med;
+                if (WANT_IDX) {
+                    int pos = 0;
+#pragma unroll
+                    for (int j = 8; j >= 0; --j)      // window row j/3 is ring slot (r + j/3) % 3
+                        pos = (raw[(r + j / 3) % 3][c4 + j % 3] == med) ? j : pos;
+                    packed |= uint32_t(pos) << (8 * c4);
+                }
+            }
+            if (col_ok && gy0 + r < a.H) {
+                stg128(a.y + obase + int64_t(r) * a.W, o);
+                if (WANT_IDX) *reinterpret_cast<uint32_t*>(a.idx + obase + int64_t(r) * a.W) = packed;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t t2 = t + int64_t(MT_STAGES) * gridDim.x;
+            if (t2 < a.total) issue(t2, s);
+        }
+    }
+}
+
+// 3x3 backward, TMA-fed: gx[p] = sum_{q in window(p)} [idx[q] == position of p in q's window] gy[q].
+// Two tile rings (gy: float, idx: uint8 with a 16-byte halo); a lane owns 4 adjacent p columns and
+// walks down its strip with the last 3 rows of (gy, idx) in registers.  Pure gather, fixed
+// summation order: deterministic.
+constexpr int MB_STAGES = 2, MB_IBW = MT_TW + 32, MB_ISTRIDE = ((MB_IBW * MT_BH + 127) / 128) * 128;
+
+struct MedBArgs {
+    float* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
+};
+
+__global__ void __launch_bounds__(MT_THREADS, 2) median3_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
+                                                                        const __grid_constant__ CUtensorMap tm_i,
+                                                                        const MedBArgs a) {
+    extern __shared__ __align__(128) float bufs[];
+    uint8_t* ibufs = reinterpret_cast<uint8_t*>(bufs + MB_STAGES * MT_STRIDE);
+    __shared__ uint64_t full[MB_STAGES];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_g);
+        tma_prefetch_desc(&tm_i);
+#pragma unroll
+        for (int s = 0; s < MB_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int per_plane = a.tiles_x * a.tiles_y;
+    auto issue = [&](int64_t t, int s) {
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float) + MB_IBW * MT_BH);
+        tma_load_3d(bufs + s * MT_STRIDE, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
+        tma_load_3d(ibufs + s * MB_ISTRIDE, &tm_i, tx * MT_TW - 16, ty * MT_TH - 1, n, &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < MB_STAGES; ++s) {
+            const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
+            if (t < a.total) issue(t, s);
+        }
+    }
+    const int cg = tid & 31, strip = tid >> 5;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
+        const int s = it % MB_STAGES;
+        mbar_wait(&full[s], (it / MB_STAGES) & 1);
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
+        const float* gcol = bufs + s * MT_STRIDE + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
+        const uint8_t* icol = ibufs + s * MB_ISTRIDE + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
+        float g[3][6];
+        int ix[3][6];
+        auto load_row = [&](int row, int slot) {
+            const float* p = gcol + row * MT_BW;
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            g[slot][0] = p[-1]; g[slot][1] = c.x; g[slot][2] = c.y; g[slot][3] = c.z; g[slot][4] = c.w; g[slot][5] = p[4];
+            const uint8_t* q = icol + row * MB_IBW;
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(q);
+            ix[slot][0] = q[-1];
+            ix[slot][1] = w4 & 0xff; ix[slot][2] = (w4 >> 8) & 0xff; ix[slot][3] = (w4 >> 16) & 0xff; ix[slot][4] = w4 >> 24;
+            ix[slot][5] = q[4];
+        };
+        load_row(0, 0);
+        load_row(1, 1);
+        const bool col_ok = gx < a.W;
+        float* dst = a.gx + (int64_t(n) * a.H + gy0) * a.W + gx;
+#pragma unroll
+        for (int r = 0; r < MT_ROWS; ++r) {
+            load_row(r + 2, (r + 2) % 3);
+            float4 o;
+            float* op = &o.x;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float acc = 0.f;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        // q = p + (dy, dx): tile row r + 1 + dy = ring slot (r + 1 + dy) % 3; p is at
+                        // window position (1 - dy, 1 - dx) of q
+                        const int slot = (r + 1 + dy) % 3, want = (1 - dy) * 3 + (1 - dx);
+                        acc += (ix[slot][c4 + 1 + dx] == want) ? g[slot][c4 + 1 + dx] : 0.f;
+                    }
+                op[c4] = acc;
+            }
+            if (col_ok && gy0 + r < a.H) stg128(dst + int64_t(r) * a.W, o);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t t2 = t + int64_t(MB_STAGES) * gridDim.x;
+            if (t2 < a.total) issue(t2, s);
+        }
+    }
+}
+
 // gx[p] = sum over outputs q with p in window(q) and argmedian(q) == p of gy[q]
 template <int K>
 __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ idx,
@@ -141,10 +339,27 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_fwd: kernel size must be 3 or 5 (got %d)", k);
     WM_REQUIRE(N >= 0 && N <= 65535 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd: bad shape N=%d H=%d W=%d", N, H, W);
     if (N == 0) return WM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k == 3 && W % 4 == 0 && aligned(y, 16) && (!idx || aligned(idx, 4)) && tmap_ok(x, x_sp, x_sh, 4)) {
+        CUtensorMap tm;
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, MT_BW, MT_BH)) {
+            set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
+            return WM_E_ARG;
+        }
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
+        ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
+        auto kern = idx ? median3_tma_kernel<true> : median3_tma_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
+        const int64_t cap = int64_t(sm_count()) * 2;
+        kern<<<(unsigned)(ta.total < cap ? ta.total : cap), MT_THREADS, smem, st>>>(tm, ta);
+        WM_LAUNCH_CHECK("wm_median_fwd(tma)");
+        return WM_OK;
+    }
     MedArgs a{x, x_sp, x_sh, y, idx, N, H, W};
     const int tiles = ((W + MD_TW - 1) / MD_TW) * ((H + MD_TH - 1) / MD_TH);
     dim3 grid(tiles, N);
-    cudaStream_t st = (cudaStream_t)stream;
     if (k == 3) { if (idx) median_fwd_kernel<3, true><<<grid, MD_THREADS, 0, st>>>(a); else median_fwd_kernel<3, false><<<grid, MD_THREADS, 0, st>>>(a); }
     else        { if (idx) median_fwd_kernel<5, true><<<grid, MD_THREADS, 0, st>>>(a); else median_fwd_kernel<5, false><<<grid, MD_THREADS, 0, st>>>(a); }
     WM_LAUNCH_CHECK("wm_median_fwd");
@@ -156,6 +371,21 @@ extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_bwd: kernel size must be 3 or 5 (got %d)", k);
     const int64_t total = int64_t(N) * H * W;
     if (total <= 0) return WM_OK;
+    if (k == 3 && W % 16 == 0 && aligned(gx, 16) && tmap_ok(gy, int64_t(H) * W, W, 4) && tmap_ok(idx, int64_t(H) * W, W, 1)) {
+        CUtensorMap tg, ti;
+        int rc = tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, MT_BH);
+        if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * W, W, MB_IBW, MT_BH);
+        if (rc) { set_error("wm_median_bwd: cuTensorMapEncodeTiled failed (%d)", rc); return WM_E_ARG; }
+        MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
+        ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
+        const size_t smem = sizeof(float) * size_t(MB_STAGES) * MT_STRIDE + size_t(MB_STAGES) * MB_ISTRIDE;
+        cudaError_t e = cudaFuncSetAttribute(median3_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
+        const int64_t cap2 = int64_t(sm_count()) * 2;
+        median3_bwd_tma_kernel<<<(unsigned)(ba.total < cap2 ? ba.total : cap2), MT_THREADS, smem, (cudaStream_t)stream>>>(tg, ti, ba);
+        WM_LAUNCH_CHECK("wm_median_bwd(tma)");
+        return WM_OK;
+    }
     const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 32;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (k == 3) median_bwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, idx, gx, N, H, W);

@@ -1,0 +1,107 @@
+// TMA (cp.async.bulk.tensor) + mbarrier plumbing shared by the plane-stencil kernels
+// (blur.cu, median.cu, resize.cu).
+//
+// The filters of the attack layer use ZERO padding (GaussianBlur: noise_layers/gaussian_blur.py:47,
+// MiddleBlur -> kornia MedianBlur).  A TMA tiled load fills out-of-bounds box elements with
+// zeros, also for negative start coordinates, so the halo'd tile of a plane arrives in shared
+// memory already padded: no per-element bounds test, no address arithmetic in the SM, and the
+// whole tile is one outstanding transaction per stage of the ring.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wm_common.cuh"
+
+namespace wm {
+
+// ---- host: tensor-map encoding through the driver entry point (no -lcuda link dependency) ----
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// Can [planes, H, W] with element strides (sp, sh, 1) be described by a tiled tensor map?
+inline bool tmap_ok(const void* base, int64_t sp, int64_t sh, size_t elem) {
+    return aligned(base, 16) && (sh * (int64_t)elem) % 16 == 0 && (sp * (int64_t)elem) % 16 == 0 && tmap_encoder() != nullptr;
+}
+
+// 3-D map over planes: dim0 = W (innermost), dim1 = H, dim2 = N; box = (box_w, box_h, 1).
+// Returns 0 on success (CUresult otherwise).
+inline int tmap_planes(CUtensorMap* m, CUtensorMapDataType dt, size_t elem, const void* base, int N, int H, int W,
+                       int64_t sp, int64_t sh, int box_w, int box_h) {
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)(sh * (int64_t)elem), (cuuint64_t)(sp * (int64_t)elem)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    auto enc = [&]() {
+        return (int)tmap_encoder()(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    int rc = enc();
+    if (rc == (int)CUDA_ERROR_INVALID_CONTEXT) {
+        // a thread that has made no runtime call yet (e.g. an autograd worker whose allocations were
+        // served from the caching allocator) has no current driver context: bind the primary one
+        cudaFree(nullptr);
+        rc = enc();
+    }
+    return rc;
+}
+
+// ---- device ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+// box (c0.., c1.., c2) of a 3-D tiled map -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ float4 ldg128_nc(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg128(float* p, const float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace wm
