@@ -180,6 +180,21 @@ int wm_interp_bwd(const float* gy, const float* pre, const uint32_t* maskbits, i
                   int mode, float* workspace, void* stream);
 int wm_interp_is_tiled(int Hin, int Win, int Hout, int Wout, int N);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused Resize round trip (Resize.forward, noise_layers/resize.py:38-53):
+ *   y = clamp( interpolate( interpolate(x, (Hm, Wm)), (H, W) ), 0, 1 )   in ONE kernel,
+ * x: N planes [H, W] (plane stride x_sp, row stride x_sh), y dense [N, H, W]; mode as above.
+ * maskbits (optional, uint32 [N, H, ceil(W/32)]): bit = 1 where 0 <= pre-clamp value <= 1.
+ * Supported when wm_resize_is_fused(...) == 1 (both ratios Hm/H, Wm/W within [0.45, 2.2]);
+ * otherwise compose two wm_interp_fwd calls.  wm_resize_bwd is the exact adjoint
+ * (gx = D^T U^T (gy .* mask)), deterministic.
+ * ------------------------------------------------------------------------------------------ */
+int wm_resize_is_fused(int H, int W, int Hm, int Wm, int N);
+int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
+                  int mode, uint32_t* maskbits, void* stream);
+int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
+                  int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -569,8 +569,42 @@ def interpolate(x, size, mode: str = "bilinear", window=None, clamp: bool = Fals
     return _InterpFn.apply(x, tuple(int(v) for v in window), (int(size[0]), int(size[1])), _MODES[mode], clamp)
 
 
+class _ResizeFusedFn(torch.autograd.Function):
+    """clamp(up(down(x)), 0, 1) in one kernel; the clamp pass-through mask is saved as 1 bit/value."""
+
+    @staticmethod
+    def forward(ctx, x, mid_hw, mode):
+        need_grad = bool(ctx.needs_input_grad[0])
+        x, sp, sh = _planes(x, "resize")
+        b, c, h, w = x.shape
+        n = b * c
+        y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+        mask = torch.empty((n, h, (w + 31) // 32), device=x.device, dtype=torch.int32) if need_grad else None
+        _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
+                  _ptr(mask), _stream())
+        ctx.meta = (tuple(mid_hw), mode, (b, c, h, w))
+        if need_grad:
+            ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        mid_hw, mode, (b, c, h, w) = ctx.meta
+        (mask,) = ctx.saved_tensors
+        gy = _flat(gy, "resize backward")
+        n = b * c
+        gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
+        _lib.call("wm_resize_bwd", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
+                  _stream())
+        return gx, None, None
+
+
 def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
     """Resize.forward arithmetic (noise_layers/resize.py:38-53)."""
     h, w = x.shape[2:]
+    mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
+    n = x.shape[0] * x.shape[1]
+    if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n):
+        return _ResizeFusedFn.apply(x, mid_hw, _MODES[mode])
     mid = interpolate(x, mid_hw, mode)
     return interpolate(mid, (h, w), mode, clamp=True)
