@@ -208,21 +208,115 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
     }
 }
 
-// 3x3 backward, TMA-fed: gx[p] = sum_{q in window(p)} [idx[q] == position of p in q's window] gy[q].
+// 5x5 fast path: same TMA ring; one lane per column, two 35-row strips per tile.  A lane keeps
+// the last 5 window rows sorted (9-comparator network per row, shared by the 5 vertically adjacent
+// outputs) and selects the median of the 5 sorted groups with the generated 67-comparator network;
+// the raw rows stay in registers for the arg-median search.  The row loop is unrolled by 5 so that
+// ring slots are compile-time indices.
+constexpr int M5_TW = 128, M5_TH = 70, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
+              M5_THREADS = 256, M5_ROWS = 35, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
+
+template <bool WANT_IDX>
+__global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
+    extern __shared__ __align__(128) float bufs[];
+    __shared__ uint64_t full[M5_STAGES];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < M5_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int per_plane = a.tiles_x * a.tiles_y;
+    auto issue = [&](int64_t t, int s) {
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        mbar_expect_tx(&full[s], M5_BW * M5_BH * sizeof(float));
+        tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, ty * M5_TH - 2, n, &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < M5_STAGES; ++s) {
+            const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
+            if (t < a.total) issue(t, s);
+        }
+    }
+    const int c = tid & 127, strip = tid >> 7;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
+        const int s = it % M5_STAGES;
+        mbar_wait(&full[s], (it / M5_STAGES) & 1);
+        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int gx = tx * M5_TW + c, gy0 = ty * M5_TH + strip * M5_ROWS;
+        const float* col = bufs + s * M5_STRIDE + (strip * M5_ROWS) * M5_BW + M5_HALO - 2 + c;
+        float srt[5][5], raw[WANT_IDX ? 5 : 1][5];
+        auto load_row = [&](int row, int slot) {
+            const float* p = col + row * M5_BW;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                srt[slot][k] = p[k];
+                if (WANT_IDX) raw[slot][k] = srt[slot][k];
+            }
+            sort5(srt[slot]);
+        };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load_row(j, j);
+        const bool col_ok = gx < a.W;
+        const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
+#pragma unroll 1
+        for (int r0 = 0; r0 < M5_ROWS; r0 += 5) {
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int r = r0 + u;
+                load_row(r + 4, (u + 4) % 5);          // (r + 4) % 5 == (u + 4) % 5 since r0 % 5 == 0
+                float v[25];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[j][k];
+                const float med = median25_sorted_groups(v);
+                if (col_ok && gy0 + r < a.H) {
+                    a.y[obase + int64_t(r) * a.W] = med;
+                    if (WANT_IDX) {
+                        int pos = 0;
+#pragma unroll
+                        for (int j = 24; j >= 0; --j)      // window row j/5 is ring slot (u + j/5) % 5
+                            pos = (raw[(u + j / 5) % 5][j % 5] == med) ? j : pos;
+                        a.idx[obase + int64_t(r) * a.W] = (uint8_t)pos;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t t2 = t + int64_t(M5_STAGES) * gridDim.x;
+            if (t2 < a.total) issue(t2, s);
+        }
+    }
+}
+
+// Backward, TMA-fed (K = 3, 5): gx[p] = sum_{q in window(p)} [idx[q] == position of p in q's window] gy[q].
 // Two tile rings (gy: float, idx: uint8 with a 16-byte halo); a lane owns 4 adjacent p columns and
-// walks down its strip with the last 3 rows of (gy, idx) in registers.  Pure gather, fixed
+// walks down its strip with the last K rows of (gy, idx) in registers.  Pure gather, fixed
 // summation order: deterministic.
-constexpr int MB_STAGES = 2, MB_IBW = MT_TW + 32, MB_ISTRIDE = ((MB_IBW * MT_BH + 127) / 128) * 128;
+constexpr int MB_STAGES = 2, MB_IBW = MT_TW + 32;
+template <int K> constexpr int mb_bh() { return MT_TH + K - 1; }
+template <int K> constexpr int mb_gstride() { return ((MT_BW * mb_bh<K>() + 31) / 32) * 32; }          // floats
+template <int K> constexpr int mb_istride() { return ((MB_IBW * mb_bh<K>() + 127) / 128) * 128; }      // bytes
 
 struct MedBArgs {
     float* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
 };
 
-__global__ void __launch_bounds__(MT_THREADS, 2) median3_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
-                                                                        const __grid_constant__ CUtensorMap tm_i,
-                                                                        const MedBArgs a) {
+template <int K>
+__global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
+                                                                       const __grid_constant__ CUtensorMap tm_i,
+                                                                       const MedBArgs a) {
+    constexpr int R = K / 2, BH = mb_bh<K>(), GS = mb_gstride<K>(), IS = mb_istride<K>(), WC = 4 + 2 * R;
     extern __shared__ __align__(128) float bufs[];
-    uint8_t* ibufs = reinterpret_cast<uint8_t*>(bufs + MB_STAGES * MT_STRIDE);
+    uint8_t* ibufs = reinterpret_cast<uint8_t*>(bufs + MB_STAGES * GS);
     __shared__ uint64_t full[MB_STAGES];
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -237,9 +331,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_bwd_tma_kernel(const __
     auto issue = [&](int64_t t, int s) {
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float) + MB_IBW * MT_BH);
-        tma_load_3d(bufs + s * MT_STRIDE, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
-        tma_load_3d(ibufs + s * MB_ISTRIDE, &tm_i, tx * MT_TW - 16, ty * MT_TH - 1, n, &full[s]);
+        mbar_expect_tx(&full[s], MT_BW * BH * sizeof(float) + MB_IBW * BH);
+        tma_load_3d(bufs + s * GS, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - R, n, &full[s]);
+        tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
     };
     if (tid == 0) {
 #pragma unroll
@@ -256,40 +350,43 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_bwd_tma_kernel(const __
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
-        const float* gcol = bufs + s * MT_STRIDE + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
-        const uint8_t* icol = ibufs + s * MB_ISTRIDE + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
-        float g[3][6];
-        int ix[3][6];
+        const float* gcol = bufs + s * GS + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
+        const uint8_t* icol = ibufs + s * IS + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
+        float g[K][WC];       // window columns -R .. 4+R-1 of the lane's 4 columns
+        int ix[K][WC];
         auto load_row = [&](int row, int slot) {
             const float* p = gcol + row * MT_BW;
             const float4 c = *reinterpret_cast<const float4*>(p);
-            g[slot][0] = p[-1]; g[slot][1] = c.x; g[slot][2] = c.y; g[slot][3] = c.z; g[slot][4] = c.w; g[slot][5] = p[4];
+            g[slot][R] = c.x; g[slot][R + 1] = c.y; g[slot][R + 2] = c.z; g[slot][R + 3] = c.w;
             const uint8_t* q = icol + row * MB_IBW;
             const uint32_t w4 = *reinterpret_cast<const uint32_t*>(q);
-            ix[slot][0] = q[-1];
-            ix[slot][1] = w4 & 0xff; ix[slot][2] = (w4 >> 8) & 0xff; ix[slot][3] = (w4 >> 16) & 0xff; ix[slot][4] = w4 >> 24;
-            ix[slot][5] = q[4];
+            ix[slot][R] = w4 & 0xff; ix[slot][R + 1] = (w4 >> 8) & 0xff; ix[slot][R + 2] = (w4 >> 16) & 0xff; ix[slot][R + 3] = w4 >> 24;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                g[slot][R - 1 - i] = p[-1 - i]; g[slot][R + 4 + i] = p[4 + i];
+                ix[slot][R - 1 - i] = q[-1 - i]; ix[slot][R + 4 + i] = q[4 + i];
+            }
         };
-        load_row(0, 0);
-        load_row(1, 1);
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) load_row(j, j);
         const bool col_ok = gx < a.W;
         float* dst = a.gx + (int64_t(n) * a.H + gy0) * a.W + gx;
 #pragma unroll
         for (int r = 0; r < MT_ROWS; ++r) {
-            load_row(r + 2, (r + 2) % 3);
+            load_row(r + K - 1, (r + K - 1) % K);
             float4 o;
             float* op = &o.x;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 float acc = 0.f;
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
+                for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        // q = p + (dy, dx): tile row r + 1 + dy = ring slot (r + 1 + dy) % 3; p is at
-                        // window position (1 - dy, 1 - dx) of q
-                        const int slot = (r + 1 + dy) % 3, want = (1 - dy) * 3 + (1 - dx);
-                        acc += (ix[slot][c4 + 1 + dx] == want) ? g[slot][c4 + 1 + dx] : 0.f;
+                    for (int dx = -R; dx <= R; ++dx) {
+                        // q = p + (dy, dx): tile row r + R + dy = ring slot (r + R + dy) % K; p is at
+                        // window position (R - dy, R - dx) of q
+                        const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
+                        acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
                     }
                 op[c4] = acc;
             }
@@ -301,6 +398,23 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_bwd_tma_kernel(const __
             if (t2 < a.total) issue(t2, s);
         }
     }
+}
+
+template <int K>
+static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, cudaStream_t st) {
+    CUtensorMap tg, ti;
+    int rc = tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, mb_bh<K>());
+    if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * W, W, MB_IBW, mb_bh<K>());
+    if (rc) { set_error("wm_median_bwd: cuTensorMapEncodeTiled failed (%d)", rc); return WM_E_ARG; }
+    MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
+    ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
+    const size_t smem = sizeof(float) * size_t(MB_STAGES) * mb_gstride<K>() + size_t(MB_STAGES) * mb_istride<K>();
+    cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    median_bwd_tma_kernel<K><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
+    WM_LAUNCH_CHECK("wm_median_bwd(tma)");
+    return WM_OK;
 }
 
 // gx[p] = sum over outputs q with p in window(q) and argmedian(q) == p of gy[q]
@@ -357,6 +471,23 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
         WM_LAUNCH_CHECK("wm_median_fwd(tma)");
         return WM_OK;
     }
+    if (k == 5 && tmap_ok(x, x_sp, x_sh, 4)) {
+        CUtensorMap tm;
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, M5_BW, M5_BH)) {
+            set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
+            return WM_E_ARG;
+        }
+        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0};
+        ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
+        auto kern = idx ? median5_tma_kernel<true> : median5_tma_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
+        const int64_t cap = int64_t(sm_count()) * 2;
+        kern<<<(unsigned)(ta.total < cap ? ta.total : cap), M5_THREADS, smem, st>>>(tm, ta);
+        WM_LAUNCH_CHECK("wm_median_fwd(tma5)");
+        return WM_OK;
+    }
     MedArgs a{x, x_sp, x_sh, y, idx, N, H, W};
     const int tiles = ((W + MD_TW - 1) / MD_TW) * ((H + MD_TH - 1) / MD_TH);
     dim3 grid(tiles, N);
@@ -371,21 +502,9 @@ extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_bwd: kernel size must be 3 or 5 (got %d)", k);
     const int64_t total = int64_t(N) * H * W;
     if (total <= 0) return WM_OK;
-    if (k == 3 && W % 16 == 0 && aligned(gx, 16) && tmap_ok(gy, int64_t(H) * W, W, 4) && tmap_ok(idx, int64_t(H) * W, W, 1)) {
-        CUtensorMap tg, ti;
-        int rc = tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, MT_BH);
-        if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * W, W, MB_IBW, MT_BH);
-        if (rc) { set_error("wm_median_bwd: cuTensorMapEncodeTiled failed (%d)", rc); return WM_E_ARG; }
-        MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
-        ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
-        const size_t smem = sizeof(float) * size_t(MB_STAGES) * MT_STRIDE + size_t(MB_STAGES) * MB_ISTRIDE;
-        cudaError_t e = cudaFuncSetAttribute(median3_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
-        const int64_t cap2 = int64_t(sm_count()) * 2;
-        median3_bwd_tma_kernel<<<(unsigned)(ba.total < cap2 ? ba.total : cap2), MT_THREADS, smem, (cudaStream_t)stream>>>(tg, ti, ba);
-        WM_LAUNCH_CHECK("wm_median_bwd(tma)");
-        return WM_OK;
-    }
+    if (W % 16 == 0 && aligned(gx, 16) && tmap_ok(gy, int64_t(H) * W, W, 4) && tmap_ok(idx, int64_t(H) * W, W, 1))
+        return k == 3 ? launch_median_bwd_tma<3>(gy, idx, gx, N, H, W, (cudaStream_t)stream)
+                      : launch_median_bwd_tma<5>(gy, idx, gx, N, H, W, (cudaStream_t)stream);
     const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 32;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (k == 3) median_bwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, idx, gx, N, H, W);
