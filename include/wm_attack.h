@@ -183,17 +183,23 @@ int wm_interp_is_tiled(int Hin, int Win, int Hout, int Wout, int N);
 /* ------------------------------------------------------------------------------------------
  * Fused Resize round trip (Resize.forward, noise_layers/resize.py:38-53):
  *   y = clamp( interpolate( interpolate(x, (Hm, Wm)), (H, W) ), 0, 1 )   in ONE kernel,
- * x: N planes [H, W] (plane stride x_sp, row stride x_sh), y dense [N, H, W]; mode as above.
- * maskbits (optional, uint32 [N, H, ceil(W/32)]): bit = 1 where 0 <= pre-clamp value <= 1.
- * Supported when wm_resize_is_fused(...) == 1 (both ratios Hm/H, Wm/W within [0.45, 2.2]);
- * otherwise compose two wm_interp_fwd calls.  wm_resize_bwd is the exact adjoint
- * (gx = D^T U^T (gy .* mask)), deterministic.
+ * x: N planes [H, W] (plane stride x_sp, row stride x_sh, multiples of 4), y dense [N, H, W].
+ * Supported when wm_resize_is_fused(...) == 1 (W % 4 == 0, both ratios Hm/H, Wm/W within
+ * [0.45, 2.2]); otherwise compose two wm_interp_fwd calls.
+ * tables: device workspace of wm_resize_table_floats(H, W, Hm, Wm) floats filled once per
+ *   geometry by wm_resize_tables (band starts + weights of the per-axis operators U*D and
+ *   their transposes); it may be cached and shared by any number of fwd/bwd calls.
+ * maskbits (optional, uint32 [N, H, ceil(W/128), 4], 16-byte aligned): word k of a (row, 128-column
+ *   tile) holds in bit l the flag 0 <= pre-clamp value <= 1 of column 128*tile + 4*l + k.
+ * wm_resize_bwd is the exact adjoint gx = D^T U^T (gy .* mask) (gy, gx dense), deterministic.
  * ------------------------------------------------------------------------------------------ */
 int wm_resize_is_fused(int H, int W, int Hm, int Wm, int N);
+int64_t wm_resize_table_floats(int H, int W, int Hm, int Wm);
+int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int mode, void* stream);
 int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
-                  int mode, uint32_t* maskbits, void* stream);
+                  int mode, uint32_t* maskbits, const float* tables, void* stream);
 int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
-                  int mode, void* stream);
+                  int mode, const float* tables, void* stream);
 
 #ifdef __cplusplus
 }

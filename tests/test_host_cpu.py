@@ -29,7 +29,7 @@ def lib():
 def header_functions():
     src = open(os.path.join(ROOT, "include", "wm_attack.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return set(re.findall(r"\b(?:int|const char\s*\*)\s*(wm_\w+)\s*\(", src))
+    return set(re.findall(r"\b(?:int64_t|int|const char\s*\*)\s*(wm_\w+)\s*\(", src))
 
 
 def test_library_exports_every_header_symbol(lib):

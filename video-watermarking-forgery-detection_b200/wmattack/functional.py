@@ -569,6 +569,22 @@ def interpolate(x, size, mode: str = "bilinear", window=None, clamp: bool = Fals
     return _InterpFn.apply(x, tuple(int(v) for v in window), (int(size[0]), int(size[1])), _MODES[mode], clamp)
 
 
+_RESIZE_TABLES: dict = {}      # (device, H, W, Hm, Wm, mode) -> device tensor of band tables (tiny, LRU-capped)
+
+
+def _resize_tables(device, h, w, mid_hw, mode):
+    key = (str(device), h, w, mid_hw[0], mid_hw[1], mode)
+    t = _RESIZE_TABLES.get(key)
+    if t is None:
+        if len(_RESIZE_TABLES) >= 256:
+            _RESIZE_TABLES.pop(next(iter(_RESIZE_TABLES)))
+        n = int(_lib.load().wm_resize_table_floats(h, w, mid_hw[0], mid_hw[1]))
+        t = torch.empty(n, device=device, dtype=torch.float32)
+        _lib.call("wm_resize_tables", t.data_ptr(), h, w, mid_hw[0], mid_hw[1], mode, _stream())
+        _RESIZE_TABLES[key] = t
+    return t
+
+
 class _ResizeFusedFn(torch.autograd.Function):
     """clamp(up(down(x)), 0, 1) in one kernel; the clamp pass-through mask is saved as 1 bit/value."""
 
@@ -578,24 +594,25 @@ class _ResizeFusedFn(torch.autograd.Function):
         x, sp, sh = _planes(x, "resize")
         b, c, h, w = x.shape
         n = b * c
+        tables = _resize_tables(x.device, h, w, mid_hw, mode)
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
-        mask = torch.empty((n, h, (w + 31) // 32), device=x.device, dtype=torch.int32) if need_grad else None
+        mask = torch.empty((n, h, 4 * ((w + 127) // 128)), device=x.device, dtype=torch.int32) if need_grad else None
         _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
-                  _ptr(mask), _stream())
+                  _ptr(mask), tables.data_ptr(), _stream())
         ctx.meta = (tuple(mid_hw), mode, (b, c, h, w))
         if need_grad:
-            ctx.save_for_backward(mask)
+            ctx.save_for_backward(mask, tables)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         mid_hw, mode, (b, c, h, w) = ctx.meta
-        (mask,) = ctx.saved_tensors
+        mask, tables = ctx.saved_tensors
         gy = _flat(gy, "resize backward")
         n = b * c
         gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
         _lib.call("wm_resize_bwd", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
-                  _stream())
+                  tables.data_ptr(), _stream())
         return gx, None, None
 
 
@@ -604,7 +621,8 @@ def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
     h, w = x.shape[2:]
     mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
     n = x.shape[0] * x.shape[1]
-    if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n):
+    if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and x.stride(2) % 4 == 0 and x.stride(1) % 4 == 0 \
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
         return _ResizeFusedFn.apply(x, mid_hw, _MODES[mode])
     mid = interpolate(x, mid_hw, mode)
     return interpolate(mid, (h, w), mode, clamp=True)
