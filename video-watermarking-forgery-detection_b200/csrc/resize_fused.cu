@@ -12,7 +12,7 @@
 // for r = 0.5).  A small table kernel builds, per axis, the band start and weights of every row of
 // A (forward) and of A^T (adjoint) with ATen's fp32 coordinate arithmetic; the main kernel is a
 // generic separable banded transform  Y = A_v X A_h^T  on shared-memory tiles:
-//   stage  : TMA box (forward) / masked 128-bit loads (backward) of the source region of a tile
+//   stage  : TMA box of the source region of a tile (backward: cotangent, then masked in place)
 //   H pass : lane = output column (its band weights live in registers), warps walk the rows
 //   V pass : lane = 4 adjacent columns (LDS.128), warps walk the output rows with broadcast weights,
 //            clamp + 1-bit pass-through mask (4 ballots per tile row), STG.128
@@ -106,24 +106,26 @@ struct RBArgs {
     const int* lox; const float* wx;              // column-axis tables of this direction
     const int* loy; const float* wy;              // row-axis tables
     int N, H, W, tiles_x, tiles_y;
+    int* overflow;                                // optional: set to 1 if a band did not fit its window
 };
 
 template <int BT> struct RBGeom {
-    static constexpr int IW = ((RB_TW + BT + 8 + 3) / 4) * 4 + 4;   // staged columns (+4: start aligned down to 4)
+    static constexpr int IW = ((RB_TW + BT + 16 + 3) / 4) * 4;      // staged columns (start = 4-aligned band start - 8)
     static constexpr int IH = RB_TH + BT + 4;                       // staged rows
-    static constexpr size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * RB_TW + size_t(RB_TH) * BT) +
-                                   sizeof(int) * RB_TH + 128;
+    static constexpr int NP = RB_TH / 2;                            // output row pairs of a tile
+    static constexpr size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * RB_TW + size_t(NP) * 2 * BT) +
+                                   sizeof(int) * NP + 128;
 };
 
-// DIR 0: forward (TMA staging, clamp, mask out)   DIR 1: adjoint (masked staging, no clamp)
+// DIR 0: forward (clamp, mask out)   DIR 1: adjoint (cotangent masked in shared memory, no clamp)
 template <int BT, int DIR>
 __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_constant__ CUtensorMap tmap, const RBArgs a) {
     using G = RBGeom<BT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* in = reinterpret_cast<float*>(smem_raw);                  // [IH][IW]
     float* tmp = in + G::IH * G::IW;                                 // [IH][TW]
-    float* wys = tmp + G::IH * RB_TW;                                // [TH][BT]
-    int* ylos = reinterpret_cast<int*>(wys + RB_TH * BT);            // [TH] band start relative to the staged rows
+    float* wyp = tmp + G::IH * RB_TW;                                // [NP][2][BT] weights of a row pair on its shared window
+    int* ylop = reinterpret_cast<int*>(wyp + G::NP * 2 * BT);        // [NP] first staged row of the pair's window
     __shared__ uint64_t full;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,27 +133,51 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     const int ox0 = tx * RB_TW, oy0 = ty * RB_TH;
     const int tw = min(RB_TW, a.W - ox0), th = min(RB_TH, a.H - oy0);
 
-    // staged region: columns [xlo, xlo + IW), rows [ylo, ylo + IH)
-    const int xlo = __ldg(a.lox + ox0) & ~3;
-    const int ylo = __ldg(a.loy + oy0);
+    // staged region: columns [xs, xs + IW) (xs may be negative: zero filled), rows [ys, ys + IH).
+    // The 8-column margin absorbs the regularised window starts (flat band starts at a clamped border).
+    const int xs = (__ldg(a.lox + ox0) & ~3) - 8;
+    const int ys = __ldg(a.loy + oy0);
     // rows the V pass can touch (rows past the image bottom are staged as zeros: their weights are 0)
-    const int ih = min(__ldg(a.loy + oy0 + th - 1) + BT - ylo, G::IH);
+    const int ih = min(__ldg(a.loy + oy0 + th - 1) + BT - ys, G::IH);
 
-    // H pass role: lane = output column, band weights in registers
+    // H pass role: lane = output column.  The 32 windows of a warp are made REGULAR (start = base +
+    // lane, so the lanes of every LDS hit 32 distinct banks); the band of each lane is shifted
+    // inside its BT-wide register window accordingly.
     const int hg = warp & 3, hr = warp >> 2;                         // 32-column group, row parity
     const int ho = min(ox0 + 32 * hg + lane, a.W - 1);
+    const int hlo = __ldg(a.lox + ho);
+    const bool hvalid = 32 * hg + lane < tw;                         // lanes past the image edge hold zero weights
+    int hmin = hvalid ? hlo - lane : (1 << 30);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) hmin = min(hmin, __shfl_xor_sync(0xffffffffu, hmin, d));
+    hmin = min(hmin, a.W);                                           // (a group with no valid lane)
+    const int hshift = hvalid ? hlo - (hmin + lane) : BT;            // >= 0
     float wreg[BT];
 #pragma unroll
-    for (int j = 0; j < BT; ++j) wreg[j] = __ldg(a.wx + int64_t(ho) * BT + j);
-    const int hbase = min(max(__ldg(a.lox + ho) - xlo, 0), G::IW - BT);
-
-    // V pass tables of the tile rows
-    for (int i = tid; i < RB_TH * BT; i += RB_THREADS) {
-        const int r = i / BT, j = i - r * BT;
-        wys[i] = __ldg(a.wy + int64_t(min(oy0 + r, a.H - 1)) * BT + j);
+    for (int t = 0; t < BT; ++t) {
+        const int j = t - hshift;
+        wreg[t] = (j >= 0 && j < BT) ? __ldg(a.wx + int64_t(ho) * BT + j) : 0.f;
     }
-    if (tid < RB_TH) ylos[tid] = min(max(__ldg(a.loy + min(oy0 + tid, a.H - 1)) - ylo, 0), G::IH - BT);
-    if (DIR == 0 && tid == 0) {
+    if (a.overflow && hvalid) {          // a weight that does not fit the regular window would be lost
+        bool lost = false;
+        for (int j = BT - hshift; j < BT; ++j) lost |= j >= 0 && __ldg(a.wx + int64_t(ho) * BT + j) != 0.f;
+        if (lost) atomicExch(a.overflow, 1);
+    }
+    const int hbase = min(max(hmin - xs + lane, 0), G::IW - BT);
+    if (a.overflow && hvalid && hbase != hmin - xs + lane) atomicExch(a.overflow, 1);
+
+    // V pass tables: rows (2p, 2p+1) share the window starting at the first row's band start
+    for (int i = tid; i < G::NP * BT; i += RB_THREADS) {
+        const int p = i / BT, t = i - p * BT;
+        const int r0 = min(oy0 + 2 * p, a.H - 1), r1 = min(oy0 + 2 * p + 1, a.H - 1);
+        const int d = __ldg(a.loy + r1) - __ldg(a.loy + r0);
+        wyp[(2 * p) * BT + t] = __ldg(a.wy + int64_t(r0) * BT + t);
+        const int j = t - d;
+        wyp[(2 * p + 1) * BT + t] = (j >= 0 && j < BT) ? __ldg(a.wy + int64_t(r1) * BT + j) : 0.f;
+        if (a.overflow && t >= BT - d && t >= 0 && __ldg(a.wy + int64_t(r1) * BT + t) != 0.f) atomicExch(a.overflow, 1);
+    }
+    if (tid < G::NP) ylop[tid] = min(max(__ldg(a.loy + min(oy0 + 2 * tid, a.H - 1)) - ys, 0), G::IH - BT);
+    if (tid == 0) {
         tma_prefetch_desc(&tmap);
         mbar_init(&full, 1);
         mbar_fence_init();
@@ -159,38 +185,34 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     __syncthreads();
 
     int n = blockIdx.z;
-    if (DIR == 0 && tid == 0 && n < a.N) {
+    if (tid == 0 && n < a.N) {
         mbar_expect_tx(&full, G::IW * G::IH * sizeof(float));
-        tma_load_3d(in, &tmap, xlo, ylo, n, &full);
+        tma_load_3d(in, &tmap, xs, ys, n, &full);
     }
     for (int it = 0; n < a.N; n += gridDim.z, ++it) {
-        // ---- stage ----------------------------------------------------------------------------
-        if (DIR == 0) {
-            mbar_wait(&full, it & 1);
-        } else {
-            // gy .* mask: 128-bit loads, the 4 ballot words of a (row, 128-column tile) sit in one uint4
+        // ---- stage: the TMA box of this plane was requested one plane ago -----------------------
+        mbar_wait(&full, it & 1);
+        if (DIR == 1 && a.mask) {
+            // gy .* mask in place; the 4 ballot words of a (row, 128-column tile) sit in one uint4
             constexpr int C4 = G::IW / 4;
-            const float* gsrc = a.src + int64_t(n) * a.s_sp;
+            const uint4* mrow = reinterpret_cast<const uint4*>(a.mask) + int64_t(n) * a.H * a.tiles_x;
             for (int i = tid; i < ih * C4; i += RB_THREADS) {
                 const int r = i / C4, c4 = i - r * C4;
-                const int gy = ylo + r, gx = xlo + 4 * c4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gx < a.W && gy < a.H) {
-                    v = ldg128_nc(gsrc + int64_t(gy) * a.s_sh + gx);
-                    if (a.mask) {
-                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask) +
-                                              (int64_t(n) * a.H + gy) * a.tiles_x + (gx >> 7));
-                        const int b = (gx & 127) >> 2;
-                        v.x = (m.x >> b) & 1u ? v.x : 0.f; v.y = (m.y >> b) & 1u ? v.y : 0.f;
-                        v.z = (m.z >> b) & 1u ? v.z : 0.f; v.w = (m.w >> b) & 1u ? v.w : 0.f;
-                    }
+                const int gy = ys + r, gx = xs + 4 * c4;
+                if (gx >= 0 && gx < a.W && gy < a.H) {
+                    float4* q = reinterpret_cast<float4*>(in + r * G::IW + 4 * c4);
+                    float4 v = *q;
+                    const uint4 m = __ldg(mrow + int64_t(gy) * a.tiles_x + (gx >> 7));
+                    const int b = (gx & 127) >> 2;
+                    v.x = (m.x >> b) & 1u ? v.x : 0.f; v.y = (m.y >> b) & 1u ? v.y : 0.f;
+                    v.z = (m.z >> b) & 1u ? v.z : 0.f; v.w = (m.w >> b) & 1u ? v.w : 0.f;
+                    *q = v;
                 }
-                *reinterpret_cast<float4*>(in + r * G::IW + 4 * c4) = v;
             }
             __syncthreads();
         }
 
-        // ---- H pass: tmp[r][o] = sum_j wreg[j] * in[r][hbase + j] -------------------------------
+        // ---- H pass: tmp[r][o] = sum_t wreg[t] * in[r][hbase + t] -------------------------------
         {
             const float* p = in + hr * G::IW + hbase;
             float* q = tmp + hr * RB_TW + 32 * hg + lane;
@@ -198,51 +220,60 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
             for (int r = hr; r < ih; r += 2) {
                 float acc = wreg[0] * p[0];
 #pragma unroll
-                for (int j = 1; j < BT; ++j) acc = fmaf(wreg[j], p[j], acc);
+                for (int t = 1; t < BT; ++t) acc = fmaf(wreg[t], p[t], acc);
                 *q = acc;
                 p += 2 * G::IW; q += 2 * RB_TW;
             }
         }
         __syncthreads();
         // `in` is dead: prefetch the next plane's tile while the V pass runs
-        if (DIR == 0 && tid == 0 && n + gridDim.z < a.N) {
+        if (tid == 0 && n + gridDim.z < a.N) {
             mbar_expect_tx(&full, G::IW * G::IH * sizeof(float));
-            tma_load_3d(in, &tmap, xlo, ylo, n + gridDim.z, &full);
+            tma_load_3d(in, &tmap, xs, ys, n + gridDim.z, &full);
         }
 
-        // ---- V pass: out[o][4 cols] = sum_j wy[o][j] * tmp[ylos[o] + j][4 cols] -------------------
+        // ---- V pass: rows (2p, 2p+1) x 4 columns per lane from one shared window of tmp -----------
         {
             const bool okc = 4 * lane < tw;
             float* dst = a.dst + (int64_t(n) * a.H + oy0) * a.W + ox0 + 4 * lane;
-            for (int o = warp; o < th; o += RB_THREADS / 32) {
-                const float* wrow = wys + o * BT;
-                const float* p = tmp + ylos[o] * RB_TW + 4 * lane;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pr = warp; 2 * pr < th; pr += RB_THREADS / 32) {
+                const float* w0 = wyp + (2 * pr) * BT;
+                const float* p = tmp + ylop[pr] * RB_TW + 4 * lane;
+                float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
 #pragma unroll
-                for (int j4 = 0; j4 < BT; j4 += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wrow + j4);
-                    const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int t2 = 0; t2 < BT; t2 += 2) {      // BT is even: weights as 8-byte broadcast loads
+                    const float2 wa = *reinterpret_cast<const float2*>(w0 + t2);
+                    const float2 wb = *reinterpret_cast<const float2*>(w0 + BT + t2);
+                    const float a0[2] = {wa.x, wa.y}, a1[2] = {wb.x, wb.y};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 v = *reinterpret_cast<const float4*>(p + (j4 + j) * RB_TW);
-                        acc.x = fmaf(wj[j], v.x, acc.x); acc.y = fmaf(wj[j], v.y, acc.y);
-                        acc.z = fmaf(wj[j], v.z, acc.z); acc.w = fmaf(wj[j], v.w, acc.w);
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 v = *reinterpret_cast<const float4*>(p + (t2 + u) * RB_TW);
+                        acc[0].x = fmaf(a0[u], v.x, acc[0].x); acc[0].y = fmaf(a0[u], v.y, acc[0].y);
+                        acc[0].z = fmaf(a0[u], v.z, acc[0].z); acc[0].w = fmaf(a0[u], v.w, acc[0].w);
+                        acc[1].x = fmaf(a1[u], v.x, acc[1].x); acc[1].y = fmaf(a1[u], v.y, acc[1].y);
+                        acc[1].z = fmaf(a1[u], v.z, acc[1].z); acc[1].w = fmaf(a1[u], v.w, acc[1].w);
                     }
                 }
-                if (DIR == 0) {
-                    const float4 c = make_float4(__saturatef(acc.x), __saturatef(acc.y), __saturatef(acc.z), __saturatef(acc.w));
-                    if (okc) stg128(dst + int64_t(o) * a.W, c);
-                    if (a.mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
-                        const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
-                        const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc.y);
-                        const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc.z);
-                        const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc.w);
-                        if (lane < 4)
-                            a.mask[((int64_t(n) * a.H + oy0 + o) * a.tiles_x + tx) * 4 + lane] =
-                                lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int o = 2 * pr + k;
+                    if (o >= th) break;
+                    if (DIR == 0) {
+                        const float4 c = make_float4(__saturatef(acc[k].x), __saturatef(acc[k].y), __saturatef(acc[k].z),
+                                                     __saturatef(acc[k].w));
+                        if (okc) stg128(dst + int64_t(o) * a.W, c);
+                        if (a.mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
+                            const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc[k].x);
+                            const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc[k].y);
+                            const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc[k].z);
+                            const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc[k].w);
+                            if (lane < 4)
+                                a.mask[((int64_t(n) * a.H + oy0 + o) * a.tiles_x + tx) * 4 + lane] =
+                                    lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+                        }
+                    } else if (okc) {
+                        stg128(dst + int64_t(o) * a.W, acc[k]);
                     }
-                } else if (okc) {
-                    stg128(dst + int64_t(o) * a.W, acc);
                 }
             }
         }
@@ -257,11 +288,13 @@ static inline bool rb_ok(int H, int W, int Hm, int Wm, int N) {
            (H + RB_TH - 1) / RB_TH <= 65535 && tmap_encoder() != nullptr;
 }
 
-// band bound of A = U D and of A^T: floor(3 n / nm) + 6 entries; rounded up to a template size
+// Window size: the band of A = U D / A^T is at most floor(3 n / nm) + 6 entries; made regular over
+// 32 lanes (H pass) or shared by a row pair (V pass) it needs floor(3 n / nm) + 7
+// (checked over geometries in tests/test_host_cpu.py::test_resize_band_bound).
 static inline int rb_band(int H, int W, int Hm, int Wm) {
     const float s = fmaxf((float)H / (float)Hm, (float)W / (float)Wm);
-    const int need = (int)floorf(3.f * s) + 6;      // checked exhaustively against U*D in tests (row and column spans)
-    return need <= 8 ? 8 : (need <= 12 ? 12 : 16);
+    const int need = (int)floorf(3.f * s + 1e-3f) + 7;
+    return need <= 8 ? 8 : (need <= 10 ? 10 : (need <= 12 ? 12 : 14));
 }
 
 static inline RBAxis rb_axis(int n, int nm) { return RBAxis{n, nm, (float)n / (float)nm, (float)nm / (float)n}; }
@@ -289,7 +322,7 @@ extern "C" int wm_resize_is_fused(int H, int W, int Hm, int Wm, int N) { return 
 // floats of table workspace needed by wm_resize_fwd / wm_resize_bwd for this geometry
 extern "C" int64_t wm_resize_table_floats(int H, int W, int Hm, int Wm) {
     const int BT = rb_band(H, W, Hm, Wm);
-    return 2 * (rb_axis_words(W, BT) + rb_axis_words(H, BT));
+    return 2 * (rb_axis_words(W, BT) + rb_axis_words(H, BT)) + 4;      // + overflow flag
 }
 
 extern "C" int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int mode, void* stream) {
@@ -311,6 +344,7 @@ extern "C" int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int
     }
     rb_adj_tables_kernel<<<(W + 127) / 128, 128, 0, st>>>(W, BT, lo(fx), fx + W, lo(bx), bx + W);
     rb_adj_tables_kernel<<<(H + 127) / 128, 128, 0, st>>>(H, BT, lo(fy), fy + H, lo(by), by + H);
+    cudaMemsetAsync(by + rb_axis_words(H, BT), 0, 4 * sizeof(float), st);
     WM_LAUNCH_CHECK("wm_resize_tables");
     return WM_OK;
 }
@@ -326,23 +360,22 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
     a.lox = reinterpret_cast<const int*>(tx); a.wx = tx + W;
     a.loy = reinterpret_cast<const int*>(ty); a.wy = ty + H;
     a.N = N; a.H = H; a.W = W; a.tiles_x = (W + RB_TW - 1) / RB_TW; a.tiles_y = (H + RB_TH - 1) / RB_TH;
+    a.overflow = reinterpret_cast<int*>(const_cast<float*>(by + rb_axis_words(H, BT)));
     CUtensorMap tm{};
     cudaStream_t st = (cudaStream_t)stream;
 #define RB_CASE(B)                                                                                                  \
     case B:                                                                                                         \
-        if (dir == 0) {                                                                                             \
-            if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh,             \
-                                     RBGeom<B>::IW, RBGeom<B>::IH)) {                                               \
-                set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, rc);                                       \
-                return WM_E_ARG;                                                                                    \
-            }                                                                                                       \
-            return rb_launch<B, 0>(a, tm, st, who);                                                                 \
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh,                 \
+                                 RBGeom<B>::IW, RBGeom<B>::IH)) {                                                   \
+            set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, rc);                                           \
+            return WM_E_ARG;                                                                                        \
         }                                                                                                           \
-        return rb_launch<B, 1>(a, tm, st, who);
+        return dir == 0 ? rb_launch<B, 0>(a, tm, st, who) : rb_launch<B, 1>(a, tm, st, who);
     switch (BT) {
         RB_CASE(8)
+        RB_CASE(10)
         RB_CASE(12)
-        RB_CASE(16)
+        RB_CASE(14)
     }
 #undef RB_CASE
     set_error("%s: unsupported band %d", who, BT);
