@@ -112,19 +112,22 @@ struct RBArgs {
 template <int BT> struct RBGeom {
     static constexpr int IW = ((RB_TW + BT + 16 + 3) / 4) * 4;      // staged columns (start = 4-aligned band start - 8)
     static constexpr int IH = RB_TH + BT + 4;                       // staged rows
+    static constexpr int IHA = ((IH + 7) / 8) * 8;                  // allocated rows (the H pass runs 8 rows per step)
     static constexpr int NP = RB_TH / 2;                            // output row pairs of a tile
-    static constexpr size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * RB_TW + size_t(NP) * 2 * BT) +
-                                   sizeof(int) * NP + 128;
+    static constexpr size_t smem = sizeof(float) * (size_t(IHA) * IW + size_t(IHA) * RB_TW + size_t(NP) * 2 * BT) +
+                                   sizeof(int) * NP + sizeof(uint32_t) * IH * 12 + 128;
 };
 
 // DIR 0: forward (clamp, mask out)   DIR 1: adjoint (cotangent masked in shared memory, no clamp)
 template <int BT, int DIR>
-__global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_constant__ CUtensorMap tmap, const RBArgs a) {
+__global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_mask,
+                                                                  const RBArgs a) {
     using G = RBGeom<BT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* in = reinterpret_cast<float*>(smem_raw);                  // [IH][IW]
-    float* tmp = in + G::IH * G::IW;                                 // [IH][TW]
-    float* wyp = tmp + G::IH * RB_TW;                                // [NP][2][BT] weights of a row pair on its shared window
+    float* in = reinterpret_cast<float*>(smem_raw);                  // [IHA][IW] (TMA fills IH rows)
+    float* tmp = in + G::IHA * G::IW;                                // [IHA][TW]
+    uint32_t* mb = reinterpret_cast<uint32_t*>(tmp + G::IHA * RB_TW);   // [IH][12] mask words of the staged rows (adjoint)
+    float* wyp = reinterpret_cast<float*>(mb + G::IH * 12);          // [NP][2][BT] weights of a row pair on its shared window
     int* ylop = reinterpret_cast<int*>(wyp + G::NP * 2 * BT);        // [NP] first staged row of the pair's window
     __shared__ uint64_t full;
 
@@ -184,25 +187,28 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     }
     __syncthreads();
 
+    const bool masked = DIR == 1 && a.mask != nullptr;
+    const int mt0 = max(xs, 0) >> 7;                                 // first 128-column mask tile of the staged region
+    auto request = [&](int plane) {
+        mbar_expect_tx(&full, G::IW * G::IH * sizeof(float) + (masked ? 12 * G::IH * sizeof(uint32_t) : 0));
+        tma_load_3d(in, &tmap, xs, ys, plane, &full);
+        if (masked) tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
+    };
     int n = blockIdx.z;
-    if (tid == 0 && n < a.N) {
-        mbar_expect_tx(&full, G::IW * G::IH * sizeof(float));
-        tma_load_3d(in, &tmap, xs, ys, n, &full);
-    }
+    if (tid == 0 && n < a.N) request(n);
     for (int it = 0; n < a.N; n += gridDim.z, ++it) {
         // ---- stage: the TMA box of this plane was requested one plane ago -----------------------
         mbar_wait(&full, it & 1);
-        if (DIR == 1 && a.mask) {
-            // gy .* mask in place; the 4 ballot words of a (row, 128-column tile) sit in one uint4
+        if (masked) {
+            // gy .* mask in place; the 4 ballot words of a (row, 128-column tile) sit in one uint4 of mb
             constexpr int C4 = G::IW / 4;
-            const uint4* mrow = reinterpret_cast<const uint4*>(a.mask) + int64_t(n) * a.H * a.tiles_x;
             for (int i = tid; i < ih * C4; i += RB_THREADS) {
                 const int r = i / C4, c4 = i - r * C4;
-                const int gy = ys + r, gx = xs + 4 * c4;
-                if (gx >= 0 && gx < a.W && gy < a.H) {
+                const int gx = xs + 4 * c4;
+                if (gx >= 0 && gx < a.W) {
                     float4* q = reinterpret_cast<float4*>(in + r * G::IW + 4 * c4);
                     float4 v = *q;
-                    const uint4 m = __ldg(mrow + int64_t(gy) * a.tiles_x + (gx >> 7));
+                    const uint4 m = *reinterpret_cast<const uint4*>(mb + r * 12 + 4 * ((gx >> 7) - mt0));
                     const int b = (gx & 127) >> 2;
                     v.x = (m.x >> b) & 1u ? v.x : 0.f; v.y = (m.y >> b) & 1u ? v.y : 0.f;
                     v.z = (m.z >> b) & 1u ? v.z : 0.f; v.w = (m.w >> b) & 1u ? v.w : 0.f;
@@ -214,23 +220,28 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 
         // ---- H pass: tmp[r][o] = sum_t wreg[t] * in[r][hbase + t] -------------------------------
         {
+            // 4 rows per iteration, two partial sums per row: 8 independent FMA chains per lane
             const float* p = in + hr * G::IW + hbase;
             float* q = tmp + hr * RB_TW + 32 * hg + lane;
-#pragma unroll 2
-            for (int r = hr; r < ih; r += 2) {
-                float acc = wreg[0] * p[0];
+            for (int r = hr; r < ih; r += 8) {
+                float e[4], o[4];
 #pragma unroll
-                for (int t = 1; t < BT; ++t) acc = fmaf(wreg[t], p[t], acc);
-                *q = acc;
-                p += 2 * G::IW; q += 2 * RB_TW;
+                for (int k = 0; k < 4; ++k) { e[k] = wreg[0] * p[2 * k * G::IW]; o[k] = wreg[1] * p[2 * k * G::IW + 1]; }
+#pragma unroll
+                for (int t = 2; t < BT; t += 2)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        e[k] = fmaf(wreg[t], p[2 * k * G::IW + t], e[k]);
+                        o[k] = fmaf(wreg[t + 1], p[2 * k * G::IW + t + 1], o[k]);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[2 * k * RB_TW] = e[k] + o[k];     // rows past ih land in spare rows
+                p += 8 * G::IW; q += 8 * RB_TW;
             }
         }
         __syncthreads();
         // `in` is dead: prefetch the next plane's tile while the V pass runs
-        if (tid == 0 && n + gridDim.z < a.N) {
-            mbar_expect_tx(&full, G::IW * G::IH * sizeof(float));
-            tma_load_3d(in, &tmap, xs, ys, n + gridDim.z, &full);
-        }
+        if (tid == 0 && n + gridDim.z < a.N) request(n + gridDim.z);
 
         // ---- V pass: rows (2p, 2p+1) x 4 columns per lane from one shared window of tmp -----------
         {
@@ -289,18 +300,19 @@ static inline bool rb_ok(int H, int W, int Hm, int Wm, int N) {
 }
 
 // Window size: the band of A = U D / A^T is at most floor(3 n / nm) + 6 entries; made regular over
-// 32 lanes (H pass) or shared by a row pair (V pass) it needs floor(3 n / nm) + 7
+// 32 lanes (H pass) or shared by a row pair (V pass) it needs floor(3 n / nm) + 7 (8 when n <= nm)
 // (checked over geometries in tests/test_host_cpu.py::test_resize_band_bound).
 static inline int rb_band(int H, int W, int Hm, int Wm) {
     const float s = fmaxf((float)H / (float)Hm, (float)W / (float)Wm);
-    const int need = (int)floorf(3.f * s + 1e-3f) + 7;
+    const int fl = (int)floorf(3.f * s + 1e-3f);
+    const int need = fl <= 2 ? 8 : fl + 7;
     return need <= 8 ? 8 : (need <= 10 ? 10 : (need <= 12 ? 12 : 14));
 }
 
 static inline RBAxis rb_axis(int n, int nm) { return RBAxis{n, nm, (float)n / (float)nm, (float)nm / (float)n}; }
 
 template <int BT, int DIR>
-static int rb_launch(const RBArgs& a, const CUtensorMap& tm, cudaStream_t st, const char* who) {
+static int rb_launch(const RBArgs& a, const CUtensorMap& tm, const CUtensorMap& tmm, cudaStream_t st, const char* who) {
     const size_t smem = RBGeom<BT>::smem;
     cudaError_t e = cudaFuncSetAttribute(rb_banded_kernel<BT, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
@@ -308,7 +320,7 @@ static int rb_launch(const RBArgs& a, const CUtensorMap& tm, cudaStream_t st, co
     const int pos = a.tiles_x * a.tiles_y;
     int gz = (2 * sm_count()) / pos;
     gz = gz < 1 ? 1 : (gz > a.N ? a.N : gz);
-    rb_banded_kernel<BT, DIR><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, a);
+    rb_banded_kernel<BT, DIR><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, tmm, a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
 }
@@ -361,16 +373,21 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
     a.loy = reinterpret_cast<const int*>(ty); a.wy = ty + H;
     a.N = N; a.H = H; a.W = W; a.tiles_x = (W + RB_TW - 1) / RB_TW; a.tiles_y = (H + RB_TH - 1) / RB_TH;
     a.overflow = reinterpret_cast<int*>(const_cast<float*>(by + rb_axis_words(H, BT)));
-    CUtensorMap tm{};
+    CUtensorMap tm{}, tmm{};
+    int rc = 0;
     cudaStream_t st = (cudaStream_t)stream;
 #define RB_CASE(B)                                                                                                  \
     case B:                                                                                                         \
-        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh,                 \
-                                 RBGeom<B>::IW, RBGeom<B>::IH)) {                                                   \
+        rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh, RBGeom<B>::IW,          \
+                         RBGeom<B>::IH);                                                                            \
+        if (!rc && dir == 1 && mask)                                                                                \
+            rc = tmap_planes(&tmm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, mask, N, H, 4 * a.tiles_x,                    \
+                             int64_t(H) * 4 * a.tiles_x, 4 * a.tiles_x, 12, RBGeom<B>::IH);                         \
+        if (rc) {                                                                                                   \
             set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, rc);                                           \
             return WM_E_ARG;                                                                                        \
         }                                                                                                           \
-        return dir == 0 ? rb_launch<B, 0>(a, tm, st, who) : rb_launch<B, 1>(a, tm, st, who);
+        return dir == 0 ? rb_launch<B, 0>(a, tm, tmm, st, who) : rb_launch<B, 1>(a, tm, tmm, st, who);
     switch (BT) {
         RB_CASE(8)
         RB_CASE(10)
