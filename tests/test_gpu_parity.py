@@ -549,3 +549,125 @@ def test_combined_matches_reference_choices():
     for i, nm in enumerate(("JpegCompression", "G_Blur", "MiddleBlur5", "Gaussian", "Resize")):
         y = c2(x, id=i)
         assert c2.name == nm and y.shape == x.shape
+
+
+# ==================================================== round-1 additions: TMA stencils / fused resize
+def _resize_tables_overflow():
+    """1 if any fused-resize launch so far lost a band weight (window too small) — must stay 0."""
+    return max((int(t[-4:].view(torch.int32)[0]) for t in WF._RESIZE_TABLES.values()), default=0)
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1080, 1920), (2, 3, 540, 964), (1, 1, 70, 132), (3, 2, 64, 128)])
+def test_tma_stencils_at_frame_sizes(shape):
+    """BASELINE config 3 shapes (1080p frames) and ragged tiles through the TMA-fed blur / median kernels."""
+    x, g = rnd(shape, 31), rnd(shape, 32)
+    c = shape[1]
+    for k in (3, 7):
+        y, gx = fwd_bwd(wmattack.GaussianBlur(k, channels=c), x, g)
+        yo, go = oracle_fwd_bwd(lambda t: O.gaussian_blur(t, k), x, g)
+        assert md(y, yo) <= 1e-6 and md(gx, go) <= 1e-6
+    for k in (3, 5):
+        y, gx = fwd_bwd(wmattack.MiddleBlur(k), x, g)
+        yo, idx = O.median_blur(x, k, return_index=True)
+        assert torch.equal(y, yo)                                          # selection: bit-exact
+        assert torch.equal(gx, O.median_blur_backward(g, idx, k))         # routing: bit-exact
+
+
+def test_stencils_and_resize_on_clip_slices():
+    """The trainers pass x[:, :, t] slices of a [B,3,T,H,W] clip (models/IRNcrop_model.py:362-366):
+    plane strides go straight into the tensor maps, no .contiguous()."""
+    clip = rnd((2, 3, 4, 48, 160), 33)
+    g = rnd((2, 3, 48, 160), 34)
+    for t in (0, 3):
+        xs = clip[:, :, t]
+        xd = clip.to(DEV)[:, :, t]
+        assert not xd.is_contiguous()
+        for layer, ref in ((wmattack.GaussianBlur(), lambda v: O.gaussian_blur(v, 3)),
+                           (wmattack.MiddleBlur(3), lambda v: O.median_blur(v, 3)),
+                           (lambda v: wmattack.Resize()(v, resize_ratio=0.8), lambda v: O.resize(v, 0.8))):
+            xx = xd.detach().requires_grad_(True)
+            y = layer(xx)
+            y.backward(g.to(DEV))
+            yo, go = oracle_fwd_bwd(ref, xs.contiguous(), g)
+            assert md(y, yo) <= 2e-5
+            assert float(((xx.grad.cpu().double() - go).abs() > 2e-5).float().mean()) < 2e-3
+    assert _resize_tables_overflow() == 0
+
+
+@pytest.mark.parametrize("mode", ("bicubic", "bilinear"))
+def test_fused_resize_geometry_sweep(mode):
+    """Every window size (8/10/12/14), ragged tiles, borders, both axes with different ratios."""
+    for (h, w), seed in (((70, 132), 41), ((64, 128), 42), ((130, 260), 43), ((33, 36), 44)):
+        x, g = rnd((2, 2, h, w), seed), rnd((2, 2, h, w), seed + 100)
+        for r in (0.46, 0.5, 0.58, 0.66, 0.75, 0.9, 1.0, 1.1, 1.5, 2.0, 2.19):
+            mid = (max(int(r * h), 1), max(int(r * w), 1))
+            in_range = all(0.45 <= m / n <= 2.2 for m, n in zip(mid, (h, w)))     # else: two-call fallback
+            assert WF._lib.load().wm_resize_is_fused(h, w, mid[0], mid[1], 4) == int(in_range)
+            xx = x.to(DEV).requires_grad_(True)
+            y = WF.resize_roundtrip(xx, mid, mode)
+            y.backward(g.to(DEV))
+            # Comparators: the reference's own op, torch fp32 F.interpolate (noise_layers/resize.py:38-47),
+            # (1) on the CPU and (2) on this GPU — the trainers run it on CUDA.  ATen evaluates the source
+            # coordinate scale*(o+0.5)-0.5 in fp32, so at non-dyadic scales its taps carry an error of
+            # ~ulp(coordinate) that differs between builds (FMA contraction): two correct fp32
+            # implementations agree only to that — the CPU bound scales with it, the same-device one is tight.
+            Fi = torch.nn.functional.interpolate
+            coord_ulp = 2.0 ** (np.floor(np.log2(max(h, w) * max(1.0, 1.0 / r))) - 23)
+            for dev, tol_y, tol_g in (("cpu", 1e-5 + 2 * coord_ulp, 2e-5 + 2 * coord_ulp), (DEV, 1e-5, 2e-5)):
+                xo = x.detach().clone().to(dev).requires_grad_(True)
+                pre = Fi(Fi(xo, size=list(mid), mode=mode), size=[h, w], mode=mode)
+                yo = pre.clamp(0, 1)
+                yo.backward(g.to(dev))
+                assert md(y, yo) <= tol_y, (h, w, r, dev)
+                # gradient: where a pre-clamp value is within fp32 noise of a clamp bound the
+                # pass-through decision of ANY fp32 implementation is arbitrary: bound the fraction
+                pd = pre.detach()
+                frag = bool(((pd.abs() < tol_y) | ((pd - 1).abs() < tol_y)).any())
+                err = (xx.grad.cpu().double() - xo.grad.cpu().double()).abs()
+                if not frag:
+                    assert float(err.max()) <= tol_g, (h, w, r, dev)
+                else:
+                    assert float((err > tol_g).float().mean()) < 5e-3, (h, w, r, dev)
+    assert _resize_tables_overflow() == 0
+
+
+def test_fused_resize_full_size_adjoint_and_determinism():
+    """BASELINE config-2 size: with the clamp inactive the layer is linear, so <A x, g> = <x, A^T g>;
+    the adjoint is a gather (no atomics), so two runs are bit-identical."""
+    gen = torch.Generator(DEV).manual_seed(5)
+    x = (0.4 + 0.2 * torch.rand(64, 3, 512, 512, device=DEV, generator=gen)).requires_grad_(True)
+    g = torch.rand(64, 3, 512, 512, device=DEV, generator=gen)
+    for r in (0.5, 0.75, 1.25, 1.5):
+        x.grad = None
+        y = wmattack.Resize()(x, resize_ratio=r)
+        assert float(y.min()) > 0 and float(y.max()) < 1              # clamp inactive
+        y.backward(g)
+        g1 = x.grad.clone()
+        lhs = float((y.double() * g.double()).sum())
+        rhs = float((x.detach().double() * g1.double()).sum())
+        assert abs(lhs - rhs) <= 1e-6 * abs(lhs)
+        x.grad = None
+        wmattack.Resize()(x, resize_ratio=r).backward(g)
+        assert torch.equal(g1, x.grad)
+    assert _resize_tables_overflow() == 0
+
+
+def test_diffjpeg_4k_quality_sweep_mcu_independence():
+    """BASELINE config 5 shape (one 4K frame per call here): every 16x16 MCU is independent, so any
+    MCU-aligned crop of the 4K result equals the oracle run on that crop alone."""
+    gen = torch.Generator(DEV).manual_seed(7)
+    x = torch.rand(1, 3, 2160, 3840, device=DEV, generator=gen)
+    g = torch.rand(1, 3, 2160, 3840, device=DEV, generator=gen)
+    for q in (10, 50, 95):
+        xx = x.clone().requires_grad_(True)
+        m = wmattack.DiffJPEG(True, 2160, 3840, quality=q)
+        y = m(xx)
+        y.backward(g)
+        assert torch.isfinite(y).all() and float(y.min()) >= 0 and float(y.max()) <= 1
+        for (r0, c0) in ((0, 0), (1088, 2048), (2160 - 64, 3840 - 96)):
+            xc = x[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double().requires_grad_(True)
+            yo = O.diffjpeg(xc, q)
+            yo.backward(g[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double())
+            assert md(y[:, :, r0:r0 + 64, c0:c0 + 96], yo) <= 1e-5
+            err = (xx.grad[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double() - xc.grad).abs()
+            assert float((err > grad_tol(q)).float().mean()) < 1e-3

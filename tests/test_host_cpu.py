@@ -227,3 +227,41 @@ def test_two_rank_plumbing_on_gloo():
         assert spans == [(0, 7), (7, 13)]
         assert offs[0][0] == offs[1][0] and offs[0][1] != offs[1][1]      # same seed, disjoint Philox sub-streams
         assert mx == 11.0                                                  # max over ranks
+
+
+def test_resize_band_bound():
+    """The fused Resize kernel keeps, per lane, a register window of 8/10/12/14 taps of the banded
+    operator A = U D (and of A^T).  Mirror of csrc/resize_fused.cu::rb_band: the window must hold the
+    band made regular over 32 consecutive outputs (H pass) and the band shared by a row pair (V pass)."""
+    import math
+    import numpy as np
+    from oracle import attack_oracle as O
+
+    def window(n, nm):
+        fl = math.floor(3.0 * np.float32(n) / np.float32(nm) + 1e-3)
+        need = 8 if fl <= 2 else fl + 7
+        return 8 if need <= 8 else 10 if need <= 10 else 12 if need <= 12 else 14
+
+    for n in (20, 64, 100, 512):
+        for ratio in (0.45, 0.5, 0.53, 0.6, 0.667, 0.75, 0.8, 0.99, 1.0, 1.01, 1.25, 1.5, 2.0, 2.2):
+            nm = int(ratio * n)
+            if nm < 1 or not (0.45 <= nm / n <= 2.2):
+                continue
+            for mode in ("bicubic", "bilinear"):
+                A = (O.interp_matrix(nm, n, mode) @ O.interp_matrix(n, nm, mode)).numpy()
+                for M in (A, A.T):
+                    nz = [np.nonzero(r)[0] for r in M]      # a source index bilinear never samples has an empty row of A^T
+                    keep = [k for k, i in enumerate(nz) if len(i)]
+                    if len(keep) < len(nz):                 # empty rows: zero weights, any in-range start works
+                        for k in range(len(nz)):
+                            if not len(nz[k]):
+                                nb = min(keep, key=lambda j: abs(j - k))
+                                nz[k] = np.array([min(max(nz[nb][0] + (k - nb), 0), n - 1)])
+                    lo = np.array([i[0] for i in nz]); hi = np.array([i[-1] for i in nz])
+                    need = 0
+                    for g0 in range(0, n, 32):            # H pass: regular starts base + lane
+                        l, h = lo[g0:g0 + 32], hi[g0:g0 + 32]
+                        base = (l - np.arange(len(l))).min()
+                        need = max(need, int((h - (base + np.arange(len(l))) + 1).max()))
+                    pair = int((np.maximum(hi[1:], hi[:-1]) - lo[:-1] + 1).max()) if n > 1 else 1
+                    assert max(need, pair) <= window(n, nm), (n, nm, mode, need, pair, window(n, nm))

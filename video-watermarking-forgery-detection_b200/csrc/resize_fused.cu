@@ -80,20 +80,32 @@ __global__ void rb_fwd_tables_kernel(RBAxis ax, int BT, int* __restrict__ lo, fl
 }
 
 // adjoint rows: for input index i the outputs o with A[o][i] != 0 form a contiguous range
+__device__ __forceinline__ int rb_first_output(int n, int BT, const int* __restrict__ flo, const float* __restrict__ fw, int i) {
+    for (int o = max(0, i - 2 * BT - 8); o <= min(n - 1, i + 2 * BT + 8); ++o) {
+        const int c = i - flo[o];
+        if (c >= 0 && c < BT && fw[int64_t(o) * BT + c] != 0.f) return o;
+    }
+    return -1;
+}
+
 __global__ void rb_adj_tables_kernel(int n, int BT, const int* __restrict__ flo, const float* __restrict__ fw,
                                      int* __restrict__ lo, float* __restrict__ w) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int first = -1;
     for (int j = 0; j < BT; ++j) w[int64_t(i) * BT + j] = 0.f;
-    for (int o = max(0, i - 2 * BT - 8); o <= min(n - 1, i + 2 * BT + 8); ++o) {
-        const int c = i - flo[o];
-        if (c < 0 || c >= BT) continue;
-        const float v = fw[int64_t(o) * BT + c];
-        if (first < 0) { if (v == 0.f) continue; first = o; }
-        if (o - first < BT) w[int64_t(i) * BT + (o - first)] = v;
+    int first = rb_first_output(n, BT, flo, fw, i);
+    if (first >= 0) {
+        for (int o = first; o < min(first + BT, n); ++o) {
+            const int c = i - flo[o];
+            if (c >= 0 && c < BT) w[int64_t(i) * BT + (o - first)] = fw[int64_t(o) * BT + c];
+        }
+    } else {
+        // a source index no output samples (bilinear downsampling skips some): all-zero row; keep the
+        // band starts non-decreasing by inheriting the start of the nearest sampled index below
+        for (int k = i - 1; k >= 0 && first < 0; --k) first = rb_first_output(n, BT, flo, fw, k);
+        if (first < 0) first = 0;
     }
-    lo[i] = first < 0 ? min(i, n - 1) : first;
+    lo[i] = first;
 }
 
 // ---------------------------------------------------------------------------------------------
