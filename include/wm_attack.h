@@ -201,6 +201,26 @@ int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, i
 int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
                   int mode, const float* tables, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Neighbours of the attack layer in the trainers' step (SURVEY 8f "next" rows).
+ *
+ * Post-attack epilogue (models/IRNp_model.py:674-680):
+ *   out = Quantization( x + (clamp(sim, 0, 1) - x).detach() )      one pass instead of five;
+ *   `out` may be a slice of the K-way batch, which removes the torch.cat.  Bit-identical values
+ *   (same fp32 operation order).  The backward is the identity on x (straight-through), so
+ *   the K slices of a bank reduce with wm_slice_sum: out[i] = sum_k g[k*n + i].
+ * Tamper / splice (models/IRNcrop_model.py:348, models/IRNp_model.py:600):
+ *   out = a * (1 - mask) + b * mask,  a, b: [B, C, H, W], mask: [B, 1, H, W], H*W % 4 == 0.
+ *   bwd: ga = gy * (1 - mask), gb = gy * mask (either may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
+                           void* stream);
+int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream);
+int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out, int64_t B, int C, int64_t hw,
+                  void* stream);
+int wm_splice_bwd(const float* gy, const float* mask, float* ga, float* gb, int64_t B, int C, int64_t hw,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -671,3 +671,49 @@ def test_diffjpeg_4k_quality_sweep_mcu_independence():
             assert md(y[:, :, r0:r0 + 64, c0:c0 + 96], yo) <= 1e-5
             err = (xx.grad[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double() - xc.grad).abs()
             assert float((err > grad_tol(q)).float().mean()) < 1e-3
+
+
+# ======================================================= SURVEY 8f "next" rows: epilogue, bank, splice
+def test_attack_epilogue_bank_and_splice_match_the_trainer_arithmetic():
+    """models/IRNp_model.py:609-680 (8-way attack, clamp, straight-through, Quantization) and
+    models/IRNcrop_model.py:348 (splice), restated with plain torch ops on the CPU: values are
+    bit-identical, gradients are the straight-through identities."""
+    x, prev = rnd((2, 3, 40, 64), 51), rnd((2, 3, 40, 64), 52)
+    mask = (rnd((2, 1, 40, 64), 53) > 0.88).float()
+    g = rnd((2, 3, 40, 64), 54)
+    # splice
+    a = x.to(DEV).requires_grad_(True); b = prev.to(DEV).requires_grad_(True)
+    out = wmattack.Splice()(a, b, mask.to(DEV))
+    out.backward(g.to(DEV))
+    ac = x.clone().requires_grad_(True); bc = prev.clone().requires_grad_(True)
+    ref = ac * (1 - mask) + bc * mask
+    ref.backward(g)
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    assert torch.equal(a.grad.cpu(), ac.grad) and torch.equal(b.grad.cpu(), bc.grad)
+    # epilogue on an attacked batch that leaves [0,1]
+    sim = (x + 0.6 * (rnd((2, 3, 40, 64), 55) - 0.5)) * 1.2 - 0.1
+    xx = x.to(DEV).requires_grad_(True)
+    y = wmattack.AttackEpilogue()(xx, sim.to(DEV))
+    y.backward(g.to(DEV))
+    xc = x.clone().requires_grad_(True)
+    att = xc + (torch.clamp(sim, 0, 1) - xc).detach()
+    refq = (att * 255.).round() / 255.                        # Quant.forward, models/modules/Quantization.py:9
+    assert torch.equal(y.detach().cpu(), refq.detach())
+    assert torch.equal(xx.grad.cpu(), g)                       # identity (Quant.backward + straight-through)
+    # K-way bank: same values as cat([...]) of the per-layer epilogues, gradient = sum over the K slices
+    np.random.seed(3)
+    layers = [wmattack.Resize(), wmattack.JpegMask(50), wmattack.MiddleBlur(3), wmattack.GaussianBlur(), wmattack.Identity()]
+    bank = wmattack.AttackBank(layers)
+    xx = x.to(DEV).requires_grad_(True)
+    np.random.seed(3)
+    yb = bank(xx)
+    assert yb.shape == (10, 3, 40, 64) and bank.names[1] == "JpegMask50"
+    gk = rnd((10, 3, 40, 64), 56)
+    yb.backward(gk.to(DEV))
+    np.random.seed(3)
+    parts = []
+    for layer in layers:
+        s = layer(x.to(DEV))
+        parts.append(wmattack.AttackEpilogue()(x.to(DEV), s))
+    assert torch.equal(yb.detach(), torch.cat(parts, 0))
+    assert md(xx.grad, gk.view(5, 2, 3, 40, 64).sum(0)) <= 1e-6

@@ -189,6 +189,66 @@ __global__ void __launch_bounds__(256) cropout_kernel(const float* __restrict__ 
     }
 }
 
+// ---- post-attack epilogue (models/IRNp_model.py:674-680) --------------------------------------
+//   sim = clamp(attack(x), 0, 1);  attacked = x + (sim - x).detach();  out = Quantization(attacked)
+// = four elementwise torch passes + a torch.cat in the reference; here one pass that can write
+// straight into a slice of the K-way batch.  Same fp32 operation order (no FMA contraction), so the
+// values are bit-identical to the reference's.  Backward is the identity on x (straight-through).
+__device__ __forceinline__ float epilogue1(float x, float s, int clamp01, int quant) {
+    if (clamp01) s = fminf(fmaxf(s, 0.f), 1.f);
+    float v = __fadd_rn(x, __fsub_rn(s, x));
+    if (quant) v = __fdiv_rn(rintf(__fmul_rn(v, 255.f)), 255.f);
+    return v;
+}
+__global__ void __launch_bounds__(256) attack_epilogue_kernel(const float* __restrict__ x, const float* __restrict__ sim,
+                                                              float* __restrict__ out, int64_t n, int clamp01, int quant) {
+    WM_EW_LOOP(i) {
+        const float4 a = ld4(x, i, n), b = ld4(sim, i, n);
+        st4(out, i, n, make_float4(epilogue1(a.x, b.x, clamp01, quant), epilogue1(a.y, b.y, clamp01, quant),
+                                   epilogue1(a.z, b.z, clamp01, quant), epilogue1(a.w, b.w, clamp01, quant)));
+    }
+}
+// out[i] = sum_k g[k * n + i]   (straight-through backward of the K-way bank: every slice passes gy to x)
+__global__ void __launch_bounds__(256) slice_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n, int K) {
+    WM_EW_LOOP(i) {
+        float4 acc = ld4(g, i, n);
+        for (int k = 1; k < K; ++k) {
+            const float4 v = ld4(g + int64_t(k) * n, i, n);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        st4(out, i, n, acc);
+    }
+}
+
+// ---- tamper / splice (models/IRNcrop_model.py:348, models/IRNp_model.py:600) ---------------------
+//   out = a * (1 - m) + b * m,  m: [B, 1, H, W] broadcast over the C channels of a, b: [B, C, H, W]
+// bwd: ga = gy * (1 - m), gb = gy * m.  hw % 4 == 0 keeps a float4 inside one plane.
+template <bool BWD>
+__global__ void __launch_bounds__(256) splice_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                     const float* __restrict__ m, float* __restrict__ o1, float* __restrict__ o2,
+                                                     int64_t n, int64_t hw, int C) {
+    WM_EW_LOOP(i) {
+        const int64_t plane = i / hw, bi = plane / C;
+        const float4 mm = *reinterpret_cast<const float4*>(m + bi * hw + (i - plane * hw));
+        const float4 va = *reinterpret_cast<const float4*>(a + i);
+        const float mv[4] = {mm.x, mm.y, mm.z, mm.w}, av[4] = {va.x, va.y, va.z, va.w};
+        float r1[4], r2[4];
+        if (!BWD) {
+            const float4 vb = *reinterpret_cast<const float4*>(b + i);
+            const float bv[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                r1[k] = __fadd_rn(__fmul_rn(av[k], __fsub_rn(1.f, mv[k])), __fmul_rn(bv[k], mv[k]));
+            *reinterpret_cast<float4*>(o1 + i) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { r1[k] = __fmul_rn(av[k], __fsub_rn(1.f, mv[k])); r2[k] = __fmul_rn(av[k], mv[k]); }
+            if (o1) *reinterpret_cast<float4*>(o1 + i) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+            if (o2) *reinterpret_cast<float4*>(o2 + i) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+        }
+    }
+}
+
 static inline unsigned ew_grid(int64_t n_vec) {
     const int64_t want = (n_vec + 255) / 256;
     const int64_t cap = int64_t(sm_count()) * 16;
@@ -311,5 +371,46 @@ extern "C" int wm_cropout_fwd(const float* image, const float* cover, float* y, 
     if (total <= 0) return WM_OK;
     cropout_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, cover, y, total, H, W, h0, h1, w0, w1);
     WM_LAUNCH_CHECK("wm_cropout_fwd");
+    return WM_OK;
+}
+
+extern "C" int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
+                                      void* stream) {
+    WM_REQUIRE(x && sim && out, WM_E_NULL, "wm_attack_epilogue_fwd: null pointer");
+    EW_ALIGN_CHECK("wm_attack_epilogue_fwd", x, sim, out);
+    if (n <= 0) return WM_OK;
+    attack_epilogue_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, sim, out, n, clamp01, quantize);
+    WM_LAUNCH_CHECK("wm_attack_epilogue_fwd");
+    return WM_OK;
+}
+extern "C" int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream) {
+    WM_REQUIRE(g && out, WM_E_NULL, "wm_slice_sum: null pointer");
+    WM_REQUIRE(K >= 1 && n % 4 == 0, WM_E_ARG, "wm_slice_sum: K >= 1 and n %% 4 == 0 required (K=%d n=%lld)", K, (long long)n);
+    EW_ALIGN_CHECK("wm_slice_sum", g, out);
+    if (n <= 0) return WM_OK;
+    slice_sum_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(g, out, n, K);
+    WM_LAUNCH_CHECK("wm_slice_sum");
+    return WM_OK;
+}
+extern "C" int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out, int64_t B, int C, int64_t hw,
+                             void* stream) {
+    WM_REQUIRE(a && b && mask && out, WM_E_NULL, "wm_splice_fwd: null pointer");
+    WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_fwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
+    EW_ALIGN_CHECK("wm_splice_fwd", a, b, mask, out);
+    const int64_t n = B * C * hw;
+    if (n <= 0) return WM_OK;
+    splice_kernel<false><<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, mask, out, nullptr, n, hw, C);
+    WM_LAUNCH_CHECK("wm_splice_fwd");
+    return WM_OK;
+}
+extern "C" int wm_splice_bwd(const float* gy, const float* mask, float* ga, float* gb, int64_t B, int C, int64_t hw,
+                             void* stream) {
+    WM_REQUIRE(gy && mask && (ga || gb), WM_E_NULL, "wm_splice_bwd: null pointer");
+    WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_bwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
+    EW_ALIGN_CHECK("wm_splice_bwd", gy, mask, ga, gb);
+    const int64_t n = B * C * hw;
+    if (n <= 0) return WM_OK;
+    splice_kernel<true><<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask, ga, gb, n, hw, C);
+    WM_LAUNCH_CHECK("wm_splice_bwd");
     return WM_OK;
 }

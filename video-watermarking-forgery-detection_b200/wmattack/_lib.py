@@ -52,6 +52,10 @@ SIGNATURES = {
     "wm_cropout_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, i32, i32, vp],
     "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
     "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
+    "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
+    "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],
+    "wm_splice_fwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
+    "wm_splice_bwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
     "wm_resize_tables": [c_f32p, i32, i32, i32, i32, i32, vp],
     "wm_resize_fwd": [c_f32p, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, vp],
     "wm_resize_bwd": [c_f32p, vp, c_f32p, i32, i32, i32, i32, i32, i32, c_f32p, vp],

@@ -626,3 +626,96 @@ def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
         return _ResizeFusedFn.apply(x, mid_hw, _MODES[mode])
     mid = interpolate(x, mid_hw, mode)
     return interpolate(mid, (h, w), mode, clamp=True)
+
+
+# --------------------------------------------------------------------------------------
+# neighbours of the attack layer: post-attack epilogue, K-way bank, tamper/splice
+# --------------------------------------------------------------------------------------
+
+class _EpilogueFn(torch.autograd.Function):
+    """out = Quantization(x + (clamp(sim,0,1) - x).detach())  (models/IRNp_model.py:674-680).
+    Straight-through: d out / d x = I, nothing flows into `sim`."""
+
+    @staticmethod
+    def forward(ctx, x, sim, clamp, quantize, out):
+        x = _flat(x, "attack epilogue")
+        sim = _flat(sim.detach(), "attack epilogue")
+        if sim.shape != x.shape:
+            raise ValueError(f"attack epilogue: shape mismatch {tuple(x.shape)} vs {tuple(sim.shape)}")
+        if out is None:
+            out = torch.empty_like(x)
+        elif out.shape != x.shape or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("attack epilogue: `out` must be a contiguous fp32 tensor (or slice) of x's shape")
+        _lib.call("wm_attack_epilogue_fwd", x.data_ptr(), sim.data_ptr(), out.data_ptr(), x.numel(), int(clamp),
+                  int(quantize), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy, None, None, None, None
+
+
+def attack_epilogue(x, sim, clamp: bool = True, quantize: bool = True, out=None):
+    return _EpilogueFn.apply(x, sim, clamp, quantize, out)
+
+
+class _BankFn(torch.autograd.Function):
+    """K attacked variants of the same batch, each finished by the epilogue and written straight
+    into its slice of one [K*B, C, H, W] tensor (no torch.cat).  Backward: gx = sum_k gy_k."""
+
+    @staticmethod
+    def forward(ctx, x, clamp, quantize, *sims):
+        x = _flat(x, "attack bank")
+        k = len(sims)
+        out = torch.empty((k * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+        n = x.numel()
+        for i, sim in enumerate(sims):
+            sim = _flat(sim.detach(), "attack bank")
+            _lib.call("wm_attack_epilogue_fwd", x.data_ptr(), sim.data_ptr(), out.data_ptr() + 4 * n * i, n, int(clamp),
+                      int(quantize), _stream())
+        ctx.meta = (k, tuple(x.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, shape = ctx.meta
+        gy = _flat(gy, "attack bank backward")
+        gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
+        _lib.call("wm_slice_sum", gy.data_ptr(), gx.data_ptr(), gx.numel(), k, _stream())
+        return (gx, None, None) + (None,) * k
+
+
+def attack_bank(x, sims, clamp: bool = True, quantize: bool = True):
+    return _BankFn.apply(x, clamp, quantize, *sims)
+
+
+class _SpliceFn(torch.autograd.Function):
+    """out = a * (1 - mask) + b * mask, mask [B,1,H,W] broadcast over channels
+    (models/IRNcrop_model.py:348)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mask):
+        a = _flat(a, "splice"); b = _flat(b, "splice"); mask = _flat(mask, "splice")
+        bsz, c, h, w = a.shape
+        if b.shape != a.shape or mask.shape != (bsz, 1, h, w):
+            raise ValueError(f"splice: expected b {tuple(a.shape)} and mask {(bsz, 1, h, w)}, got {tuple(b.shape)}, {tuple(mask.shape)}")
+        out = torch.empty_like(a)
+        _lib.call("wm_splice_fwd", a.data_ptr(), b.data_ptr(), mask.data_ptr(), out.data_ptr(), bsz, c, h * w, _stream())
+        ctx.save_for_backward(mask)
+        ctx.shape = (bsz, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        (mask,) = ctx.saved_tensors
+        bsz, c, h, w = ctx.shape
+        gy = _flat(gy, "splice backward")
+        ga = torch.empty_like(gy) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(gy) if ctx.needs_input_grad[1] else None
+        if ga is not None or gb is not None:
+            _lib.call("wm_splice_bwd", gy.data_ptr(), mask.data_ptr(), _ptr(ga), _ptr(gb), bsz, c, h * w, _stream())
+        return ga, gb, None
+
+
+def splice(a, b, mask):
+    return _SpliceFn.apply(a, b, mask)

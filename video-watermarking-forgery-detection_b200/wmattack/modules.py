@@ -586,3 +586,46 @@ class Cropout(nn.Module):
         if box is None:
             box = Crop.get_random_rectangle_inside(self, image.shape, self.height_ratio, self.width_ratio)
         return F_.cropout(image, cover_image, box)
+
+
+# ---- neighbours of the attack layer in the trainers' step ------------------------
+class AttackEpilogue(nn.Module):
+    """clamp + straight-through + Quantization in one pass (models/IRNp_model.py:674-680):
+    `Quantization(x + (clamp(sim, 0, 1) - x).detach())`, bit-identical values, identity gradient to x."""
+
+    def __init__(self, clamp: bool = True, quantize: bool = True):
+        super().__init__()
+        self.clamp, self.quantize = clamp, quantize
+
+    def forward(self, x, simulated):
+        return F_.attack_epilogue(x, simulated, self.clamp, self.quantize)
+
+
+class AttackBank(nn.Module):
+    """The K-way attack of the trainers (models/IRNp_model.py:609-680; the per-frame 5-way loop of
+    models/IRNcrop_model.py:357-370): every layer attacks the SAME batch, each result is clamped,
+    made straight-through and 8-bit quantised, and the K results are concatenated on the batch axis.
+    Here each epilogue writes directly into its slice of the output (no cat, one pass per layer)."""
+
+    def __init__(self, layers: Sequence[nn.Module], clamp: bool = True, quantize: bool = True):
+        super().__init__()
+        self.list = list(layers)          # plain list, like Combined (noise_layers/combined.py:10)
+        self.clamp, self.quantize = clamp, quantize
+        self.names = []
+
+    def forward(self, x):
+        with torch.no_grad():             # straight-through: the attacks' own graphs are never needed
+            sims = []
+            self.names = []
+            for layer in self.list:
+                y = layer(x)
+                sims.append(y[0] if isinstance(y, tuple) else y)
+                self.names.append(getattr(layer, "name", type(layer).__name__))
+        return F_.attack_bank(x, sims, self.clamp, self.quantize)
+
+
+class Splice(nn.Module):
+    """`forward_image * (1 - mask) + other * mask` (models/IRNcrop_model.py:348), mask [B,1,H,W]."""
+
+    def forward(self, image, other, mask):
+        return F_.splice(image, other, mask)
