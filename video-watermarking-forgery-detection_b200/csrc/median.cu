@@ -33,6 +33,15 @@ __device__ __forceinline__ void sort3(float& a, float& b, float& c) {
 __device__ __forceinline__ float med3(float a, float b, float c) {
     return mid3(a, b, c, fmin3(a, b, c), fmax3(a, b, c));
 }
+// (a == b) as 1.0f / 0.0f (FSET.BF): lets the arg-median search accumulate match bits with FFMA on
+// the FMA pipe instead of FSETP + SEL pairs on the (half-rate, already saturated) ALU pipe
+__device__ __forceinline__ float feq(float a, float b) {
+    float d; asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d;
+}
+// code = sum_j match_j * 2^(n-1-j) (exact in fp32 for n <= 24): raster index of the FIRST match
+__device__ __forceinline__ int first_match(float code, int n) {
+    return n - 1 - ((__float_as_int(code) >> 23) - 127);
+}
 #define MD_CE(a, b) { const float lo__ = fminf(a, b); b = fmaxf(a, b); a = lo__; }
 __device__ __forceinline__ void sort5(float (&v)[5]) {
     // optimal 9-comparator network
@@ -188,11 +197,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
                                        fmin3(hi[0][c4], hi[1][c4], hi[2][c4]));
                 op[c4] = med;
                 if (WANT_IDX) {
-                    int pos = 0;
+                    float code = 0.f;
 #pragma unroll
-                    for (int j = 8; j >= 0; --j)      // window row j/3 is ring slot (r + j/3) % 3
-                        pos = (raw[(r + j / 3) % 3][c4 + j % 3] == med) ? j : pos;
-                    packed |= uint32_t(pos) << (8 * c4);
+                    for (int j = 0; j < 9; ++j)       // window row j/3 is ring slot (r + j/3) % 3
+                        code = fmaf(code, 2.f, feq(raw[(r + j / 3) % 3][c4 + j % 3], med));
+                    packed |= uint32_t(first_match(code, 9)) << (8 * c4);
                 }
             }
             if (col_ok && gy0 + r < a.H) {
@@ -280,10 +289,14 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
                 if (col_ok && gy0 + r < a.H) {
                     a.y[obase + int64_t(r) * a.W] = med;
                     if (WANT_IDX) {
-                        int pos = 0;
+                        float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
 #pragma unroll
-                        for (int j = 24; j >= 0; --j)      // window row j/5 is ring slot (u + j/5) % 5
-                            pos = (raw[(u + j / 5) % 5][j % 5] == med) ? j : pos;
+                        for (int j = 0; j < 15; ++j)       // window row j/5 is ring slot (u + j/5) % 5
+                            hi = fmaf(hi, 2.f, feq(raw[(u + j / 5) % 5][j % 5], med));
+#pragma unroll
+                        for (int j = 15; j < 25; ++j)
+                            lo = fmaf(lo, 2.f, feq(raw[(u + j / 5) % 5][j % 5], med));
+                        const int pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
                         a.idx[obase + int64_t(r) * a.W] = (uint8_t)pos;
                     }
                 }
