@@ -62,6 +62,18 @@ int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                     float* gx, int B, int H, int W,
                     float factor, const float* factor_per_sample, int rounding, void* stream);
 
+/* Training pair: the forward additionally saves 7 B/px of state — round'(q) of every luminance
+ * (dY [B,H,W]) and chroma (dC [B,2,H/2,W/2]) coefficient and the clamp code (0 outside / 1 inside /
+ * 2 on a bound) of every output value (clamp_codes [B,H,W/8], 48 bits per 8-pixel row) — and the
+ * backward runs from gy + that state alone (no x, no forward recomputation; 31 B/px each way,
+ * every rounding mode).  The layouts are private to this pair. */
+int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
+                         float* dY, float* dC, uint64_t* clamp_codes, int B, int H, int W,
+                         float factor, const float* factor_per_sample, int rounding, void* stream);
+int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
+                          const float* dY, const float* dC, const uint64_t* clamp_codes, float* gx,
+                          int B, int H, int W, void* stream);
+
 /* compress_jpeg.forward (utils/JPEG.py:279-291): rounded quantised coefficients,
  * coef_y [B, H*W/64, 8, 8], coef_cb / coef_cr [B, H*W/256, 8, 8] (block raster order). */
 int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,

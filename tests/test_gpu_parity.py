@@ -717,3 +717,23 @@ def test_attack_epilogue_bank_and_splice_match_the_trainer_arithmetic():
         parts.append(wmattack.AttackEpilogue()(x.to(DEV), s))
     assert torch.equal(yb.detach(), torch.cat(parts, 0))
     assert md(xx.grad, gk.view(5, 2, 3, 40, 64).sum(0)) <= 1e-6
+
+
+@pytest.mark.parametrize("mode", (0, 1, 3))
+def test_diffjpeg_saved_state_and_recompute_backward_agree(mode):
+    """Two backward implementations of the same chain: from 7 B/px of state saved by the forward
+    (default) and recomputed from x (`recompute_backward = True`, saves nothing)."""
+    for shape, q, seed in (((2, 3, 64, 96), 50, 61), ((1, 3, 32, 272), 90, 62), ((3, 3, 48, 48), 20, 63)):
+        x, g = rnd(shape, seed), rnd(shape, seed + 1)
+        if seed == 62:
+            x = torch.round(x * 3) / 3 * 1.2 - 0.1      # saturated, flat regions: clamp ties (code 2) occur
+            x = x.clamp(0, 1)
+        qs = torch.tensor([q, 35.0, 75.0][: shape[0]])
+        outs = []
+        for recompute in (False, True):
+            m = wmattack.DiffJPEG(True, shape[2], shape[3], quality=q, rounding=mode)
+            m.recompute_backward = recompute
+            y, gx = fwd_bwd(lambda t: m(t, quality=qs.to(DEV)), x, g)
+            outs.append((y, gx))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert md(outs[0][1], outs[1][1]) <= 2e-6

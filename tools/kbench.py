@@ -112,7 +112,10 @@ if "resize" in which:
 
 if "diffjpeg" in which:
     m = wmattack.DiffJPEG(True, H, W, quality=50)
-    fwd_bwd("diffjpeg q50", lambda t: m(t), 24, 36)
+    fwd_bwd("diffjpeg q50 (saved state)", lambda t: m(t), 24, 36)
+    m2 = wmattack.DiffJPEG(True, H, W, quality=50)
+    m2.recompute_backward = True
+    fwd_bwd("diffjpeg q50 (recompute)", lambda t: m2(t), 24, 36)
 
 if "jpeg8" in which:
     for nm, mod, bb in (("jpegcompression", wmattack.JpegCompression(dev), 24), ("jpegss50", wmattack.JpegSS(50), 36),

@@ -154,9 +154,164 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward from the state saved by wm_diffjpeg_fwd_save: gy, round'(q) and the clamp codes in,
+// gx out (31 B/px); no forward recomputation, the forward's 24-chunk scratch and occupancy.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float code_mul(float g, unsigned code) {      // 0 -> 0, 1 -> g, 2 -> g/2
+    return (code & 1u) ? g : ((code & 2u) ? 0.5f * g : 0.f);
+}
+
+__global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const DJArgs a) {
+    constexpr int NT = DJ_THREADS;
+    extern __shared__ float4 smem[];
+    float4* scr = smem + threadIdx.x;
+    const DJThread t = dj_locate(a);
+    const float* gr = a.gy + int64_t(t.b) * a.g_sb + int64_t(t.row0) * a.g_sh + t.col0;
+    const unsigned long long* cmr = a.cm + (int64_t(t.b) * a.H + t.row0) * (a.W >> 3) + (t.col0 >> 3);
+    const float* dYr = a.dY + (int64_t(t.b) * a.H + t.row0) * a.W + t.col0;
+    const int64_t Wc = a.W >> 1, plane_c = int64_t(a.H >> 1) * Wc;
+    const float* dCr = a.dC + int64_t(t.b) * 2 * plane_c + int64_t(t.mcu_y * 8 + t.by * 4) * Wc + t.mcu_x * 8 + t.bx * 4;
+
+    // ---- masked cotangent through Mi^T, chroma 2x2 sum, row DCT; one row pair per (rolled) iteration ---------------------------------
+    auto consume = [&](const RowPair& g, int rp) {
+        float gcb[4], gcr[4];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * rp + rr;
+            const unsigned long long cw = t.active ? __ldg(cmr + int64_t(r) * (a.W >> 3)) : 0ull;
+            const unsigned lo = (unsigned)cw, hi = (unsigned)(cw >> 32);
+            float gyv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned code = ((c < 4 ? lo : hi) >> (6 * (c & 3))) & 63u;
+                const float mr = code_mul(g.R[rr].v[c], code), mg = code_mul(g.G[rr].v[c], code >> 2),
+                            mb = code_mul(g.B[rr].v[c], code >> 4);
+                gyv[c] = (mr + mg) + mb;                                   // Mi[:,0] = 1
+                const float ccb = fmaf(-0.344136f, mg, 1.772f * mb);       // Mi[:,1]
+                const float ccr = fmaf(1.402f, mr, -0.714136f * mg);       // Mi[:,2]
+                if (rr == 0 && (c & 1) == 0) { gcb[c >> 1] = ccb; gcr[c >> 1] = ccr; }
+                else { gcb[c >> 1] += ccb; gcr[c >> 1] += ccr; }
+            }
+            dct8(gyv);
+            scr_store_row<NT>(scr, r, gyv);
+        }
+        scr[(SC_CB + rp) * NT] = to_f4(gcb);
+        scr[(SC_CR + rp) * NT] = to_f4(gcr);
+    };
+    {
+        RowPair A, Bp;          // one pair of loads in flight ahead of the arithmetic
+        dj_load_pair(A, gr, a.g_sh, a.g_sc, t.active);
+#pragma unroll 1
+        for (int rp = 0; rp < 4; ++rp) {
+            if (rp < 3) dj_load_pair(Bp, gr + int64_t(2 * rp + 2) * a.g_sh, a.g_sh, a.g_sc, t.active);
+            consume(A, rp);
+            A = Bp;
+        }
+    }
+
+    // ---- luminance: column DCT, times round'(q), column IDCT ----------------------------------
+#pragma unroll 1
+    for (int cg = 0; cg < 2; ++cg) {
+        float v[8][4];
+        float4 d4[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            d4[r] = t.active ? ldg128_stream(dYr + int64_t(r) * a.W + 4 * cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) f4_to(v[r], scr[(SC_Y + 2 * r + cg) * NT]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { v[r][0] *= d4[r].x; v[r][1] *= d4[r].y; v[r][2] *= d4[r].z; v[r][3] *= d4[r].w; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            idct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) scr[(SC_Y + 2 * r + cg) * NT] = to_f4(v[r]);
+    }
+
+    // ---- chroma: split DCT, times round'(q), split IDCT ---------------------------------------
+    QuadCoef qx, qy;
+    quad_coef_init(qx, t.bx);
+    quad_coef_init(qy, t.by);
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        float p[4][4];
+        float4 d4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            d4[i] = t.active ? ldg128_stream(dCr + pl * plane_c + int64_t(i) * Wc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f4_to(p[i], scr[(SC_CB + 4 * pl + i) * NT]);
+        quad_dct_rows(p, qx, 1);
+        quad_dct_cols(p, qy, 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { p[i][0] *= d4[i].x; p[i][1] *= d4[i].y; p[i][2] *= d4[i].z; p[i][3] *= d4[i].w; }
+        quad_idct_cols(p, qy, 16);
+        quad_idct_rows(p, qx, 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) scr[(SC_CB + 4 * pl + i) * NT] = to_f4(p[i]);
+    }
+
+    // ---- back through the colour transform ----------------------------------------------------
+    float* go = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
+    const int64_t plane = int64_t(a.H) * a.W;
+#pragma unroll 1
+    for (int rp = 0; rp < 4; ++rp) {
+        float gcb[4], gcr[4], tR[4], tG[4], tB[4];
+        f4_to(gcb, scr[(SC_CB + rp) * NT]);
+        f4_to(gcr, scr[(SC_CR + rp) * NT]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {      // avg-pool adjoint (/4) folded in
+            const float b4 = gcb[j] * 0.25f, r4 = gcr[j] * 0.25f;
+            tR[j] = fmaf(-0.168736f, b4, 0.5f * r4);
+            tG[j] = fmaf(-0.331264f, b4, -0.418688f * r4);
+            tB[j] = fmaf(0.5f, b4, -0.081312f * r4);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * rp + rr;
+            float gv[8];
+            scr_load_row<NT>(scr, r, gv);
+            idct8(gv);
+            f8 oR, oG, oB;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                oR.v[c] = fmaf(0.299f, gv[c], tR[c >> 1]);
+                oG.v[c] = fmaf(0.587f, gv[c], tG[c >> 1]);
+                oB.v[c] = fmaf(0.114f, gv[c], tB[c >> 1]);
+            }
+            if (t.active) {
+                float* p = go + int64_t(r) * a.W;
+                stg256(p, oR);
+                stg256(p + plane, oG);
+                stg256(p + 2 * plane, oB);
+            }
+        }
+    }
+}
+
 }  // namespace wm
 
 using namespace wm;
+
+extern "C" int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
+                                     const float* dY, const float* dC, const uint64_t* clamp_codes, float* gx,
+                                     int B, int H, int W, void* stream) {
+    if (int rc = dj_check(gy, g_sb, g_sc, g_sh, B, H, W, "wm_diffjpeg_bwd_saved(gy)")) return rc;
+    WM_REQUIRE(dY && dC && clamp_codes && gx, WM_E_NULL, "wm_diffjpeg_bwd_saved: null pointer");
+    WM_REQUIRE(aligned(gx, 32) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
+               "wm_diffjpeg_bwd_saved: gx must be 32-byte, dY/dC 16-byte, clamp_codes 8-byte aligned");
+    DJArgs a = dj_args(B, H, W, 1.f, nullptr);
+    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = gx;
+    a.dY = const_cast<float*>(dY); a.dC = const_cast<float*>(dC);
+    a.cm = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(clamp_codes));
+    const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
+    return dj_launch(diffjpeg_bwd_saved_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd_saved");
+}
+
 
 extern "C" int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                                const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, float* gx,

@@ -101,6 +101,10 @@ struct DJArgs {
     const float* gy; int64_t g_sb, g_sc, g_sh;
     float* out;                 // y (fwd) or gx (bwd), dense NCHW
     float* coef_y; float* coef_cb; float* coef_cr;  // compress / decompress
+    // state saved by the forward for the backward (wm_diffjpeg_fwd_save / wm_diffjpeg_bwd_saved):
+    float* dY;                  // [B, H, W]        round'(q) of the luminance coefficient at [8i+u, 8j+v]
+    float* dC;                  // [B, 2, H/2, W/2] round'(q) of Cb, Cr (per-thread quadrant order)
+    unsigned long long* cm;     // [B, H, W/8]      clamp codes of one 8-pixel row: 2 bits x (8 px x RGB)
     int B, H, W;
     int mcu_w, mcu_per_img; int64_t n_mcu;
     float factor; const float* factor_ps;
@@ -236,6 +240,67 @@ __device__ __forceinline__ void dj_luma_columns(float4* scr, float f) {
     }
 }
 
+// Phase 2 of the state-saving forward: as dj_luma_columns<ROUND, false, ...> but round'(q) goes
+// straight to global memory (two 16-byte stores per block row; the halves of a 32-byte sector are
+// written by the two column groups back to back and merge in L2).
+template <int ROUND, int NT>
+__device__ __forceinline__ void dj_luma_columns_save(float4* scr, float f, float* dY, int64_t W, bool active) {
+#pragma unroll 1
+    for (int cg = 0; cg < 2; ++cg) {
+        float v[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) f4_to(v[r], scr[(SC_Y + 2 * r + cg) * NT]);
+        float d[8][4];
+        const float* tab = cTY + 4 * cg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float tf = tab[u * 8 + j] * f;
+                const float q = div_by_recip(v[u][j], tf, fast_rcp(tf));
+                d[u][j] = round_grad<ROUND>(q);
+                v[u][j] = round_fwd<ROUND>(q) * tf;
+            }
+            idct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            scr[(SC_Y + 2 * r + cg) * NT] = to_f4(v[r]);
+            if (active) *reinterpret_cast<float4*>(dY + int64_t(r) * W + 4 * cg) = to_f4(d[r]);
+        }
+    }
+}
+
+template <int ROUND, int NT>
+__device__ __forceinline__ void dj_chroma_planes_save(float4* scr, const QuadCoef& qx, const QuadCoef& qy,
+                                                      int bx, int by, float f, float* dC, int64_t plane_c, int64_t Wc, bool active) {
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        float p[4][4], d[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f4_to(p[i], scr[(SC_CB + 4 * pl + i) * NT]);
+        quad_dct_rows(p, qx, 1);
+        quad_dct_cols(p, qy, 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float tf = cTC[(16 * i + 2 * j) + (8 * by + bx)] * f;   // [u=2i+by][v=2j+bx]
+                const float q = div_by_recip(p[i][j], tf, fast_rcp(tf));
+                d[i][j] = round_grad<ROUND>(q);
+                p[i][j] = round_fwd<ROUND>(q) * tf;
+            }
+        quad_idct_cols(p, qy, 16);
+        quad_idct_rows(p, qx, 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            scr[(SC_CB + 4 * pl + i) * NT] = to_f4(p[i]);
+            if (active) *reinterpret_cast<float4*>(dC + pl * plane_c + int64_t(i) * Wc) = to_f4(d[i]);
+        }
+    }
+}
+
 // Phase 3: chroma quadrants (rolled over the two planes): split DCT -> quantise / round /
 // dequantise -> split IDCT, in place in the SC_CB / SC_CR chunks.
 template <int ROUND, bool KEEP_Q, bool GRAD, int NT>
@@ -311,6 +376,51 @@ __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, 
                 stg256(p, oR);
                 stg256(p + plane, oG);
                 stg256(p + 2 * plane, oB);
+            }
+        }
+    }
+}
+
+// Final phase of the state-saving forward: as dj_emit_rgb, plus the clamp code of every value
+// (0 outside, 1 strictly inside, 2 exactly on a bound: the backward multiplies by 0 / 1 / 0.5, the
+// tie rule of the reference's binary min/max clamp, utils/JPEG.py:467-468): 48 bits per 8-pixel row.
+__device__ __forceinline__ unsigned clamp_code(float u) {
+    const bool open_in = u > 0.f && u < 1.f, closed_in = u >= 0.f && u <= 1.f;
+    return open_in ? 1u : (closed_in ? 2u : 0u);
+}
+template <int NT>
+__device__ __forceinline__ void dj_emit_rgb_save(const DJArgs& a, const DJThread& t, const float4* scr) {
+    float* yo = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
+    unsigned long long* cmo = a.cm + (int64_t(t.b) * a.H + t.row0) * (a.W >> 3) + (t.col0 >> 3);
+    const int64_t plane = int64_t(a.H) * a.W;
+#pragma unroll 1
+    for (int rp = 0; rp < 4; ++rp) {
+        float cb[4], cr[4], tR[4], tG[4], tB[4];
+        f4_to(cb, scr[(SC_CB + rp) * NT]);
+        f4_to(cr, scr[(SC_CR + rp) * NT]);
+        dj_chroma_terms(cb, cr, tR, tG, tB);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * rp + rr;
+            float yv[8];
+            scr_load_row<NT>(scr, r, yv);
+            idct8(yv);
+            f8 oR, oG, oB;
+            unsigned lo = 0, hi = 0;          // pixels 0-3 (24 bits) and 4-7 (24 bits)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float uR = fmaf(yv[c], DJ_I255, tR[c >> 1]), uG = fmaf(yv[c], DJ_I255, tG[c >> 1]),
+                            uB = fmaf(yv[c], DJ_I255, tB[c >> 1]);
+                oR.v[c] = __saturatef(uR); oG.v[c] = __saturatef(uG); oB.v[c] = __saturatef(uB);
+                const unsigned code = clamp_code(uR) | (clamp_code(uG) << 2) | (clamp_code(uB) << 4);
+                if (c < 4) lo |= code << (6 * c); else hi |= code << (6 * (c - 4));
+            }
+            if (t.active) {
+                float* p = yo + int64_t(r) * a.W;
+                stg256(p, oR);
+                stg256(p + plane, oG);
+                stg256(p + 2 * plane, oB);
+                cmo[int64_t(r) * (a.W >> 3)] = (unsigned long long)lo | ((unsigned long long)hi << 32);
             }
         }
     }

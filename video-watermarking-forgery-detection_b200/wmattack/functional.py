@@ -122,8 +122,12 @@ def _factor_args(factor, batch: int, device) -> Tuple[float, Optional[torch.Tens
 
 
 class _DiffJPEGFn(torch.autograd.Function):
+    """Forward-only calls (no grad needed) use wm_diffjpeg_fwd and save nothing.  When the input
+    requires grad the forward saves 7 B/px (round'(q) + clamp codes) and the backward runs from gy and
+    that state alone; `recompute=True` keeps the save-nothing pair (backward recomputes from x)."""
+
     @staticmethod
-    def forward(ctx, x, factor, rounding):
+    def forward(ctx, x, factor, rounding, recompute):
         x, sb, sc, sh = _image(x, "DiffJPEG")
         b, c, h, w = x.shape
         if c != 3:
@@ -133,30 +137,48 @@ class _DiffJPEGFn(torch.autograd.Function):
                              "block_merging views require it (utils/JPEG.py:371-376)")
         fs, fps = _factor_args(factor, b, x.device)
         y = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
-        _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
-        ctx.save_for_backward(x, fps if fps is not None else torch.empty(0, device=x.device))
-        ctx.meta = (fs, fps is not None, rounding)
+        need_grad = bool(ctx.needs_input_grad[0])
+        ctx.mode = "none"
+        if need_grad and rounding != ROUND_HARD and not recompute:
+            d_y = torch.empty((b, h, w), device=x.device, dtype=torch.float32)
+            d_c = torch.empty((b, 2, h // 2, w // 2), device=x.device, dtype=torch.float32)
+            codes = torch.empty((b, h, w // 8), device=x.device, dtype=torch.int64)
+            _lib.call("wm_diffjpeg_fwd_save", x.data_ptr(), sb, sc, sh, y.data_ptr(), d_y.data_ptr(), d_c.data_ptr(),
+                      codes.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+            ctx.save_for_backward(d_y, d_c, codes)
+            ctx.mode = "saved"
+        else:
+            _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+            if need_grad and rounding != ROUND_HARD:
+                ctx.save_for_backward(x, fps if fps is not None else torch.empty(0, device=x.device))
+                ctx.mode = "recompute"
+        ctx.meta = (fs, fps is not None, rounding, (b, 3, h, w))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, fps_t = ctx.saved_tensors
-        fs, has_fps, rounding = ctx.meta
-        b, _, h, w = x.shape
-        if rounding == ROUND_HARD:
-            return torch.zeros_like(x), None, None
+        fs, has_fps, rounding, (b, _, h, w) = ctx.meta
+        if ctx.mode == "none":                        # torch.round: zero gradient everywhere
+            return torch.zeros((b, 3, h, w), device=gy.device, dtype=torch.float32), None, None, None
         gy, gsb, gsc, gsh = _image(gy, "DiffJPEG.backward")
-        sb, sc, sh, _ = x.stride()
-        gx = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
-        _lib.call("wm_diffjpeg_bwd", x.data_ptr(), sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(),
-                  b, h, w, fs, _ptr(fps_t) if has_fps else None, rounding, _stream())
-        return gx, None, None
+        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
+        if ctx.mode == "saved":
+            d_y, d_c, codes = ctx.saved_tensors
+            _lib.call("wm_diffjpeg_bwd_saved", gy.data_ptr(), gsb, gsc, gsh, d_y.data_ptr(), d_c.data_ptr(),
+                      codes.data_ptr(), gx.data_ptr(), b, h, w, _stream())
+        else:
+            x, fps_t = ctx.saved_tensors
+            sb, sc, sh, _ = x.stride()
+            _lib.call("wm_diffjpeg_bwd", x.data_ptr(), sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(),
+                      b, h, w, fs, _ptr(fps_t) if has_fps else None, rounding, _stream())
+        return gx, None, None, None
 
 
-def diffjpeg(x: torch.Tensor, factor, rounding: int = ROUND_ONLY_AT_0) -> torch.Tensor:
+def diffjpeg(x: torch.Tensor, factor, rounding: int = ROUND_ONLY_AT_0, recompute: bool = False) -> torch.Tensor:
     """Fused DiffJPEG (utils/JPEG.py:535-540).  `factor` = quality_to_factor(quality), a python
-    float or a per-sample tensor [B]."""
-    return _DiffJPEGFn.apply(x, factor, rounding)
+    float or a per-sample tensor [B].  recompute=True: the backward recomputes the forward from x
+    instead of reading 7 B/px of saved state (lower memory, slower)."""
+    return _DiffJPEGFn.apply(x, factor, rounding, recompute)
 
 
 def diffjpeg_compress(x: torch.Tensor, factor, rounding: int = ROUND_HARD):
