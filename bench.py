@@ -144,6 +144,10 @@ def run_step(dj, comb, x, g, step, events=None):
 
 def ours(args, rank, world, dev):
     from wmattack import _lib
+    # Run backward nodes on the calling thread: every layer is ONE kernel launch of 60-170 us, and the
+    # autograd engine's hand-off to its device thread (~40 us per backward() call) would otherwise leave
+    # the GPU idle between launches.  A trainer that calls .backward() once per step does not need this.
+    torch.autograd.set_multithreading_enabled(False)
     torch.manual_seed(1234 + rank)
     dj, comb = build_layers(dev)
     gen = torch.Generator(dev).manual_seed(rank)

@@ -111,6 +111,13 @@ int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
 int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                  const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
                  float* gx, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+/* JpegSS training pair: the forward also saves ss'(q) of every coefficient (d: [B,3,ceil8(H),W],
+ * 12 B/px) and the backward runs from gy + d alone (no x, no recompute).  Fast-path geometry only:
+ * W % 8 == 0, subsample == 0, 32-byte aligned pointers, strides multiples of 8. */
+int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
+                      int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, float* gx,
+                       int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
 /* std_quantization output (noise_layers/jpeg.py:52-82) as a [B,3,Hp,Wp] coefficient image,
  * Hp/Wp = H/W rounded up to x8: the integer-exact parity target for Jpeg. */
 int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,

@@ -247,6 +247,138 @@ __global__ void __launch_bounds__(J8_THREADS, 3) jpeg8_fwd_kernel(const J8Args a
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast forward path (aligned rows, W % 8 == 0, no in-block chroma decimation): TWO threads per
+// 8x8 block.  Lanes 0-15 of a warp own rows 0-3 / the left 4 columns of 16 consecutive blocks,
+// lanes 16-31 rows 4-7 / the right 4 columns of the same blocks; all three channels of a block
+// stream through 48 shared-memory chunks, so a thread never holds more than one row triple or
+// one 8x4 column group: ~half the registers and code of the one-thread-per-block kernel, twice
+// the warps per SM (16), and the column stage is a rolled loop over the channels.  Quarter-warps
+// touch 8 different blocks with the same chunk index: conflict-free LDS.128 / STS.128.
+// ---------------------------------------------------------------------------------------------
+constexpr int J8P_THREADS = 128, J8P_BLOCKS = 64, J8P_CHUNKS = 48;
+
+// DMODE 0: plain forward.  1: JpegSS forward that also saves ss'(q) of every coefficient (12 B/px,
+// [B,3,Hp,W] in coefficient-image order).  2: JpegSS backward from that state: the cotangent runs
+// through inv_color^T -> DCT -> times ss'(q) -> IDCT -> fwd_color^T, i.e. the linear pipeline with a
+// per-coefficient "mask" read from global memory (the quantisation steps cancel); no recompute.
+template <int VARIANT, int DMODE>
+__global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args a) {
+    extern __shared__ float4 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, bic = warp * 16 + (lane & 15);          // half, block in CTA
+    float4* scr = smem + bic;                                         // chunk c at scr[c * J8P_BLOCKS]
+    const int64_t blk = int64_t(blockIdx.x) * J8P_BLOCKS + bic;
+    const bool active = blk < a.n_blk;
+    const int64_t m = active ? blk : 0;
+    const int per = a.Hb * a.Wb;
+    const int b = int(m / per), rem = int(m - int64_t(b) * per), by = rem / a.Wb;
+    const int row0 = by * 8, col0 = (rem - by * a.Wb) * 8;
+    const float* xr = a.x + int64_t(b) * a.x_sb + int64_t(row0 + 4 * h) * a.x_sh + col0;
+
+    // ---- rows 4h .. 4h+3: colour transform + row DCT of the three channels -> scratch --------------
+#pragma unroll 2
+    for (int i = 0; i < 4; ++i) {
+        const int r = 4 * h + i;
+        const bool ok = active && (row0 + r) < a.H;
+        const float* p = xr + int64_t(i) * a.x_sh;
+        float R[8], G[8], Bl[8];
+        j8_load_row<true>(p, ok, 8, R);
+        j8_load_row<true>(p + a.x_sc, ok, 8, G);
+        j8_load_row<true>(p + 2 * a.x_sc, ok, 8, Bl);
+        float y[8], u[8], v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            y[c] = fmaf(a.fwd[0], R[c], fmaf(a.fwd[1], G[c], a.fwd[2] * Bl[c]));
+            u[c] = fmaf(a.fwd[3], R[c], fmaf(a.fwd[4], G[c], a.fwd[5] * Bl[c]));
+            v[c] = fmaf(a.fwd[6], R[c], fmaf(a.fwd[7], G[c], a.fwd[8] * Bl[c]));
+        }
+        dct8(y); dct8(u); dct8(v);
+        j8_scr_store<J8P_BLOCKS>(scr, r, y);
+        j8_scr_store<J8P_BLOCKS>(scr + 16 * J8P_BLOCKS, r, u);
+        j8_scr_store<J8P_BLOCKS>(scr + 32 * J8P_BLOCKS, r, v);
+    }
+    __syncwarp();
+
+    // ---- columns 4h .. 4h+3 of every channel: DCT, quantise / round / dequantise, IDCT --------------
+#pragma unroll 1
+    for (int ch = 0; ch < 3; ++ch) {
+        float4* sc = scr + (16 * ch) * J8P_BLOCKS;
+        float v[8][4];
+        float d[8][4];
+        // saved state: coefficient (u, v) of this block at [b, ch, row0 + u, col0 + v]
+        float* dp = DMODE ? a.coef + ((int64_t(b) * 3 + ch) * (a.Hb * 8) + row0) * a.W + col0 + 4 * h : nullptr;
+        if (DMODE == 2) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 t4 = active ? ldg128_stream(dp + int64_t(r) * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[r][0] = t4.x; d[r][1] = t4.y; d[r][2] = t4.z; d[r][3] = t4.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float4 t4 = sc[(2 * r + h) * J8P_BLOCKS];
+            v[r][0] = t4.x; v[r][1] = t4.y; v[r][2] = t4.z; v[r][3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (DMODE == 2) { v[u][j] *= d[u][j]; continue; }
+                if (DMODE == 1) d[u][j] = j8_quant<VARIANT, 2>(a, ch, u * 8 + 4 * h + j, v[u][j]);
+                v[u][j] = j8_quant<VARIANT, 0>(a, ch, u * 8 + 4 * h + j, v[u][j]);
+            }
+            idct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+        }
+        if (DMODE == 1 && active) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                *reinterpret_cast<float4*>(dp + int64_t(r) * a.W) = make_float4(d[r][0], d[r][1], d[r][2], d[r][3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sc[(2 * r + h) * J8P_BLOCKS] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    }
+    __syncwarp();
+
+    // ---- rows 4h .. 4h+3: row IDCT, inverse colour transform, store -----------------------------
+    float* yo = a.out + (int64_t(b) * 3 * a.H + row0 + 4 * h) * a.W + col0;
+    const int64_t plane = int64_t(a.H) * a.W;
+#pragma unroll 2
+    for (int i = 0; i < 4; ++i) {
+        const int r = 4 * h + i;
+        float y[8], u[8], v[8];
+        j8_scr_load<J8P_BLOCKS>(scr, r, y);
+        j8_scr_load<J8P_BLOCKS>(scr + 16 * J8P_BLOCKS, r, u);
+        j8_scr_load<J8P_BLOCKS>(scr + 32 * J8P_BLOCKS, r, v);
+        idct8(y); idct8(u); idct8(v);
+        float oR[8], oG[8], oB[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            oR[c] = fmaf(a.inv[0], y[c], fmaf(a.inv[1], u[c], a.inv[2] * v[c]));
+            oG[c] = fmaf(a.inv[3], y[c], fmaf(a.inv[4], u[c], a.inv[5] * v[c]));
+            oB[c] = fmaf(a.inv[6], y[c], fmaf(a.inv[7], u[c], a.inv[8] * v[c]));
+        }
+        const bool ok = active && (row0 + r) < a.H;
+        float* p = yo + int64_t(i) * a.W;
+        j8_store_row<true>(p, ok, 8, oR);
+        j8_store_row<true>(p + plane, ok, 8, oG);
+        j8_store_row<true>(p + 2 * plane, ok, 8, oB);
+    }
+}
+
+template <int VARIANT, int DMODE = 0>
+static int j8_pair_launch(const J8Args& a, cudaStream_t st, const char* who) {
+    if (a.n_blk == 0) return WM_OK;
+    const size_t smem = size_t(J8P_CHUNKS) * J8P_BLOCKS * sizeof(float4);
+    cudaError_t e = cudaFuncSetAttribute(jpeg8_pair_kernel<VARIANT, DMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    const int64_t blocks = (a.n_blk + J8P_BLOCKS - 1) / J8P_BLOCKS;
+    jpeg8_pair_kernel<VARIANT, DMODE><<<(unsigned)blocks, J8P_THREADS, smem, st>>>(a);
+    WM_LAUNCH_CHECK(who);
+    return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // JpegSS backward: per channel, recompute round'(q) from x, push the cotangent through
 // DCT -> *round' -> IDCT (the quantisation steps cancel), park, then apply fwd_color^T.
 // ---------------------------------------------------------------------------------------------
@@ -418,6 +550,11 @@ static int j8_fwd_dispatch(const J8Args& a, bool vec, bool qout, cudaStream_t st
 }
 
 static int j8_fwd_any(const J8Args& a, int variant, int submode, bool vec, bool qout, cudaStream_t st, const char* who) {
+    if (vec && !qout && submode == 0) {          // fast path: two threads per block
+        if (variant == WM_JPEG8_HARD) return j8_pair_launch<WM_JPEG8_HARD>(a, st, who);
+        if (variant == WM_JPEG8_SS) return j8_pair_launch<WM_JPEG8_SS>(a, st, who);
+        if (variant == WM_JPEG8_MASK) return j8_pair_launch<WM_JPEG8_MASK>(a, st, who);
+    }
 #define J8_CASE(V, S) if (variant == V && submode == S) return j8_fwd_dispatch<V, S>(a, vec, qout, st, who);
     J8_CASE(WM_JPEG8_HARD, 0) J8_CASE(WM_JPEG8_HARD, 2)
     J8_CASE(WM_JPEG8_SS, 0) J8_CASE(WM_JPEG8_SS, 2)
@@ -487,4 +624,36 @@ extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
                    : j8_launch(jpeg8_ss_bwd_kernel<2, false>, a, J8B_THREADS, smem, st, "wm_jpeg8_bwd");
     return vec ? j8_launch(jpeg8_ss_bwd_kernel<0, true>, a, J8B_THREADS, smem, st, "wm_jpeg8_bwd")
                : j8_launch(jpeg8_ss_bwd_kernel<0, false>, a, J8B_THREADS, smem, st, "wm_jpeg8_bwd");
+}
+
+// JpegSS training pair (see jpeg8_pair_kernel, DMODE 1 / 2).  Needs the fast-path geometry:
+// W % 8 == 0, 32-byte aligned base pointers, strides multiples of 8, subsample == 0.
+// d: [B, 3, ceil8(H), W] floats.
+extern "C" int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
+                                 int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    J8Args a{};
+    if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd_save")) return rc;
+    WM_REQUIRE(y && d, WM_E_NULL, "wm_jpeg8_fwd_save: null output");
+    WM_REQUIRE(p->variant == WM_JPEG8_SS && p->subsample == 0, WM_E_ARG, "wm_jpeg8_fwd_save: JpegSS without subsampling only");
+    WM_REQUIRE(j8_vec_ok(x, x_sb, x_sc, x_sh, W) && aligned(y, 32) && aligned(d, 16), WM_E_ALIGN,
+               "wm_jpeg8_fwd_save: needs W %% 8 == 0, 32-byte aligned x / y and strides multiples of 8");
+    a.out = y; a.coef = d;
+    return j8_pair_launch<WM_JPEG8_SS, 1>(a, (cudaStream_t)stream, "wm_jpeg8_fwd_save");
+}
+extern "C" int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, float* gx,
+                                  int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    WM_REQUIRE(p && gy && d && gx, WM_E_NULL, "wm_jpeg8_bwd_saved: null pointer");
+    wm_jpeg8_params q = *p;              // adjoint colour matrices, as for the linear variants
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            q.fwd_color[3 * i + j] = p->inv_color[3 * j + i];
+            q.inv_color[3 * i + j] = p->fwd_color[3 * j + i];
+        }
+    q.variant = WM_JPEG8_MASK; q.subsample = 0;
+    J8Args a{};
+    if (int rc = j8_fill(a, gy, g_sb, g_sc, g_sh, B, H, W, &q, "wm_jpeg8_bwd_saved")) return rc;
+    WM_REQUIRE(j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 32) && aligned(d, 16), WM_E_ALIGN,
+               "wm_jpeg8_bwd_saved: needs W %% 8 == 0, 32-byte aligned gy / gx and strides multiples of 8");
+    a.out = gx; a.coef = const_cast<float*>(d);
+    return j8_pair_launch<WM_JPEG8_MASK, 2>(a, (cudaStream_t)stream, "wm_jpeg8_bwd_saved");
 }

@@ -37,6 +37,8 @@ SIGNATURES = {
     "wm_diffjpeg_decompress": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, vp],
     "wm_jpeg8_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_fwd_save": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_quantised": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_gaussblur": [c_f32p, i64, i64, c_f32p, i32, i32, i32, C.POINTER(f32), i32, i32, i32, vp],
     "wm_median_fwd": [c_f32p, i64, i64, c_f32p, c_u8p, i32, i32, i32, i32, vp],
@@ -109,12 +111,18 @@ def load() -> C.CDLL:
     return _lib
 
 
+_fns: dict = {}            # name -> bound ctypes function (skips CDLL.__getattr__ on the hot path)
+
+
 def call(name: str, *args) -> None:
     global launch_count
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(load(), name)
+    rc = fn(*args)
     launch_count += KERNELS_PER_CALL[name]
     if rc != 0:
+        lib = load()
         msg = lib.wm_last_error().decode(errors="replace")
         kind = "invalid argument" if rc < 0 else "CUDA error"
         raise WMAttackError(f"{name} failed ({kind} {rc}): {msg}")

@@ -27,7 +27,16 @@ _MODES = {"bilinear": BILINEAR, "bicubic": BICUBIC}
 # helpers
 # --------------------------------------------------------------------------------------
 
+try:                                       # raw handle of the current stream without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                     # pragma: no cover - older/newer torch without the private hook
+    _raw_stream = None
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (every launch goes there)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -237,17 +246,33 @@ class _Jpeg8Fn(torch.autograd.Function):
         if c != 3:
             raise ValueError(f"JPEG layers expect 3 channels, got {c}")
         y = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
-        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), _stream())
         ctx.params = params
+        ctx.shape = (b, h, w)
+        ctx.saved_d = False
+        if params.variant == JPEG8_SS and ctx.needs_input_grad[0] and w % 8 == 0 and params.subsample == 0:
+            # training pair: save ss'(q) (12 B/px); the backward then needs neither x nor a recompute
+            d = torch.empty((b, 3, (h + 7) // 8 * 8, w), device=x.device, dtype=torch.float32)
+            _lib.call("wm_jpeg8_fwd_save", x.data_ptr(), sb, sc, sh, y.data_ptr(), d.data_ptr(), b, h, w,
+                      C.byref(params), _stream())
+            ctx.save_for_backward(d)
+            ctx.saved_d = True
+            return y
+        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), _stream())
         if params.variant == JPEG8_SS:
             ctx.save_for_backward(x)
-        else:
-            ctx.shape = (b, h, w)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         p = ctx.params
+        if ctx.saved_d:
+            (d,) = ctx.saved_tensors
+            b, h, w = ctx.shape
+            gy, gsb, gsc, gsh = _image(gy, "jpeg8.backward")
+            gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
+            _lib.call("wm_jpeg8_bwd_saved", gy.data_ptr(), gsb, gsc, gsh, d.data_ptr(), gx.data_ptr(), b, h, w,
+                      C.byref(p), _stream())
+            return gx, None
         if p.variant == JPEG8_SS:
             (x,) = ctx.saved_tensors
             b, _, h, w = x.shape
