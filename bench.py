@@ -359,6 +359,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line ("NCCL version ..." goes there)
         torch.distributed.init_process_group("nccl", device_id=dev)
     out = ours(args, rank, world, dev)
     if rank == 0:
