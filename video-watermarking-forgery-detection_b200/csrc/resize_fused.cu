@@ -122,7 +122,7 @@ struct RBArgs {
 };
 
 template <int BT> struct RBGeom {
-    static constexpr int IW = ((RB_TW + BT + 16 + 3) / 4) * 4;      // staged columns (start = 4-aligned band start - 8)
+    static constexpr int IW = ((RB_TW + BT + 20 + 3) / 4) * 4;      // staged columns (start = 4-aligned band start - 8)
     static constexpr int IH = RB_TH + BT + 4;                       // staged rows
     static constexpr int IHA = ((IH + 7) / 8) * 8;                  // allocated rows (the H pass runs 8 rows per step)
     static constexpr int NP = RB_TH / 2;                            // output row pairs of a tile
@@ -155,31 +155,39 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     // rows the V pass can touch (rows past the image bottom are staged as zeros: their weights are 0)
     const int ih = min(__ldg(a.loy + oy0 + th - 1) + BT - ys, G::IH);
 
-    // H pass role: lane = output column.  The 32 windows of a warp are made REGULAR (start = base +
-    // lane, so the lanes of every LDS hit 32 distinct banks); the band of each lane is shifted
-    // inside its BT-wide register window accordingly.
-    const int hg = warp & 3, hr = warp >> 2;                         // 32-column group, row parity
-    const int ho = min(ox0 + 32 * hg + lane, a.W - 1);
-    const int hlo = __ldg(a.lox + ho);
-    const bool hvalid = 32 * hg + lane < tw;                         // lanes past the image edge hold zero weights
-    int hmin = hvalid ? hlo - lane : (1 << 30);
+    // H pass role: lane = TWO adjacent output columns whose bands share one window of BTW source
+    // values, read as BTW/2 LDS.64.  The 32 windows of a warp are made REGULAR (start = even base +
+    // 2*lane: the 8-byte accesses of a half-warp hit 32 distinct banks); each output's band is shifted
+    // inside the window accordingly.
+    constexpr int BTW = BT <= 10 ? 10 : 14;
+    const int hg = warp & 1, hr = warp >> 1;                         // 64-column group, row set
+    const int oa = 64 * hg + 2 * lane;                               // tile-local column of slot 0
+    const bool hv0 = oa < tw, hv1 = oa + 1 < tw;
+    const int hg0 = min(ox0 + oa, a.W - 1), hg1 = min(ox0 + oa + 1, a.W - 1);
+    const int hlo0 = __ldg(a.lox + hg0), hlo1 = __ldg(a.lox + hg1);
+    int hmin = hv0 ? hlo0 - 2 * lane : (1 << 30);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) hmin = min(hmin, __shfl_xor_sync(0xffffffffu, hmin, d));
-    hmin = min(hmin, a.W);                                           // (a group with no valid lane)
-    const int hshift = hvalid ? hlo - (hmin + lane) : BT;            // >= 0
-    float wreg[BT];
+    hmin = min(hmin, a.W) & ~1;                                      // even (also for negative values)
+    const int hs = hmin + 2 * lane;
+    const int hshift0 = hv0 ? hlo0 - hs : BTW, hshift1 = hv1 ? hlo1 - hs : BTW;
+    float w0[BTW], w1[BTW];
 #pragma unroll
-    for (int t = 0; t < BT; ++t) {
-        const int j = t - hshift;
-        wreg[t] = (j >= 0 && j < BT) ? __ldg(a.wx + int64_t(ho) * BT + j) : 0.f;
+    for (int t = 0; t < BTW; ++t) {
+        const int j0 = t - hshift0, j1 = t - hshift1;
+        w0[t] = (j0 >= 0 && j0 < BT) ? __ldg(a.wx + int64_t(hg0) * BT + j0) : 0.f;
+        w1[t] = (j1 >= 0 && j1 < BT) ? __ldg(a.wx + int64_t(hg1) * BT + j1) : 0.f;
     }
-    if (a.overflow && hvalid) {          // a weight that does not fit the regular window would be lost
+    if (a.overflow) {                    // a weight that does not fit the shared window would be lost
         bool lost = false;
-        for (int j = BT - hshift; j < BT; ++j) lost |= j >= 0 && __ldg(a.wx + int64_t(ho) * BT + j) != 0.f;
+        for (int j = 0; j < BT; ++j) {
+            lost |= hv0 && j + hshift0 >= BTW && __ldg(a.wx + int64_t(hg0) * BT + j) != 0.f;
+            lost |= hv1 && j + hshift1 >= BTW && __ldg(a.wx + int64_t(hg1) * BT + j) != 0.f;
+        }
         if (lost) atomicExch(a.overflow, 1);
     }
-    const int hbase = min(max(hmin - xs + lane, 0), G::IW - BT);
-    if (a.overflow && hvalid && hbase != hmin - xs + lane) atomicExch(a.overflow, 1);
+    const int hbase = min(max(hs - xs, 0), G::IW - BTW) & ~1;
+    if (a.overflow && hv0 && hbase != hs - xs) atomicExch(a.overflow, 1);
 
     // V pass tables: rows (2p, 2p+1) share the window starting at the first row's band start
     for (int i = tid; i < G::NP * BT; i += RB_THREADS) {
@@ -230,24 +238,23 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
             __syncthreads();
         }
 
-        // ---- H pass: tmp[r][o] = sum_t wreg[t] * in[r][hbase + t] -------------------------------
+        // ---- H pass: tmp[r][oa .. oa+1] = sum_t {w0, w1}[t] * in[r][hbase + t] ----------------------
         {
-            // 4 rows per iteration, two partial sums per row: 8 independent FMA chains per lane
             const float* p = in + hr * G::IW + hbase;
-            float* q = tmp + hr * RB_TW + 32 * hg + lane;
-            for (int r = hr; r < ih; r += 8) {
-                float e[4], o[4];
+            float* q = tmp + hr * RB_TW + oa;
+            for (int r = hr; r < ih; r += 8) {            // rows r and r + 4 (rows past ih land in spare rows)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { e[k] = wreg[0] * p[2 * k * G::IW]; o[k] = wreg[1] * p[2 * k * G::IW + 1]; }
+                for (int k = 0; k < 2; ++k) {
+                    const float* pk = p + 4 * k * G::IW;
+                    float a0e = 0.f, a0o = 0.f, a1e = 0.f, a1o = 0.f;
 #pragma unroll
-                for (int t = 2; t < BT; t += 2)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        e[k] = fmaf(wreg[t], p[2 * k * G::IW + t], e[k]);
-                        o[k] = fmaf(wreg[t + 1], p[2 * k * G::IW + t + 1], o[k]);
+                    for (int t = 0; t < BTW; t += 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(pk + t);
+                        a0e = fmaf(w0[t], v.x, a0e); a0o = fmaf(w0[t + 1], v.y, a0o);
+                        a1e = fmaf(w1[t], v.x, a1e); a1o = fmaf(w1[t + 1], v.y, a1o);
                     }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) q[2 * k * RB_TW] = e[k] + o[k];     // rows past ih land in spare rows
+                    *reinterpret_cast<float2*>(q + 4 * k * RB_TW) = make_float2(a0e + a0o, a1e + a1o);
+                }
                 p += 8 * G::IW; q += 8 * RB_TW;
             }
         }
@@ -277,25 +284,26 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                         acc[1].z = fmaf(a1[u], v.z, acc[1].z); acc[1].w = fmaf(a1[u], v.w, acc[1].w);
                     }
                 }
+                float* drow = dst + int64_t(2 * pr) * a.W;
+                uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 2 * pr) * a.tiles_x + tx) * 4 + (lane & 3);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const int o = 2 * pr + k;
-                    if (o >= th) break;
+                    const bool okr = 2 * pr + k < th;              // uniform
                     if (DIR == 0) {
                         const float4 c = make_float4(__saturatef(acc[k].x), __saturatef(acc[k].y), __saturatef(acc[k].z),
                                                      __saturatef(acc[k].w));
-                        if (okc) stg128(dst + int64_t(o) * a.W, c);
+                        if (okc && okr) stg128(drow + int64_t(k) * a.W, c);
                         if (a.mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc[k].x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc[k].y);
                             const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc[k].z);
                             const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc[k].w);
-                            if (lane < 4)
-                                a.mask[((int64_t(n) * a.H + oy0 + o) * a.tiles_x + tx) * 4 + lane] =
-                                    lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+                            unsigned w = b0;                       // lane l < 4 stores word l
+                            w = (lane & 3) == 1 ? b1 : w; w = (lane & 3) == 2 ? b2 : w; w = (lane & 3) == 3 ? b3 : w;
+                            if (lane < 4 && okr) mrow[int64_t(k) * a.tiles_x * 4] = w;
                         }
-                    } else if (okc) {
-                        stg128(dst + int64_t(o) * a.W, acc[k]);
+                    } else if (okc && okr) {
+                        stg128(drow + int64_t(k) * a.W, acc[k]);
                     }
                 }
             }
