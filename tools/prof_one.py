@@ -18,6 +18,7 @@ fns = {
     "diffjpeg": wmattack.DiffJPEG(True, h, w, quality=50),
     "jpeg8": wmattack.JpegCompression("cuda"),
     "jpegss": wmattack.JpegSS(50),
+    "noise": wmattack.Gaussian(),
 }
 f = fns[op]
 for _ in range(3):
