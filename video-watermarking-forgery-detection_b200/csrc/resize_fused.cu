@@ -265,8 +265,13 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         // ---- V pass: rows (2p, 2p+1) x 4 columns per lane from one shared window of tmp -----------
         {
             const bool okc = 4 * lane < tw;
-            float* dst = a.dst + (int64_t(n) * a.H + oy0) * a.W + ox0 + 4 * lane;
-            for (int pr = warp; 2 * pr < th; pr += RB_THREADS / 32) {
+            const bool want_mask = DIR == 0 && a.mask != nullptr;
+            // running pointers of this warp's row pairs (pr = warp, warp + 8, ...)
+            float* drow = a.dst + (int64_t(n) * a.H + oy0 + 2 * warp) * a.W + ox0 + 4 * lane;
+            uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 2 * warp) * a.tiles_x + tx) * 4 + (lane & 3);
+            const int drow_step = 2 * (RB_THREADS / 32) * a.W, mrow_step = 2 * (RB_THREADS / 32) * a.tiles_x * 4;
+            const int mrow_k = a.tiles_x * 4;
+            for (int pr = warp; 2 * pr < th; pr += RB_THREADS / 32, drow += drow_step, mrow += mrow_step) {
                 const float* w0 = wyp + (2 * pr) * BT;
                 const float* p = tmp + ylop[pr] * RB_TW + 4 * lane;
                 float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -284,26 +289,24 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                         acc[1].z = fmaf(a1[u], v.z, acc[1].z); acc[1].w = fmaf(a1[u], v.w, acc[1].w);
                     }
                 }
-                float* drow = dst + int64_t(2 * pr) * a.W;
-                uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 2 * pr) * a.tiles_x + tx) * 4 + (lane & 3);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const bool okr = 2 * pr + k < th;              // uniform
                     if (DIR == 0) {
                         const float4 c = make_float4(__saturatef(acc[k].x), __saturatef(acc[k].y), __saturatef(acc[k].z),
                                                      __saturatef(acc[k].w));
-                        if (okc && okr) stg128(drow + int64_t(k) * a.W, c);
-                        if (a.mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
+                        if (okc && okr) stg128(drow + k * a.W, c);
+                        if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc[k].x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc[k].y);
                             const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc[k].z);
                             const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc[k].w);
                             unsigned w = b0;                       // lane l < 4 stores word l
                             w = (lane & 3) == 1 ? b1 : w; w = (lane & 3) == 2 ? b2 : w; w = (lane & 3) == 3 ? b3 : w;
-                            if (lane < 4 && okr) mrow[int64_t(k) * a.tiles_x * 4] = w;
+                            if (lane < 4 && okr) mrow[k * mrow_k] = w;
                         }
                     } else if (okc && okr) {
-                        stg128(drow + int64_t(k) * a.W, acc[k]);
+                        stg128(drow + k * a.W, acc[k]);
                     }
                 }
             }
