@@ -203,6 +203,7 @@ def ours(args, rank, world, dev):
                 "algorithmic_bytes_per_launch": dbytes}
 
     e2e = run_e2e(args, dj, comb, g, rank, world, dev, px_step)
+    e2e_u8 = run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=True)
     if len(clk.lines) < 3:               # very short runs: keep the GPU busy until a few samples exist
         t_end = time.time() + 0.5
         while time.time() < t_end:
@@ -215,7 +216,9 @@ def ours(args, rank, world, dev):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": [B, 3, H, W], "resize_ratios": list(RESIZE_RATIOS),
                    "l2": "each tensor is 201 MB > 126 MB L2, no flush needed", "sharding": f"batch x{world}, no collective"},
-        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "e2e": e2e, "e2e_u8": dict(e2e_u8, note="same step with 8-bit host frames uploaded as bytes and converted on "
+                                              "the device (wm_u8_to_unit_float); extra to the contract's fp32 e2e"),
+        "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "clocks": clk.summary(),
     }
     return out
@@ -243,11 +246,18 @@ def bind_to_gpu_numa_node(dev):
     return None
 
 
-def run_e2e(args, dj, comb, g, rank, world, dev, px_step):
+def run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=False):
     """Host-resident input: H2D of the step's batch (pinned, double-buffered on a copy stream) +
-    D2H of a result scalar, every step, inside the timed region."""
+    D2H of a result scalar, every step, inside the timed region.
+    u8=True: the host holds 8-bit frames (what a video decoder produces); they are uploaded as bytes
+    and converted to [0,1] float on the device by wmattack.functional.from_uint8 inside the timed region."""
+    from wmattack import functional as WF
     numa = bind_to_gpu_numa_node(dev) if world > 1 else None
-    host = [torch.rand(B, 3, H, W).pin_memory() for _ in range(2)]
+    if u8:
+        host = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        stage = [torch.empty(B, 3, H, W, device=dev, dtype=torch.uint8) for _ in range(2)]
+    else:
+        host = [torch.rand(B, 3, H, W).pin_memory() for _ in range(2)]
     devbuf = [torch.empty(B, 3, H, W, device=dev) for _ in range(2)]
     result = torch.zeros(1).pin_memory()
     copy_stream = torch.cuda.Stream()
@@ -258,7 +268,11 @@ def run_e2e(args, dj, comb, g, rank, world, dev, px_step):
     def upload(i):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(free[i % 2])
-            devbuf[i % 2].copy_(host[i % 2], non_blocking=True)
+            if u8:
+                stage[i % 2].copy_(host[i % 2], non_blocking=True)
+                WF.from_uint8(stage[i % 2], out=devbuf[i % 2])          # on the copy stream, ahead of the step
+            else:
+                devbuf[i % 2].copy_(host[i % 2], non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     def loop(n):
@@ -285,7 +299,7 @@ def run_e2e(args, dj, comb, g, rank, world, dev, px_step):
     torch.cuda.synchronize()
     ms = allreduce_max(t0.elapsed_time(t1), world, dev)
     return {"value": round(world * args.steps * px_step / (ms / 1e3) / 1e6, 1), "unit": "Mpix/s",
-            "h2d_bytes_per_step": B * 3 * H * W * 4, "d2h_bytes_per_step": 4,
+            "h2d_bytes_per_step": B * 3 * H * W * (1 if u8 else 4), "d2h_bytes_per_step": 4,
             "ms_per_step": round(ms / args.steps, 4), "host_cpus": numa}
 
 

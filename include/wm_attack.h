@@ -232,6 +232,9 @@ int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, i
  *   out = a * (1 - mask) + b * mask,  a, b: [B, C, H, W], mask: [B, 1, H, W], H*W % 4 == 0.
  *   bwd: ga = gy * (1 - mask), gb = gy * mask (either may be NULL).
  * ------------------------------------------------------------------------------------------ */
+/* 8-bit frames -> [0,1] float32, dst[i] = src[i] / 255 (data format on the host side of the path:
+ * upload bytes, convert on the device; same values as torch's u8.float() / 255). */
+int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream);
 int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                            void* stream);
 int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream);

@@ -759,3 +759,10 @@ def test_train_step_example_runs_and_gradients_reach_the_encoder():
     g_loc = [p.grad for p in model.localiser.parameters()]
     assert all(g is not None and torch.isfinite(g).all() for g in g_enc + g_loc)
     assert sum(float(g.abs().sum()) for g in g_enc) > 0
+
+
+def test_from_uint8_matches_torch():
+    for shape in ((2, 3, 33, 47), (1, 3, 64, 64), (5,)):
+        u = torch.randint(0, 256, shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(7))
+        got = WF.from_uint8(u.to(DEV)).cpu()
+        assert torch.equal(got, u.float() / 255)

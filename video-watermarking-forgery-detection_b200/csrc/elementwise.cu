@@ -249,6 +249,26 @@ __global__ void __launch_bounds__(256) splice_kernel(const float* __restrict__ a
     }
 }
 
+// ---- uint8 frames -> [0,1] float (the data format on the host side of the path) -----------------
+// The reference's loaders divide 8-bit frames by 255 on the CPU and upload fp32 (data/Dataloader.py);
+// uploading the bytes and converting on the device moves 4x less over PCIe.  Same value as
+// torch's  u8.float() / 255  (true division).
+__global__ void __launch_bounds__(256) u8_to_unit_float_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 16; i < n; i += int64_t(gridDim.x) * blockDim.x * 16) {
+        if (i + 15 < n) {
+            const uint4 w = *reinterpret_cast<const uint4*>(src + i);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<float4*>(dst + i + 4 * k) =
+                    make_float4(__fdiv_rn(float(ws[k] & 0xff), 255.f), __fdiv_rn(float((ws[k] >> 8) & 0xff), 255.f),
+                                __fdiv_rn(float((ws[k] >> 16) & 0xff), 255.f), __fdiv_rn(float(ws[k] >> 24), 255.f));
+        } else {
+            for (int64_t j = i; j < n; ++j) dst[j] = __fdiv_rn(float(src[j]), 255.f);
+        }
+    }
+}
+
 static inline unsigned ew_grid(int64_t n_vec) {
     const int64_t want = (n_vec + 255) / 256;
     const int64_t cap = int64_t(sm_count()) * 16;
@@ -412,5 +432,14 @@ extern "C" int wm_splice_bwd(const float* gy, const float* mask, float* ga, floa
     if (n <= 0) return WM_OK;
     splice_kernel<true><<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask, ga, gb, n, hw, C);
     WM_LAUNCH_CHECK("wm_splice_bwd");
+    return WM_OK;
+}
+
+extern "C" int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream) {
+    WM_REQUIRE(src && dst, WM_E_NULL, "wm_u8_to_unit_float: null pointer");
+    WM_REQUIRE(aligned(src, 16) && aligned(dst, 16), WM_E_ALIGN, "wm_u8_to_unit_float: pointers must be 16-byte aligned");
+    if (n <= 0) return WM_OK;
+    u8_to_unit_float_kernel<<<ew_grid((n + 15) / 16), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    WM_LAUNCH_CHECK("wm_u8_to_unit_float");
     return WM_OK;
 }

@@ -56,6 +56,7 @@ SIGNATURES = {
     "wm_cropout_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, i32, i32, vp],
     "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
     "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
+    "wm_u8_to_unit_float": [c_u8p, c_f32p, i64, vp],
     "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
     "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],
     "wm_splice_fwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
