@@ -766,3 +766,31 @@ def test_from_uint8_matches_torch():
         u = torch.randint(0, 256, shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(7))
         got = WF.from_uint8(u.to(DEV)).cpu()
         assert torch.equal(got, u.float() / 255)
+
+
+def test_degenerate_shapes():
+    """Empty batches and tiny frames go through every layer (the reference's edge cases are torch's)."""
+    for shape in ((0, 3, 32, 32), (1, 3, 1, 1), (1, 3, 2, 4), (2, 3, 7, 9), (1, 3, 8, 8)):
+        x = rnd(shape, 71) if shape[0] else torch.zeros(shape)
+        layers = [wmattack.Jpeg(50), wmattack.JpegSS(50), wmattack.JpegMask(50), wmattack.JpegCompression(DEV),
+                  wmattack.GaussianBlur(), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5), wmattack.Gaussian(),
+                  wmattack.SaltPepper(0.1), wmattack.Identity(), wmattack.Quantization()]
+        refs = {0: lambda t: O.jpeg8(t, 50, O.JPEG8_HARD), 2: lambda t: O.jpeg8(t, 50, O.JPEG8_MASK), 3: O.jpeg_compression,
+                4: lambda t: O.gaussian_blur(t, 3), 5: lambda t: O.median_blur(t, 3), 6: lambda t: O.median_blur(t, 5)}
+        for i, layer in enumerate(layers):
+            xx = x.to(DEV).requires_grad_(True)
+            y = layer(xx)
+            assert y.shape == x.shape
+            if shape[0]:
+                y.sum().backward()
+                assert torch.isfinite(y).all() and torch.isfinite(xx.grad).all()
+                if i in refs:
+                    assert md(y, refs[i](x.double())) <= 1e-5, (shape, i)
+        if shape[0] and shape[2] >= 2 and shape[3] >= 2:
+            xx = x.to(DEV).requires_grad_(True)
+            y = wmattack.Resize()(xx, resize_ratio=0.6)
+            assert md(y, O.resize(x.double(), 0.6)) <= 1e-5
+            y.sum().backward()
+        if shape[0] == 0:
+            assert wmattack.DiffJPEG(True, 32, 32, 50)(x.to(DEV)).shape == x.shape
+            assert wmattack.Resize()(x.to(DEV), resize_ratio=0.6).shape == x.shape

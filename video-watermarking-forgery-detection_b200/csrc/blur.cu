@@ -233,6 +233,7 @@ using namespace wm;
 
 extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
                             const float* taps_host, int k, int border, int adjoint, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && taps_host, WM_E_NULL, "wm_gaussblur: null pointer");
     WM_REQUIRE(k >= 1 && k <= BL_MAXK && (k & 1), WM_E_ARG, "wm_gaussblur: kernel size must be odd and <= %d (got %d)", BL_MAXK, k);
     WM_REQUIRE(border == 0 || border == 1, WM_E_ARG, "wm_gaussblur: border must be 0 (zero) or 1 (reflect)");

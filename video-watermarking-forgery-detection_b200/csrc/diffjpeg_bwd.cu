@@ -300,6 +300,7 @@ using namespace wm;
 extern "C" int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
                                      const float* dY, const float* dC, const uint64_t* clamp_codes, float* gx,
                                      int B, int H, int W, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(gy, g_sb, g_sc, g_sh, B, H, W, "wm_diffjpeg_bwd_saved(gy)")) return rc;
     WM_REQUIRE(dY && dC && clamp_codes && gx, WM_E_NULL, "wm_diffjpeg_bwd_saved: null pointer");
     WM_REQUIRE(aligned(gx, 32) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
@@ -317,6 +318,7 @@ extern "C" int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64
                                const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, float* gx,
                                int B, int H, int W, float factor, const float* factor_ps,
                                int rounding, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_bwd(x)")) return rc;
     if (int rc = dj_check(gy, g_sb, g_sc, g_sh, B, H, W, "wm_diffjpeg_bwd(gy)")) return rc;
     WM_REQUIRE(gx != nullptr && aligned(gx, 32), WM_E_ALIGN, "wm_diffjpeg_bwd: gx must be non-null, 32-byte aligned");

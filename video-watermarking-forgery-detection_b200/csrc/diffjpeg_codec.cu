@@ -110,6 +110,7 @@ using namespace wm;
 extern "C" int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                                     float* coef_y, float* coef_cb, float* coef_cr, int B, int H, int W,
                                     float factor, const float* factor_ps, int rounding, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_compress")) return rc;
     WM_REQUIRE(coef_y && coef_cb && coef_cr && aligned(coef_y, 32), WM_E_NULL,
                "wm_diffjpeg_compress: coefficient outputs must be non-null (coef_y 32-byte aligned)");
@@ -123,6 +124,7 @@ extern "C" int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, 
 extern "C" int wm_diffjpeg_decompress(const float* coef_y, const float* coef_cb, const float* coef_cr,
                                       float* y, int B, int H, int W, float factor,
                                       const float* factor_ps, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(coef_y && coef_cb && coef_cr && y, WM_E_NULL, "wm_diffjpeg_decompress: null pointer");
     WM_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, WM_E_SHAPE,
                "wm_diffjpeg_decompress: H and W must be positive multiples of 16 (got %d x %d)", H, W);

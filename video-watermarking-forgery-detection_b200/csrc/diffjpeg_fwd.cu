@@ -44,6 +44,7 @@ using namespace wm;
 extern "C" int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                                     float* dY, float* dC, uint64_t* clamp_codes, int B, int H, int W,
                                     float factor, const float* factor_ps, int rounding, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd_save")) return rc;
     WM_REQUIRE(y && dY && dC && clamp_codes, WM_E_NULL, "wm_diffjpeg_fwd_save: null output pointer");
     WM_REQUIRE(aligned(y, 32) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
@@ -59,6 +60,7 @@ extern "C" int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, 
 extern "C" int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                                int B, int H, int W, float factor, const float* factor_ps,
                                int rounding, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd")) return rc;
     WM_REQUIRE(y != nullptr && aligned(y, 32), WM_E_ALIGN, "wm_diffjpeg_fwd: y must be non-null, 32-byte aligned");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);

@@ -286,6 +286,7 @@ using namespace wm;
 
 extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
                                  uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
@@ -295,6 +296,7 @@ extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean
 }
 extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
                                  int clamp, uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && gx && (x || !clamp), WM_E_NULL, "wm_gaussnoise_bwd: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_bwd", x, gy, gx, inject);
     if (n <= 0) return WM_OK;
@@ -308,6 +310,7 @@ extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int
 }
 extern "C" int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob, uint64_t seed, uint64_t offset,
                                  const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_saltpepper_fwd: null pointer");
     EW_ALIGN_CHECK("wm_saltpepper_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
@@ -320,6 +323,7 @@ extern "C" int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob
 }
 extern "C" int wm_saltpepper_bwd(const float* gy, float* gx, int64_t n, float prob, uint64_t seed, uint64_t offset,
                                  const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && gx, WM_E_NULL, "wm_saltpepper_bwd: null pointer");
     EW_ALIGN_CHECK("wm_saltpepper_bwd", gy, gx, inject);
     if (n <= 0) return WM_OK;
@@ -330,6 +334,7 @@ extern "C" int wm_saltpepper_bwd(const float* gy, float* gx, int64_t n, float pr
 }
 extern "C" int wm_dropout_elem_fwd(const float* image, const float* cover, float* y, int64_t n, float prob,
                                    uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(image && cover && y, WM_E_NULL, "wm_dropout_elem_fwd: null pointer");
     EW_ALIGN_CHECK("wm_dropout_elem_fwd", image, cover, y, inject);
     if (n <= 0) return WM_OK;
@@ -339,6 +344,7 @@ extern "C" int wm_dropout_elem_fwd(const float* image, const float* cover, float
 }
 extern "C" int wm_dropout_elem_bwd(const float* gy, float* g_image, float* g_cover, int64_t n, float prob,
                                    uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && (g_image || g_cover), WM_E_NULL, "wm_dropout_elem_bwd: null pointer");
     EW_ALIGN_CHECK("wm_dropout_elem_bwd", gy, g_image, g_cover, inject);
     if (n <= 0) return WM_OK;
@@ -348,6 +354,7 @@ extern "C" int wm_dropout_elem_bwd(const float* gy, float* g_image, float* g_cov
 }
 extern "C" int wm_dropout_mask_fwd(const float* noised, const float* cover, const float* mask_hw, float* y,
                                    int64_t planes, int64_t hw, void* stream) {
+    if (planes * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(noised && cover && mask_hw && y, WM_E_NULL, "wm_dropout_mask_fwd: null pointer");
     WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_fwd: H*W must be a multiple of 4");
     EW_ALIGN_CHECK("wm_dropout_mask_fwd", noised, cover, mask_hw, y);
@@ -359,6 +366,7 @@ extern "C" int wm_dropout_mask_fwd(const float* noised, const float* cover, cons
 }
 extern "C" int wm_dropout_mask_bwd(const float* gy, const float* mask_hw, float* g_noised, float* g_cover,
                                    int64_t planes, int64_t hw, void* stream) {
+    if (planes * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && mask_hw && (g_noised || g_cover), WM_E_NULL, "wm_dropout_mask_bwd: null pointer");
     WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_bwd: H*W must be a multiple of 4");
     EW_ALIGN_CHECK("wm_dropout_mask_bwd", gy, mask_hw, g_noised, g_cover);
@@ -369,6 +377,7 @@ extern "C" int wm_dropout_mask_bwd(const float* gy, const float* mask_hw, float*
     return WM_OK;
 }
 extern "C" int wm_bernoulli_mask(float* mask_hw, int64_t hw, float keep, uint64_t seed, uint64_t offset, void* stream) {
+    if (hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(mask_hw, WM_E_NULL, "wm_bernoulli_mask: null pointer");
     EW_ALIGN_CHECK("wm_bernoulli_mask", mask_hw);
     if (hw <= 0) return WM_OK;
@@ -377,6 +386,7 @@ extern "C" int wm_bernoulli_mask(float* mask_hw, int64_t hw, float keep, uint64_
     return WM_OK;
 }
 extern "C" int wm_quantize8_fwd(const float* x, float* y, int64_t n, int clamp01, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_quantize8_fwd: null pointer");
     EW_ALIGN_CHECK("wm_quantize8_fwd", x, y);
     if (n <= 0) return WM_OK;
@@ -386,6 +396,7 @@ extern "C" int wm_quantize8_fwd(const float* x, float* y, int64_t n, int clamp01
 }
 extern "C" int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t planes, int H, int W,
                               int h0, int h1, int w0, int w1, void* stream) {
+    if (planes * H * W <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(image && cover && y, WM_E_NULL, "wm_cropout_fwd: null pointer");
     const int64_t total = planes * H * W;
     if (total <= 0) return WM_OK;
@@ -396,6 +407,7 @@ extern "C" int wm_cropout_fwd(const float* image, const float* cover, float* y, 
 
 extern "C" int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                                       void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && sim && out, WM_E_NULL, "wm_attack_epilogue_fwd: null pointer");
     EW_ALIGN_CHECK("wm_attack_epilogue_fwd", x, sim, out);
     if (n <= 0) return WM_OK;
@@ -404,6 +416,7 @@ extern "C" int wm_attack_epilogue_fwd(const float* x, const float* sim, float* o
     return WM_OK;
 }
 extern "C" int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(g && out, WM_E_NULL, "wm_slice_sum: null pointer");
     WM_REQUIRE(K >= 1 && n % 4 == 0, WM_E_ARG, "wm_slice_sum: K >= 1 and n %% 4 == 0 required (K=%d n=%lld)", K, (long long)n);
     EW_ALIGN_CHECK("wm_slice_sum", g, out);
@@ -414,6 +427,7 @@ extern "C" int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* 
 }
 extern "C" int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out, int64_t B, int C, int64_t hw,
                              void* stream) {
+    if (B * C * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(a && b && mask && out, WM_E_NULL, "wm_splice_fwd: null pointer");
     WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_fwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
     EW_ALIGN_CHECK("wm_splice_fwd", a, b, mask, out);
@@ -425,6 +439,7 @@ extern "C" int wm_splice_fwd(const float* a, const float* b, const float* mask, 
 }
 extern "C" int wm_splice_bwd(const float* gy, const float* mask, float* ga, float* gb, int64_t B, int C, int64_t hw,
                              void* stream) {
+    if (B * C * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && mask && (ga || gb), WM_E_NULL, "wm_splice_bwd: null pointer");
     WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_bwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
     EW_ALIGN_CHECK("wm_splice_bwd", gy, mask, ga, gb);
@@ -436,6 +451,7 @@ extern "C" int wm_splice_bwd(const float* gy, const float* mask, float* ga, floa
 }
 
 extern "C" int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(src && dst, WM_E_NULL, "wm_u8_to_unit_float: null pointer");
     WM_REQUIRE(aligned(src, 16) && aligned(dst, 16), WM_E_ALIGN, "wm_u8_to_unit_float: pointers must be 16-byte aligned");
     if (n <= 0) return WM_OK;

@@ -570,6 +570,7 @@ using namespace wm;
 
 extern "C" int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                             int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
     if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd")) return rc;
     WM_REQUIRE(y != nullptr, WM_E_NULL, "wm_jpeg8_fwd: null output");
@@ -580,6 +581,7 @@ extern "C" int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
 
 extern "C" int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* coef,
                                   int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
     if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_quantised")) return rc;
     WM_REQUIRE(coef != nullptr && aligned(coef, 32), WM_E_ALIGN, "wm_jpeg8_quantised: coef must be 32-byte aligned");
@@ -591,6 +593,7 @@ extern "C" int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, in
 extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                             const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, float* gx,
                             int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(p != nullptr && gx != nullptr && gy != nullptr, WM_E_NULL, "wm_jpeg8_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (p->variant == WM_JPEG8_HARD) {
@@ -631,6 +634,7 @@ extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
 // d: [B, 3, ceil8(H), W] floats.
 extern "C" int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
                                  int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
     if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd_save")) return rc;
     WM_REQUIRE(y && d, WM_E_NULL, "wm_jpeg8_fwd_save: null output");
@@ -642,6 +646,7 @@ extern "C" int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int
 }
 extern "C" int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, float* gx,
                                   int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+    if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(p && gy && d && gx, WM_E_NULL, "wm_jpeg8_bwd_saved: null pointer");
     wm_jpeg8_params q = *p;              // adjoint colour matrices, as for the linear variants
     for (int i = 0; i < 3; ++i)

@@ -462,6 +462,7 @@ using namespace wm;
 
 extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
                              int N, int H, int W, int k, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_median_fwd: null pointer");
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_fwd: kernel size must be 3 or 5 (got %d)", k);
     WM_REQUIRE(N >= 0 && N <= 65535 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd: bad shape N=%d H=%d W=%d", N, H, W);
@@ -511,6 +512,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
 }
 
 extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int k, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && idx && gx, WM_E_NULL, "wm_median_bwd: null pointer");
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_bwd: kernel size must be 3 or 5 (got %d)", k);
     const int64_t total = int64_t(N) * H * W;

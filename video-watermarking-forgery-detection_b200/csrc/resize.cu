@@ -341,6 +341,7 @@ using namespace wm;
 extern "C" int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0, int w0, int Hin, int Win,
                              float* y, int N, int Hout, int Wout, int mode, int clamp01,
                              uint32_t* maskbits, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_interp_fwd: null pointer");
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_interp_fwd: mode must be 0 (bilinear) or 1 (bicubic)");
     WM_REQUIRE(N >= 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && h0 >= 0 && w0 >= 0, WM_E_SHAPE,
@@ -377,6 +378,7 @@ extern "C" int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0,
 extern "C" int wm_interp_bwd(const float* gy, const float* pre, const uint32_t* maskbits, int N, int Hout, int Wout,
                              float* gx, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
                              int mode, float* workspace, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && gx, WM_E_NULL, "wm_interp_bwd: null pointer");
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_interp_bwd: mode must be 0 (bilinear) or 1 (bicubic)");
     WM_REQUIRE(N >= 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && h0 >= 0 && w0 >= 0 &&

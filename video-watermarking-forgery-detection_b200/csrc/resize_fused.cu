@@ -424,6 +424,7 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
 
 extern "C" int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
                              int mode, uint32_t* maskbits, const float* tables, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && tables, WM_E_NULL, "wm_resize_fwd: null pointer");
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_fwd: mode must be 0 (bilinear) or 1 (bicubic)");
     if (N == 0) return WM_OK;
@@ -437,6 +438,7 @@ extern "C" int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
 
 extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
                              int mode, const float* tables, void* stream) {
+    if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && gx && tables, WM_E_NULL, "wm_resize_bwd: null pointer");
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_bwd: mode must be 0 (bilinear) or 1 (bicubic)");
     if (N == 0) return WM_OK;
