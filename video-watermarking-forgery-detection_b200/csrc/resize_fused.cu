@@ -32,6 +32,18 @@ constexpr float RB_RATIO_MIN = 0.45f, RB_RATIO_MAX = 2.2f;
 __device__ __forceinline__ float rb_cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 __device__ __forceinline__ float rb_cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
 
+// Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fmas per issue slot, bit-identical to fmaf.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+}
+
 // Taps of output index o: positions i0-1 .. i0+2 of the edge-replicated source, weights w.
 // Same fp32 coordinate arithmetic as ATen (area_pixel_compute_source_index, align_corners=false).
 template <int MODE>
@@ -246,14 +258,14 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const float* pk = p + 4 * k * G::IW;
-                    float a0e = 0.f, a0o = 0.f, a1e = 0.f, a1o = 0.f;
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0;        // (even taps, odd taps) partial sums
 #pragma unroll
                     for (int t = 0; t < BTW; t += 2) {
                         const float2 v = *reinterpret_cast<const float2*>(pk + t);
-                        a0e = fmaf(w0[t], v.x, a0e); a0o = fmaf(w0[t + 1], v.y, a0o);
-                        a1e = fmaf(w1[t], v.x, a1e); a1o = fmaf(w1[t + 1], v.y, a1o);
+                        a0 = ffma2(make_float2(w0[t], w0[t + 1]), v, a0);
+                        a1 = ffma2(make_float2(w1[t], w1[t + 1]), v, a1);
                     }
-                    *reinterpret_cast<float2*>(q + 4 * k * RB_TW) = make_float2(a0e + a0o, a1e + a1o);
+                    *reinterpret_cast<float2*>(q + 4 * k * RB_TW) = make_float2(a0.x + a0.y, a1.x + a1.y);
                 }
                 p += 8 * G::IW; q += 8 * RB_TW;
             }
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
             for (int pr = warp; 2 * pr < th; pr += RB_THREADS / 32, drow += drow_step, mrow += mrow_step) {
                 const float* w0 = wyp + (2 * pr) * BT;
                 const float* p = tmp + ylop[pr] * RB_TW + 4 * lane;
-                float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+                float2 lo[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, hi[2] = {lo[0], lo[0]};   // columns (0,1), (2,3)
 #pragma unroll
                 for (int t2 = 0; t2 < BT; t2 += 2) {      // BT is even: weights as 8-byte broadcast loads
                     const float2 wa = *reinterpret_cast<const float2*>(w0 + t2);
@@ -283,12 +295,13 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const float4 v = *reinterpret_cast<const float4*>(p + (t2 + u) * RB_TW);
-                        acc[0].x = fmaf(a0[u], v.x, acc[0].x); acc[0].y = fmaf(a0[u], v.y, acc[0].y);
-                        acc[0].z = fmaf(a0[u], v.z, acc[0].z); acc[0].w = fmaf(a0[u], v.w, acc[0].w);
-                        acc[1].x = fmaf(a1[u], v.x, acc[1].x); acc[1].y = fmaf(a1[u], v.y, acc[1].y);
-                        acc[1].z = fmaf(a1[u], v.z, acc[1].z); acc[1].w = fmaf(a1[u], v.w, acc[1].w);
+                        const float2 vl = make_float2(v.x, v.y), vh = make_float2(v.z, v.w);
+                        const float2 w0p = make_float2(a0[u], a0[u]), w1p = make_float2(a1[u], a1[u]);
+                        lo[0] = ffma2(w0p, vl, lo[0]); hi[0] = ffma2(w0p, vh, hi[0]);
+                        lo[1] = ffma2(w1p, vl, lo[1]); hi[1] = ffma2(w1p, vh, hi[1]);
                     }
                 }
+                const float4 acc[2] = {make_float4(lo[0].x, lo[0].y, hi[0].x, hi[0].y), make_float4(lo[1].x, lo[1].y, hi[1].x, hi[1].y)};
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const bool okr = 2 * pr + k < th;              // uniform
