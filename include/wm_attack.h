@@ -235,6 +235,14 @@ int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, i
 /* 8-bit frames -> [0,1] float32, dst[i] = src[i] / 255 (data format on the host side of the path:
  * upload bytes, convert on the device; same values as torch's u8.float() / 255). */
 int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream);
+/* Store epilogue, fused: arms the epilogue above for the NEXT forward launch issued from the calling
+ * host thread; that kernel then writes  Quantization( x + (clamp(v, 0, 1) - x) )  instead of its own
+ * value v, reading x (dense [B,C,H,W] in the layout of the output, 32-byte aligned) at the output
+ * position — no separate pass over the attacked batch.  Consumed (and cleared) by: wm_diffjpeg_fwd,
+ * wm_jpeg8_fwd (W % 8 == 0, aligned, subsample 0), wm_gaussblur (zero border, k in {3,5,7}, W % 4 == 0),
+ * wm_median_fwd (TMA paths), wm_gaussnoise_fwd, wm_resize_fwd.  Their other code paths fail with
+ * WM_E_ARG instead of silently ignoring it.  x = NULL disarms. */
+int wm_set_store_epilogue(const float* x, int clamp01, int quantize);
 int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                            void* stream);
 int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream);

@@ -794,3 +794,37 @@ def test_degenerate_shapes():
         if shape[0] == 0:
             assert wmattack.DiffJPEG(True, 32, 32, 50)(x.to(DEV)).shape == x.shape
             assert wmattack.Resize()(x.to(DEV), resize_ratio=0.6).shape == x.shape
+
+
+def test_fused_store_epilogue_bank_is_bit_identical_to_the_unfused_bank():
+    """The attack kernels applying clamp + straight-through + Quantization in their own stores
+    (wm_set_store_epilogue) must give exactly the values of: plain kernel, then the stand-alone
+    epilogue kernel — for every layer that has a fused path, on aligned and ragged shapes."""
+    import random
+    for shape, seed in (((2, 3, 64, 96), 81), ((1, 3, 48, 132), 82), ((2, 3, 40, 56), 83)):
+        x = rnd(shape, seed)
+        h, w = shape[2:]
+        def layers():
+            ls = [wmattack.Resize(), wmattack.Resize(interpolation_method="bilinear"), wmattack.JpegMask(50), wmattack.Jpeg(70),
+                  wmattack.JpegSS(30), wmattack.JpegCompression(DEV), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5),
+                  wmattack.GaussianBlur(), wmattack.GaussianBlur(7), wmattack.Gaussian(), wmattack.Identity(),
+                  wmattack.Combined([wmattack.JpegMask(70), wmattack.Jpeg(70), wmattack.MiddleBlur(3)]), wmattack.SaltPepper(0.05)]
+            if h % 16 == 0 and w % 16 == 0:
+                ls.append(wmattack.DiffJPEG(True, h, w, quality=50))
+            return ls
+        outs = []
+        for fused in (True, False):
+            np.random.seed(5); random.seed(5); torch.manual_seed(5)
+            WF._rng_calls = 0                                   # same Philox sub-streams in both runs
+            bank = wmattack.AttackBank(layers())
+            bank.fused = fused
+            xx = x.to(DEV).requires_grad_(True)
+            y = bank(xx)
+            g = rnd(tuple(y.shape), seed + 100)
+            y.backward(g.to(DEV))
+            outs.append((y.detach().cpu(), xx.grad.cpu(), list(bank.names)))
+        assert outs[0][2] == outs[1][2]
+        assert torch.equal(outs[0][0], outs[1][0]), shape
+        assert torch.equal(outs[0][1], outs[1][1])
+        k = len(outs[0][2])
+        assert md(outs[0][1], g.view(k, *shape).sum(0)) <= 1e-5

@@ -127,3 +127,33 @@ if "noise" in which:
     fwd_bwd("gaussian", lambda t: gn(t), 24, 36)
     sp = wmattack.SaltPepper(0.01)
     fwd_bwd("saltpepper", lambda t: sp(t), 24, 24)
+
+if "crop" in which:
+    box = (int(0.2 * H), int(0.2 * H) + int(0.7 * H), int(0.1 * W), int(0.1 * W) + int(0.75 * W))
+    def crop_ref(t):
+        c = t[:, :, box[0]:box[1], box[2]:box[3]]
+        return F.interpolate(c, size=(H, W), mode="bilinear")
+    cm = wmattack.Crop()
+    fwd_bwd("crop 0.7x0.75 bilinear", lambda t: cm(t, apex=box)[0], 24, 24, crop_ref)
+
+if "bank" in which:
+    layers = [wmattack.Resize(), wmattack.JpegMask(70), wmattack.MiddleBlur(3), wmattack.GaussianBlur(), wmattack.Gaussian(), wmattack.Identity()]
+    bank = wmattack.AttackBank(layers)
+    quant = wmattack.Quantization()
+    def torch_style(t):          # models/IRNp_model.py:609-680 with torch elementwise ops around OUR attack kernels
+        import numpy as _np
+        sims = [torch.clamp(l(t.detach()), 0, 1) for l in layers]
+        rep = t.repeat(len(layers), 1, 1, 1)
+        att = rep + (torch.cat(sims, 0) - rep).detach()
+        return quant(att)
+    xx = x.clone().requires_grad_(True)
+    gk = torch.rand(6 * B, 3, H, W, device=dev)
+    us_bank = timeit(lambda: bank(xx)); us_torch = timeit(lambda: torch_style(xx))
+    print(f"6-way bank fwd: fused epilogue into batch slices {us_bank:.0f} us  vs torch clamp/sub/add/cat + Quantization {us_torch:.0f} us", flush=True)
+    yb = bank(xx)
+    def stepb():
+        xx.grad = None; yb.backward(gk, retain_graph=True)
+    yt = torch_style(xx)
+    def stept():
+        xx.grad = None; yt.backward(gk, retain_graph=True)
+    print(f"6-way bank bwd (straight-through sum over slices): {timeit(stepb):.0f} us  vs torch autograd {timeit(stept):.0f} us", flush=True)

@@ -88,6 +88,7 @@ constexpr int BT_TW = 128, BT_TH = 64, BT_HALO = 4, BT_BW = BT_TW + 2 * BT_HALO,
 struct BlurTArgs {
     float* y; int N, H, W, tiles_x, tiles_y; int64_t total;
     float taps[8];
+    StoreEp ep;
 };
 
 template <int K> constexpr int bt_stages() { return K <= 5 ? 3 : 2; }
@@ -164,7 +165,10 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
                 for (int j = 1; j < K; ++j) acc = fmaf(w[j], h[(r + j) % K][c4], acc);
                 op[c4] = acc;
             }
-            if (col_ok && gy0 + r < a.H) stg128(dst + int64_t(r) * a.W, o);
+            if (col_ok && gy0 + r < a.H) {
+                if (a.ep.x) o = ep_apply4(o, a.ep.x + (dst - a.y) + int64_t(r) * a.W, a.ep);
+                stg128(dst + int64_t(r) * a.W, o);
+            }
         }
         __syncthreads();                      // every lane is done with stage s
         if (tid == 0) {
@@ -188,6 +192,7 @@ static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y,
     a.tiles_x = (W + BT_TW - 1) / BT_TW; a.tiles_y = (H + BT_TH - 1) / BT_TH;
     a.total = int64_t(N) * a.tiles_x * a.tiles_y;
     for (int i = 0; i < K; ++i) a.taps[i] = taps_host[i];
+    a.ep = take_store_epilogue();
     const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
     cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
@@ -246,6 +251,7 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
     for (int i = 0; i < k; ++i) a.taps[i] = taps_host[i];
     cudaStream_t st = (cudaStream_t)stream;
     if (border == 1 && adjoint) {
+        if (reject_store_epilogue("wm_gaussblur (reflect adjoint)")) return WM_E_ARG;
         const int64_t total = int64_t(N) * H * W;
         const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 16;
         gaussblur_reflect_adjoint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a);
@@ -257,6 +263,7 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
         if (k == 5) return launch_blur_tma<5>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
         return launch_blur_tma<7>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
     }
+    if (reject_store_epilogue("wm_gaussblur (generic path)")) return WM_E_ARG;
     const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;
     const size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * BL_TW);
     cudaError_t e = cudaFuncSetAttribute(gaussblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -105,6 +105,7 @@ struct DJArgs {
     float* dY;                  // [B, H, W]        round'(q) of the luminance coefficient at [8i+u, 8j+v]
     float* dC;                  // [B, 2, H/2, W/2] round'(q) of Cb, Cr (per-thread quadrant order)
     unsigned long long* cm;     // [B, H, W/8]      clamp codes of one 8-pixel row: 2 bits x (8 px x RGB)
+    StoreEp ep;                 // forward-only kernel: store epilogue (x dense, same layout as out)
     int B, H, W;
     int mcu_w, mcu_per_img; int64_t n_mcu;
     float factor; const float* factor_ps;
@@ -347,7 +348,7 @@ __device__ __forceinline__ void dj_chroma_terms(const float (&cb)[4], const floa
 }
 
 // Final phase of forward / decompress: row IDCT, upsampled chroma, colour transform, clamp.
-template <int NT>
+template <int NT, bool EP = false>
 __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, const float4* scr) {
     float* yo = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
     const int64_t plane = int64_t(a.H) * a.W;
@@ -373,6 +374,15 @@ __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, 
             }
             if (t.active) {
                 float* p = yo + int64_t(r) * a.W;
+                if (EP) {          // store epilogue: x at the output position
+                    const float* xp = a.ep.x + (p - a.out);
+                    const f8 xR = ldg256_stream(xp), xG = ldg256_stream(xp + plane), xB = ldg256_stream(xp + 2 * plane);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        oR.v[c] = ep_apply(oR.v[c], xR.v[c], a.ep); oG.v[c] = ep_apply(oG.v[c], xG.v[c], a.ep);
+                        oB.v[c] = ep_apply(oB.v[c], xB.v[c], a.ep);
+                    }
+                }
                 stg256(p, oR);
                 stg256(p + plane, oG);
                 stg256(p + 2 * plane, oB);

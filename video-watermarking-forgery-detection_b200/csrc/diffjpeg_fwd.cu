@@ -3,7 +3,7 @@
 
 namespace wm {
 
-template <int ROUND>
+template <int ROUND, bool EP = false>
 __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_kernel(const DJArgs a) {
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_kernel(const DJArg
     quad_coef_init(qx, t.bx);
     quad_coef_init(qy, t.by);
     dj_chroma_planes<ROUND, false, false, DJ_THREADS>(scr, qx, qy, t.bx, t.by, f);
-    dj_emit_rgb<DJ_THREADS>(a, t, scr);
+    dj_emit_rgb<DJ_THREADS, EP>(a, t, scr);
 }
 
 // Forward that also saves what the backward needs (7 B/px: round'(q) of every coefficient and the
@@ -66,5 +66,15 @@ extern "C" int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
+    a.ep = take_store_epilogue();
+    if (a.ep.x) {
+        switch (rounding) {
+            case WM_ROUND_ONLY_AT_0: return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_ONLY_AT_0, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_CUBIC:     return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_CUBIC, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_HARD:      return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_HARD, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_FOURIER:   return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_FOURIER, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            default: set_error("unknown rounding mode %d", rounding); return WM_E_ARG;
+        }
+    }
     DJ_DISPATCH_ROUND(diffjpeg_fwd_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd")
 }

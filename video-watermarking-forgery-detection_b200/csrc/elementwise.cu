@@ -66,11 +66,11 @@ __device__ __forceinline__ void st4(float* p, int64_t i, int64_t n, float4 v) {
 // ---- Gaussian / GN ---------------------------------------------------------------------------
 // fwd: y = [clamp01](x + mean + std * N);  bwd: gx = gy * 1[0 <= x + noise <= 1] (torch.clamp is
 // inclusive) or gy when not clamped.
-template <bool BWD>
+template <bool BWD, bool EP>
 __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                                                          float* __restrict__ out, int64_t n, float mean, float std,
                                                          int clamp, uint64_t seed, uint64_t offset,
-                                                         const float* __restrict__ inject) {
+                                                         const float* __restrict__ inject, const StoreEp ep) {
     const Philox ph(seed);
     WM_EW_LOOP(i) {
         float4 nz;
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
         if (!BWD) {
             if (clamp) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
                          v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
+            if (EP) {
+                const float4 ex = ld4(ep.x, i, n);
+                v = make_float4(ep_apply(v.x, ex.x, ep), ep_apply(v.y, ex.y, ep), ep_apply(v.z, ex.z, ep), ep_apply(v.w, ex.w, ep));
+            }
             st4(out, i, n, v);
         } else {
             float4 g = ld4(gy, i, n);
@@ -290,7 +294,9 @@ extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean
     WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
-    gaussnoise_kernel<false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject);
+    const StoreEp ep = take_store_epilogue();
+    if (ep.x) gaussnoise_kernel<false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
+    else gaussnoise_kernel<false, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd");
     return WM_OK;
 }
@@ -304,7 +310,8 @@ extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int
         cudaError_t e = cudaMemcpyAsync(gx, gy, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
         return e == cudaSuccess ? WM_OK : cuda_fail(e, "wm_gaussnoise_bwd");
     }
-    gaussnoise_kernel<true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, mean, std, clamp, seed, offset, inject);
+    gaussnoise_kernel<true, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, mean, std, clamp, seed, offset, inject,
+                                                                                  StoreEp{nullptr, 0, 0});
     WM_LAUNCH_CHECK("wm_gaussnoise_bwd");
     return WM_OK;
 }

@@ -25,6 +25,7 @@ struct J8Args {
     float fwd[9], inv[9];
     float table[3][64];
     float rtable[3][64];
+    StoreEp ep;
 };
 
 struct J8Thread { bool active; int b, row0, col0; };
@@ -360,6 +361,14 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
         }
         const bool ok = active && (row0 + r) < a.H;
         float* p = yo + int64_t(i) * a.W;
+        if (a.ep.x && ok) {          // store epilogue: x at the output position (dense, same layout as out)
+            const float* xp = a.ep.x + (p - a.out);
+            const f8 xR = ldg256_stream(xp), xG = ldg256_stream(xp + plane), xB = ldg256_stream(xp + 2 * plane);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                oR[c] = ep_apply(oR[c], xR.v[c], a.ep); oG[c] = ep_apply(oG[c], xG.v[c], a.ep); oB[c] = ep_apply(oB[c], xB.v[c], a.ep);
+            }
+        }
         j8_store_row<true>(p, ok, 8, oR);
         j8_store_row<true>(p + plane, ok, 8, oG);
         j8_store_row<true>(p + 2 * plane, ok, 8, oB);
@@ -576,6 +585,8 @@ extern "C" int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
     WM_REQUIRE(y != nullptr, WM_E_NULL, "wm_jpeg8_fwd: null output");
     a.out = y;
     const bool vec = j8_vec_ok(x, x_sb, x_sc, x_sh, W) && aligned(y, 32);
+    if (vec && p->subsample == 0) a.ep = take_store_epilogue();       // the two-threads-per-block kernel applies it
+    else if (reject_store_epilogue("wm_jpeg8_fwd (ragged / subsampled path)")) return WM_E_ARG;
     return j8_fwd_any(a, p->variant, p->subsample, vec, false, (cudaStream_t)stream, "wm_jpeg8_fwd");
 }
 

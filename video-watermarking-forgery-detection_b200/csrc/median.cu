@@ -130,9 +130,10 @@ constexpr int MT_TW = 128, MT_TH = 64, MT_HALO = 4, MT_BW = MT_TW + 2 * MT_HALO,
 
 struct MedTArgs {
     float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
+    StoreEp ep;
 };
 
-template <bool WANT_IDX>
+template <bool WANT_IDX, bool EP>
 __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[MT_STAGES];
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
                 }
             }
             if (col_ok && gy0 + r < a.H) {
+                if (EP) o = ep_apply4(o, a.ep.x + obase + int64_t(r) * a.W, a.ep);
                 stg128(a.y + obase + int64_t(r) * a.W, o);
                 if (WANT_IDX) *reinterpret_cast<uint32_t*>(a.idx + obase + int64_t(r) * a.W) = packed;
             }
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
 constexpr int M5_TW = 128, M5_TH = 70, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
               M5_THREADS = 256, M5_ROWS = 35, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
 
-template <bool WANT_IDX>
+template <bool WANT_IDX, bool EP>
 __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[M5_STAGES];
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
                     for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[j][k];
                 const float med = median25_sorted_groups(v);
                 if (col_ok && gy0 + r < a.H) {
-                    a.y[obase + int64_t(r) * a.W] = med;
+                    a.y[obase + int64_t(r) * a.W] = EP ? ep_apply(med, a.ep.x[obase + int64_t(r) * a.W], a.ep) : med;
                     if (WANT_IDX) {
                         float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
 #pragma unroll
@@ -474,10 +476,12 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        ta.ep = take_store_epilogue();
         const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
-        auto kern = idx ? median3_tma_kernel<true> : median3_tma_kernel<false>;
+        auto kern = ta.ep.x ? (idx ? median3_tma_kernel<true, true> : median3_tma_kernel<false, true>)
+                            : (idx ? median3_tma_kernel<true, false> : median3_tma_kernel<false, false>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
         const int64_t cap = int64_t(sm_count()) * 2;
@@ -491,10 +495,12 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0};
+        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0, StoreEp{nullptr, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        ta.ep = take_store_epilogue();
         const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
-        auto kern = idx ? median5_tma_kernel<true> : median5_tma_kernel<false>;
+        auto kern = ta.ep.x ? (idx ? median5_tma_kernel<true, true> : median5_tma_kernel<false, true>)
+                            : (idx ? median5_tma_kernel<true, false> : median5_tma_kernel<false, false>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
         const int64_t cap = int64_t(sm_count()) * 2;
@@ -502,6 +508,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
         WM_LAUNCH_CHECK("wm_median_fwd(tma5)");
         return WM_OK;
     }
+    if (reject_store_epilogue("wm_median_fwd (generic path)")) return WM_E_ARG;
     MedArgs a{x, x_sp, x_sh, y, idx, N, H, W};
     const int tiles = ((W + MD_TW - 1) / MD_TW) * ((H + MD_TH - 1) / MD_TH);
     dim3 grid(tiles, N);

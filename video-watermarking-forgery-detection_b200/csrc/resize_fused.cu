@@ -131,6 +131,7 @@ struct RBArgs {
     const int* loy; const float* wy;              // row-axis tables
     int N, H, W, tiles_x, tiles_y;
     int* overflow;                                // optional: set to 1 if a band did not fit its window
+    StoreEp ep;                                   // forward only: store epilogue (x dense, same layout as dst)
 };
 
 template <int BT> struct RBGeom {
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     if (DIR == 0) {
                         const float4 c = make_float4(__saturatef(acc[k].x), __saturatef(acc[k].y), __saturatef(acc[k].z),
                                                      __saturatef(acc[k].w));
-                        if (okc && okr) stg128(drow + k * a.W, c);
+                        if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4(c, a.ep.x + (drow - a.dst) + k * a.W, a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc[k].x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc[k].y);
@@ -409,6 +410,7 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
     a.loy = reinterpret_cast<const int*>(ty); a.wy = ty + H;
     a.N = N; a.H = H; a.W = W; a.tiles_x = (W + RB_TW - 1) / RB_TW; a.tiles_y = (H + RB_TH - 1) / RB_TH;
     a.overflow = reinterpret_cast<int*>(const_cast<float*>(by + rb_axis_words(H, BT)));
+    a.ep = dir == 0 ? take_store_epilogue() : StoreEp{nullptr, 0, 0};
     CUtensorMap tm{}, tmm{};
     int rc = 0;
     cudaStream_t st = (cudaStream_t)stream;

@@ -69,6 +69,25 @@ __device__ __forceinline__ float fast_rcp(float b) {
     float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r;
 }
 
+// ---- store epilogue: out = Quantization( x + (clamp(v, 0, 1) - x) ) applied by a
+// forward kernel in its own store, x read at the output position (models/IRNp_model.py:674-680).
+// Armed per host thread by wm_set_store_epilogue for the NEXT forward launch (see include/wm_attack.h).
+struct StoreEp { const float* x; int clamp01; int quant; };
+void arm_store_epilogue(const StoreEp& e);
+StoreEp take_store_epilogue();                 // returns this thread's pending descriptor and clears it
+bool reject_store_epilogue(const char* who);   // true (and an error message) if one is pending
+
+__device__ __forceinline__ float ep_apply(float v, float x, const StoreEp& e) {
+    if (e.clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    v = __fadd_rn(x, __fsub_rn(v, x));                       // same fp32 operation order as the reference
+    if (e.quant) v = __fdiv_rn(rintf(__fmul_rn(v, 255.f)), 255.f);
+    return v;
+}
+__device__ __forceinline__ float4 ep_apply4(float4 v, const float* xp, const StoreEp& e) {
+    const float4 x = *reinterpret_cast<const float4*>(xp);
+    return make_float4(ep_apply(v.x, x.x, e), ep_apply(v.y, x.y, e), ep_apply(v.z, x.z, e), ep_apply(v.w, x.w, e));
+}
+
 inline int sm_count() {
     static int n = 0;
     if (!n) {

@@ -57,6 +57,7 @@ SIGNATURES = {
     "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
     "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
     "wm_u8_to_unit_float": [c_u8p, c_f32p, i64, vp],
+    "wm_set_store_epilogue": [c_f32p, i32, i32],
     "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
     "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],
     "wm_splice_fwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
@@ -69,6 +70,7 @@ SIGNATURES = {
 # kernels launched by one successful call (wm_interp_bwd runs its two gather passes)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 KERNELS_PER_CALL["wm_resize_tables"] = 4
+KERNELS_PER_CALL["wm_set_store_epilogue"] = 0
 # plain (non-status) helpers: name -> (restype, argtypes)
 HELPERS = {"wm_interp_is_tiled": (C.c_int, [i32, i32, i32, i32, i32]),
            "wm_resize_is_fused": (C.c_int, [i32, i32, i32, i32, i32]),

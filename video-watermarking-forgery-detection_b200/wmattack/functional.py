@@ -781,3 +781,135 @@ def from_uint8(frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
         raise ValueError("from_uint8: `out` must be a contiguous float32 tensor of the same shape")
     _lib.call("wm_u8_to_unit_float", frames.data_ptr(), out.data_ptr(), frames.numel(), _stream())
     return out
+
+
+# ---- fused store epilogue: the attack kernel itself writes Quantization(x + (clamp(v) - x)) ---------
+
+def _armed(ep):
+    """ep = (x_dense, clamp, quantize) or None.  Arms the epilogue for the next forward launch."""
+    if ep is not None:
+        _lib.call("wm_set_store_epilogue", ep[0].data_ptr(), int(ep[1]), int(ep[2]))
+
+
+def _disarm():
+    _lib.call("wm_set_store_epilogue", None, 0, 0)
+
+
+def _out_ok(out, shape):
+    return out is not None and tuple(out.shape) == tuple(shape) and out.is_contiguous() and out.dtype == torch.float32 \
+        and out.data_ptr() % 32 == 0
+
+
+def diffjpeg_into(x, factor, rounding, out, ep=None) -> bool:
+    """No-grad DiffJPEG forward written into `out` (optionally through the store epilogue)."""
+    x, sb, sc, sh = _image(x, "DiffJPEG")
+    b, c, h, w = x.shape
+    if c != 3 or h % 16 or w % 16 or not _out_ok(out, x.shape):
+        return False
+    fs, fps = _factor_args(factor, b, x.device)
+    _armed(ep)
+    _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+    return True
+
+
+def jpeg8_into(x, params, out, ep=None) -> bool:
+    x, sb, sc, sh = _image(x, "jpeg8")
+    b, c, h, w = x.shape
+    if c != 3 or w % 8 or params.subsample != 0 or not _out_ok(out, x.shape):
+        return False
+    _armed(ep)
+    _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _stream())
+    return True
+
+
+def gaussian_blur_into(x, taps, out, ep=None) -> bool:
+    x, sp, sh = _planes(x, "gaussian blur")
+    b, c, h, w = x.shape
+    if len(taps) not in (3, 5, 7) or w % 4 or sp % 4 or sh % 4 or x.data_ptr() % 16 or not _out_ok(out, x.shape):
+        return False
+    _armed(ep)
+    _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, out.data_ptr(), b * c, h, w, _taps_array(taps), len(taps), 0, 0, _stream())
+    return True
+
+
+def median_blur_into(x, k, out, ep=None) -> bool:
+    x, sp, sh = _planes(x, "median blur")
+    b, c, h, w = x.shape
+    if k not in (3, 5) or sp % 4 or sh % 4 or x.data_ptr() % 16 or (k == 3 and w % 4) or not _out_ok(out, x.shape):
+        return False
+    _armed(ep)
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _stream())
+    return True
+
+
+def gaussian_noise_into(x, mean, std, clamp, out, ep=None) -> bool:
+    x = _flat(x, "gaussian noise")
+    if not _out_ok(out, x.shape):
+        return False
+    seed, offset = next_philox_stream(x.numel())
+    _armed(ep)
+    _lib.call("wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
+              seed, offset, None, _stream())
+    return True
+
+
+def resize_roundtrip_into(x, mid_hw, mode, out, ep=None) -> bool:
+    h, w = x.shape[2:]
+    mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
+    n = x.shape[0] * x.shape[1]
+    x, sp, sh = _planes(x, "resize")
+    if not (_lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and sp % 4 == 0 and sh % 4 == 0
+            and x.data_ptr() % 16 == 0 and _out_ok(out, x.shape)):
+        return False
+    tables = _resize_tables(x.device, h, w, mid_hw, _MODES[mode])
+    _armed(ep)
+    _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, out.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], _MODES[mode],
+              None, tables.data_ptr(), _stream())
+    return True
+
+
+class _BankFusedFn(torch.autograd.Function):
+    """K attacked variants written by the attack kernels themselves, through the store epilogue, into
+    the slices of one [K*B, C, H, W] tensor; layers without a fused path run normally and are
+    finished by the stand-alone epilogue kernel.  Backward: straight-through, gx = sum_k gy_k."""
+
+    @staticmethod
+    def forward(ctx, x, clamp, quantize, layers):
+        x = _flat(x.detach(), "attack bank")
+        if x.data_ptr() % 32:
+            x = x.clone()
+        k, n = len(layers), x.numel()
+        out = torch.empty((k * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+        ep = (x, clamp, quantize)
+        names = []
+        for i, layer in enumerate(layers):
+            sl = out[i * x.shape[0]:(i + 1) * x.shape[0]]
+            fused = False
+            into = getattr(layer, "forward_into", None)
+            if into is not None:
+                try:
+                    fused = bool(into(x, sl, ep))
+                finally:
+                    if not fused:
+                        _disarm()
+            if not fused:
+                y = layer(x)
+                y = y[0] if isinstance(y, tuple) else y
+                _lib.call("wm_attack_epilogue_fwd", x.data_ptr(), _flat(y, "attack bank").data_ptr(), sl.data_ptr(), n,
+                          int(clamp), int(quantize), _stream())
+            names.append(getattr(layer, "name", type(layer).__name__))
+        ctx.meta = (k, tuple(x.shape))
+        ctx.names = names
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, shape = ctx.meta
+        gy = _flat(gy, "attack bank backward")
+        gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
+        _lib.call("wm_slice_sum", gy.data_ptr(), gx.data_ptr(), gx.numel(), k, _stream())
+        return gx, None, None, None
+
+
+def attack_bank_fused(x, layers, clamp: bool = True, quantize: bool = True):
+    return _BankFusedFn.apply(x, clamp, quantize, list(layers))

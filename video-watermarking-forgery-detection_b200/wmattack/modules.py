@@ -83,6 +83,14 @@ class Identity(nn.Module):
         return image
 
 
+def _identity_into(self, x, out, ep):
+    F_.attack_epilogue(x, x, ep[1], ep[2], out=out)
+    return True
+
+
+Identity.forward_into = _identity_into
+
+
 class Combined(nn.Module):
     """noise_layers/combined.py:6-20: one member per call, chosen with python `random`."""
 
@@ -92,6 +100,19 @@ class Combined(nn.Module):
             list = [Identity()]
         self.list = list            # plain python list, as upstream (not an nn.ModuleList)
         self.name = "NotChosenYet"
+
+    def forward_into(self, x, out, ep, id=None):  # noqa: A002
+        """AttackBank hook: same choice logic as forward(), then the member's fused path if it has one."""
+        if id is None or id >= len(self.list):
+            id = get_random_int([0, len(self.list) - 1])
+        selected = self.list[id]
+        self.name = selected.name
+        into = getattr(selected, "forward_into", None)
+        if into is not None and into(x, out, ep):
+            return True
+        y = selected(x)
+        F_.attack_epilogue(x, y[0] if isinstance(y, tuple) else y, ep[1], ep[2], out=out)
+        return True
 
     def forward(self, image_and_cover, id=None):  # noqa: A002
         if id is None or id >= len(self.list):
@@ -156,6 +177,10 @@ class DiffJPEG(nn.Module):
             return (torch.where(q < 50, 5000.0 / q, 200.0 - 2.0 * q) / 100.0).to(torch.float32)
         return quality_to_factor(quality)
 
+    def forward_into(self, x, out, ep):
+        """No-grad forward written into `out` through the fused store epilogue (AttackBank)."""
+        return F_.diffjpeg_into(x, self.factor, self.rounding, out, ep)
+
     def forward(self, image, quality=None):
         image = _first(image)
         factor = self.factor if quality is None else self._factor_of(quality)
@@ -203,6 +228,9 @@ class JpegBasic(nn.Module):
 
     def _table(self) -> np.ndarray:
         return _mbrs_tables(self.scale_factor)
+
+    def forward_into(self, x, out, ep):
+        return F_.jpeg8_into(x, self._params, out, ep)
 
     def forward(self, image):
         return F_.jpeg8(_first(image), self._params)
@@ -285,6 +313,9 @@ class JpegCompression(nn.Module):
         table = np.stack([_zigzag_keep(k) for k in yuv_keep_weights])
         self._params = F_.make_jpeg8_params(fwd, inv, table, F_.JPEG8_MASK, 0)
 
+    def forward_into(self, x, out, ep):
+        return F_.jpeg8_into(x, self._params, out, ep)
+
     def forward(self, noised_image):
         return F_.jpeg8(_first(noised_image), self._params)
 
@@ -308,6 +339,12 @@ class GaussianBlur(nn.Module):
         if kernel_size % 2 == 0:
             raise ValueError("even kernel sizes change the output size upstream; only odd sizes are supported")
         self._taps = _gaussian_taps(kernel_size, 2.0, (kernel_size - 1) / 2.0)
+
+    def forward_into(self, x, out, ep):
+        ok = F_.gaussian_blur_into(x, self._taps, out, ep)
+        if ok:
+            self.name = "GaussianBlur"                      # gaussian_blur.py:54 renames on first use
+        return ok
 
     def forward(self, tensor, cover_image=None):
         self.name = "GaussianBlur"
@@ -341,6 +378,9 @@ class MiddleBlur(nn.Module):
         self.kernel = kernel
         self.name = "MiddleBlur" + str(kernel)
 
+    def forward_into(self, x, out, ep):
+        return F_.median_blur_into(x, self.kernel, out, ep)
+
     def forward(self, image):
         return F_.median_blur(_first(image), self.kernel)
 
@@ -353,6 +393,10 @@ class Gaussian(nn.Module):
         super().__init__()
         self.name = "Gaussian"
         self.host_rng = host_rng
+
+    def forward_into(self, x, out, ep):
+        self.name = "Gaussian"
+        return F_.gaussian_noise_into(x, 0.0, 0.05, True, out, ep)
 
     def forward(self, tensor, cover_image=None, mean=0, stddev=0.05, noise=None):
         self.name = "Gaussian"
@@ -490,6 +534,16 @@ class Resize(nn.Module):
             raise ValueError("interpolation_method must be 'bicubic' or 'bilinear'")
         self.interpolation_method = interpolation_method
 
+    def forward_into(self, x, out, ep):
+        h, w = x.shape[2], x.shape[3]
+        r = random_float(self.resize_ratio_min, self.resize_ratio_max)        # same RNG call as forward()
+        mid = (int(r * h), int(r * w))
+        if F_.resize_roundtrip_into(x, mid, self.interpolation_method, out, ep):
+            return True
+        out_plain = F_.resize_roundtrip(x, mid, self.interpolation_method)      # keep the ratio that was drawn
+        F_.attack_epilogue(x, out_plain, ep[1], ep[2], out=out)
+        return True
+
     def forward(self, noised_image, resize_ratio=None):
         self.name = "Resize"
         noised_image = _first(noised_image)
@@ -616,8 +670,14 @@ class AttackBank(nn.Module):
         self.list = list(layers)          # plain list, like Combined (noise_layers/combined.py:10)
         self.clamp, self.quantize = clamp, quantize
         self.names = []
+        self.fused = True                 # False: run every layer plainly + the stand-alone epilogue kernel
 
     def forward(self, x):
+        if self.fused:
+            # the attack kernels write clamp + straight-through + Quantization in their own stores
+            y = F_._BankFusedFn.apply(x, self.clamp, self.quantize, self.list)
+            self.names = [getattr(layer, "name", type(layer).__name__) for layer in self.list]
+            return y
         with torch.no_grad():             # straight-through: the attacks' own graphs are never needed
             sims = []
             self.names = []
