@@ -416,15 +416,22 @@ __device__ __forceinline__ void dj_emit_rgb_save(const DJArgs& a, const DJThread
             scr_load_row<NT>(scr, r, yv);
             idct8(yv);
             f8 oR, oG, oB;
-            unsigned lo = 0, hi = 0;          // pixels 0-3 (24 bits) and 4-7 (24 bits)
+            // codes accumulated in base 4 as exact fp32 integers (< 2^24 per 4 pixels) with FSET + FFMA:
+            // code = 2 * [s == u] - [0 < s < 1]  (1 strictly inside, 2 exactly on a bound, 0 outside)
+            float accl = 0.f, acch = 0.f;     // pixels 0-3 and 4-7; pixel c occupies bits 6c .. 6c+5 (R, G, B)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 7; c >= 0; --c) {
                 const float uR = fmaf(yv[c], DJ_I255, tR[c >> 1]), uG = fmaf(yv[c], DJ_I255, tG[c >> 1]),
                             uB = fmaf(yv[c], DJ_I255, tB[c >> 1]);
-                oR.v[c] = __saturatef(uR); oG.v[c] = __saturatef(uG); oB.v[c] = __saturatef(uB);
-                const unsigned code = clamp_code(uR) | (clamp_code(uG) << 2) | (clamp_code(uB) << 4);
-                if (c < 4) lo |= code << (6 * c); else hi |= code << (6 * (c - 4));
+                const float sR = __saturatef(uR), sG = __saturatef(uG), sB = __saturatef(uB);
+                oR.v[c] = sR; oG.v[c] = sG; oB.v[c] = sB;
+                const float cB = fmaf(fset_eq(sB, uB), 2.f, -fset_gt(fmaf(-sB, sB, sB), 0.f));
+                const float cG = fmaf(fset_eq(sG, uG), 2.f, -fset_gt(fmaf(-sG, sG, sG), 0.f));
+                const float cR = fmaf(fset_eq(sR, uR), 2.f, -fset_gt(fmaf(-sR, sR, sR), 0.f));
+                float& acc = c < 4 ? accl : acch;
+                acc = fmaf(fmaf(fmaf(acc, 4.f, cB), 4.f, cG), 4.f, cR);
             }
+            const unsigned lo = __float2uint_rn(accl), hi = __float2uint_rn(acch);
             if (t.active) {
                 float* p = yo + int64_t(r) * a.W;
                 stg256(p, oR);

@@ -58,6 +58,15 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
 }
 
+// comparisons as 1.0f / 0.0f (FSET.BF): lets bit fields be accumulated with FFMA on the FMA pipe
+// instead of FSETP + SEL pairs on the half-rate ALU pipe
+__device__ __forceinline__ float fset_eq(float a, float b) {
+    float d; asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d;
+}
+__device__ __forceinline__ float fset_gt(float a, float b) {
+    float d; asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d;
+}
+
 // a / b with one Newton correction on MUFU.RCP: correctly rounded for the operand ranges
 // of the quantiser (no denormals/inf) at 1/3 the issue cost of the IEEE division sequence.
 __device__ __forceinline__ float div_by_recip(float a, float b, float rb) {
