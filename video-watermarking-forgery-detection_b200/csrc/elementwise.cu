@@ -37,7 +37,10 @@ __device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t ctr) {
     // Box-Muller on (0,1] x [0,1)
     const float u1 = ((r.x >> 8) + 1) * (1.0f / 16777216.0f), u2 = u01(r.y);
     const float u3 = ((r.z >> 8) + 1) * (1.0f / 16777216.0f), u4 = u01(r.w);
-    const float ra = sqrtf(-2.f * __logf(u1)), rb = sqrtf(-2.f * __logf(u3));
+    // sqrt.approx (MUFU.SQRT, max 1 ulp): the radius of a RANDOM draw needs no IEEE rounding
+    float ra, rb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-2.f * __logf(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-2.f * __logf(u3)));
     float s1, c1, s2, c2;
     __sincosf(6.283185307179586f * u2, &s1, &c1);
     __sincosf(6.283185307179586f * u4, &s2, &c2);
