@@ -232,7 +232,8 @@ def test_two_rank_plumbing_on_gloo():
 def test_resize_band_bound():
     """The fused Resize kernel keeps, per lane, a register window of 8/10/12/14 taps of the banded
     operator A = U D (and of A^T).  Mirror of csrc/resize_fused.cu::rb_band: the window must hold the
-    band made regular over 32 consecutive outputs (H pass) and the band shared by a row pair (V pass)."""
+    band made regular over the outputs of a warp (H pass: two outputs per lane share a 10- or 14-wide window) and
+    the band shared by a quad of output rows (V pass: window + 2)."""
     import math
     import numpy as np
     from oracle import attack_oracle as O
@@ -263,5 +264,14 @@ def test_resize_band_bound():
                         l, h = lo[g0:g0 + 32], hi[g0:g0 + 32]
                         base = (l - np.arange(len(l))).min()
                         need = max(need, int((h - (base + np.arange(len(l))) + 1).max()))
-                    pair = int((np.maximum(hi[1:], hi[:-1]) - lo[:-1] + 1).max()) if n > 1 else 1
-                    assert max(need, pair) <= window(n, nm), (n, nm, mode, need, pair, window(n, nm))
+                    need2 = 0
+                    for g0 in range(0, n, 64):            # H pass as built: two outputs per lane, even regular starts
+                        l, h = lo[g0:g0 + 64], hi[g0:g0 + 64]
+                        if len(l) % 2:
+                            l, h = np.append(l, l[-1]), np.append(h, h[-1])
+                        lane = np.arange(len(l) // 2)
+                        base = int((l[0::2] - 2 * lane).min()); base -= base % 2
+                        need2 = max(need2, int((np.maximum(h[0::2], h[1::2]) - (base + 2 * lane) + 1).max()))
+                    quad = max(int(hi[o:o + 4].max() - lo[o] + 1) for o in range(0, n, 4))   # V pass: 4 rows share a window
+                    bt = window(n, nm)
+                    assert need <= bt and need2 <= (10 if bt <= 10 else 14) and quad <= bt + 2, (n, nm, mode, need, need2, quad, bt)

@@ -14,7 +14,8 @@
 // generic separable banded transform  Y = A_v X A_h^T  on shared-memory tiles:
 //   stage  : TMA box of the source region of a tile (backward: cotangent, then masked in place)
 //   H pass : lane = output column (its band weights live in registers), warps walk the rows
-//   V pass : lane = 4 adjacent columns (LDS.128), warps walk the output rows with broadcast weights,
+//   V pass : lane = 4 adjacent columns (LDS.128), warps walk output row QUADS that share one window of tmp
+//            (each tmp value is read (BT+2)/4 times instead of BT), broadcast weights,
 //            clamp + 1-bit pass-through mask (4 ballots per tile row), STG.128
 // CTAs are persistent over the planes of one tile position, so tables are read once per CTA.
 // The adjoint is the SAME kernel run with the tables of A^T: a deterministic gather, no atomics
@@ -138,9 +139,10 @@ template <int BT> struct RBGeom {
     static constexpr int IW = ((RB_TW + BT + 20 + 3) / 4) * 4;      // staged columns (start = 4-aligned band start - 8)
     static constexpr int IH = RB_TH + BT + 4;                       // staged rows
     static constexpr int IHA = ((IH + 7) / 8) * 8;                  // allocated rows (the H pass runs 8 rows per step)
-    static constexpr int NP = RB_TH / 2;                            // output row pairs of a tile
-    static constexpr size_t smem = sizeof(float) * (size_t(IHA) * IW + size_t(IHA) * RB_TW + size_t(NP) * 2 * BT) +
-                                   sizeof(int) * NP + sizeof(uint32_t) * IH * 12 + 128;
+    static constexpr int NQ = RB_TH / 4;                            // output row quads of a tile
+    static constexpr int BTV = BT + 2;                              // window shared by the 4 rows of a quad
+    static constexpr size_t smem = sizeof(float) * (size_t(IHA) * IW + size_t(IHA) * RB_TW + size_t(NQ) * 4 * BTV) +
+                                   sizeof(int) * NQ + sizeof(uint32_t) * IH * 12 + 128;
 };
 
 // DIR 0: forward (clamp, mask out)   DIR 1: adjoint (cotangent masked in shared memory, no clamp)
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     float* in = reinterpret_cast<float*>(smem_raw);                  // [IHA][IW] (TMA fills IH rows)
     float* tmp = in + G::IHA * G::IW;                                // [IHA][TW]
     uint32_t* mb = reinterpret_cast<uint32_t*>(tmp + G::IHA * RB_TW);   // [IH][12] mask words of the staged rows (adjoint)
-    float* wyp = reinterpret_cast<float*>(mb + G::IH * 12);          // [NP][2][BT] weights of a row pair on its shared window
-    int* ylop = reinterpret_cast<int*>(wyp + G::NP * 2 * BT);        // [NP] first staged row of the pair's window
+    float* wyq = reinterpret_cast<float*>(mb + G::IH * 12);          // [NQ][BTV][4] weights of a row quad on its shared window
+    int* yloq = reinterpret_cast<int*>(wyq + G::NQ * 4 * G::BTV);    // [NQ] first staged row of the quad's window
     __shared__ uint64_t full;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     const int xs = (__ldg(a.lox + ox0) & ~3) - 8;
     const int ys = __ldg(a.loy + oy0);
     // rows the V pass can touch (rows past the image bottom are staged as zeros: their weights are 0)
-    const int ih = min(__ldg(a.loy + oy0 + th - 1) + BT - ys, G::IH);
+    const int ih = min(max(__ldg(a.loy + oy0 + th - 1) + BT, __ldg(a.loy + oy0 + ((th - 1) & ~3)) + BT + 2) - ys, G::IH);
 
     // H pass role: lane = TWO adjacent output columns whose bands share one window of BTW source
     // values, read as BTW/2 LDS.64.  The 32 windows of a warp are made REGULAR (start = even base +
@@ -202,17 +204,17 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     const int hbase = min(max(hs - xs, 0), G::IW - BTW) & ~1;
     if (a.overflow && hv0 && hbase != hs - xs) atomicExch(a.overflow, 1);
 
-    // V pass tables: rows (2p, 2p+1) share the window starting at the first row's band start
-    for (int i = tid; i < G::NP * BT; i += RB_THREADS) {
-        const int p = i / BT, t = i - p * BT;
-        const int r0 = min(oy0 + 2 * p, a.H - 1), r1 = min(oy0 + 2 * p + 1, a.H - 1);
-        const int d = __ldg(a.loy + r1) - __ldg(a.loy + r0);
-        wyp[(2 * p) * BT + t] = __ldg(a.wy + int64_t(r0) * BT + t);
+    // V pass tables: rows 4p .. 4p+3 share the BTV-row window that starts at the first row's band start
+    constexpr int BTV = G::BTV;
+    for (int i = tid; i < G::NQ * BTV * 4; i += RB_THREADS) {
+        const int p = i / (BTV * 4), t = (i / 4) % BTV, k = i & 3;
+        const int r0 = min(oy0 + 4 * p, a.H - 1), rk = min(oy0 + 4 * p + k, a.H - 1);
+        const int d = __ldg(a.loy + rk) - __ldg(a.loy + r0);
         const int j = t - d;
-        wyp[(2 * p + 1) * BT + t] = (j >= 0 && j < BT) ? __ldg(a.wy + int64_t(r1) * BT + j) : 0.f;
-        if (a.overflow && t >= BT - d && t >= 0 && __ldg(a.wy + int64_t(r1) * BT + t) != 0.f) atomicExch(a.overflow, 1);
+        wyq[i] = (j >= 0 && j < BT) ? __ldg(a.wy + int64_t(rk) * BT + j) : 0.f;
+        if (a.overflow && t < BT && t + d >= BTV && __ldg(a.wy + int64_t(rk) * BT + t) != 0.f) atomicExch(a.overflow, 1);
     }
-    if (tid < G::NP) ylop[tid] = min(max(__ldg(a.loy + min(oy0 + 2 * tid, a.H - 1)) - ys, 0), G::IH - BT);
+    if (tid < G::NQ) yloq[tid] = min(max(__ldg(a.loy + min(oy0 + 4 * tid, a.H - 1)) - ys, 0), G::IH - BTV);
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         mbar_init(&full, 1);
@@ -275,52 +277,51 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         // `in` is dead: prefetch the next plane's tile while the V pass runs
         if (tid == 0 && n + gridDim.z < a.N) request(n + gridDim.z);
 
-        // ---- V pass: rows (2p, 2p+1) x 4 columns per lane from one shared window of tmp -----------
+        // ---- V pass: rows 4p .. 4p+3 x 4 columns per lane from one shared window of tmp --------------
         {
             const bool okc = 4 * lane < tw;
             const bool want_mask = DIR == 0 && a.mask != nullptr;
-            // running pointers of this warp's row pairs (pr = warp, warp + 8, ...)
-            float* drow = a.dst + (int64_t(n) * a.H + oy0 + 2 * warp) * a.W + ox0 + 4 * lane;
-            uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 2 * warp) * a.tiles_x + tx) * 4 + (lane & 3);
-            const int drow_step = 2 * (RB_THREADS / 32) * a.W, mrow_step = 2 * (RB_THREADS / 32) * a.tiles_x * 4;
+            // running pointers of this warp's row quads (q = warp, warp + 8, ...)
+            float* drow = a.dst + (int64_t(n) * a.H + oy0 + 4 * warp) * a.W + ox0 + 4 * lane;
+            uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 4 * warp) * a.tiles_x + tx) * 4 + (lane & 3);
+            const int drow_step = 4 * (RB_THREADS / 32) * a.W, mrow_step = 4 * (RB_THREADS / 32) * a.tiles_x * 4;
             const int mrow_k = a.tiles_x * 4;
-            for (int pr = warp; 2 * pr < th; pr += RB_THREADS / 32, drow += drow_step, mrow += mrow_step) {
-                const float* w0 = wyp + (2 * pr) * BT;
-                const float* p = tmp + ylop[pr] * RB_TW + 4 * lane;
-                float2 lo[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, hi[2] = {lo[0], lo[0]};   // columns (0,1), (2,3)
+            for (int qd = warp; 4 * qd < th; qd += RB_THREADS / 32, drow += drow_step, mrow += mrow_step) {
+                const float4* wq = reinterpret_cast<const float4*>(wyq + qd * BTV * 4);     // [t] -> weights of the 4 rows
+                const float* p = tmp + yloq[qd] * RB_TW + 4 * lane;
+                float2 lo[4], hi[4];                                // columns (0,1), (2,3) of the 4 rows
 #pragma unroll
-                for (int t2 = 0; t2 < BT; t2 += 2) {      // BT is even: weights as 8-byte broadcast loads
-                    const float2 wa = *reinterpret_cast<const float2*>(w0 + t2);
-                    const float2 wb = *reinterpret_cast<const float2*>(w0 + BT + t2);
-                    const float a0[2] = {wa.x, wa.y}, a1[2] = {wb.x, wb.y};
+                for (int k = 0; k < 4; ++k) lo[k] = hi[k] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 v = *reinterpret_cast<const float4*>(p + (t2 + u) * RB_TW);
-                        const float2 vl = make_float2(v.x, v.y), vh = make_float2(v.z, v.w);
-                        const float2 w0p = make_float2(a0[u], a0[u]), w1p = make_float2(a1[u], a1[u]);
-                        lo[0] = ffma2(w0p, vl, lo[0]); hi[0] = ffma2(w0p, vh, hi[0]);
-                        lo[1] = ffma2(w1p, vl, lo[1]); hi[1] = ffma2(w1p, vh, hi[1]);
+                for (int t = 0; t < BTV; ++t) {
+                    const float4 v = *reinterpret_cast<const float4*>(p + t * RB_TW);
+                    const float4 w4 = wq[t];
+                    const float2 vl = make_float2(v.x, v.y), vh = make_float2(v.z, v.w);
+                    const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 wp = make_float2(wk[k], wk[k]);
+                        lo[k] = ffma2(wp, vl, lo[k]); hi[k] = ffma2(wp, vh, hi[k]);
                     }
                 }
-                const float4 acc[2] = {make_float4(lo[0].x, lo[0].y, hi[0].x, hi[0].y), make_float4(lo[1].x, lo[1].y, hi[1].x, hi[1].y)};
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const bool okr = 2 * pr + k < th;              // uniform
+                for (int k = 0; k < 4; ++k) {
+                    const bool okr = 4 * qd + k < th;              // uniform
+                    const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
-                        const float4 c = make_float4(__saturatef(acc[k].x), __saturatef(acc[k].y), __saturatef(acc[k].z),
-                                                     __saturatef(acc[k].w));
+                        const float4 c = make_float4(__saturatef(acc.x), __saturatef(acc.y), __saturatef(acc.z), __saturatef(acc.w));
                         if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4(c, a.ep.x + (drow - a.dst) + k * a.W, a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
-                            const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc[k].x);
-                            const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc[k].y);
-                            const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc[k].z);
-                            const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc[k].w);
+                            const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
+                            const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc.y);
+                            const unsigned b2 = __ballot_sync(0xffffffffu, okc && c.z == acc.z);
+                            const unsigned b3 = __ballot_sync(0xffffffffu, okc && c.w == acc.w);
                             unsigned w = b0;                       // lane l < 4 stores word l
                             w = (lane & 3) == 1 ? b1 : w; w = (lane & 3) == 2 ? b2 : w; w = (lane & 3) == 3 ? b3 : w;
                             if (lane < 4 && okr) mrow[k * mrow_k] = w;
                         }
                     } else if (okc && okr) {
-                        stg128(drow + k * a.W, acc[k]);
+                        stg128(drow + k * a.W, acc);
                     }
                 }
             }
