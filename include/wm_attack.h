@@ -251,6 +251,28 @@ int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out,
 int wm_splice_bwd(const float* gy, const float* mask, float* ga, float* gb, int64_t B, int C, int64_t hw,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Real-codec round trip.  Replaces JpegTest.forward, noise_layers/jpeg.py:21-45
+ * (PIL save(format="JPEG", quality, subsampling) to a temp file + Image.open, frame by frame).
+ * Entropy coding is lossless, so the decoded pixels are an integer function of the input bytes:
+ * libjpeg's fixed-point colour conversion, box downsampling, "islow" 8x8 DCT pair, quantisation
+ * with the Annex-K tables scaled by `quality` (jpeg_set_quality, baseline), "fancy" chroma
+ * upsampling.  Output is bit-identical to Pillow/libjpeg-turbo's.  Not differentiable (as upstream).
+ *   x: [B,3,H,W], element strides x_sb/x_sc/x_sh (W stride 1); y: dense [B,3,H,W]; any H, W >= 1.
+ *   mode 0: float32 in [-1,1] both sides, with JpegTest's own conversions
+ *           (u8 = trunc((clamp(x,-1,1)+1)/2*255);  out = (u8/255 - 0.5)/0.5);
+ *   mode 1: float32 in [0,1] (u8 = rint(clamp(x,0,1)*255); out = u8/255);
+ *   mode 2: uint8 both sides.
+ *   subsampling: Pillow's numbering, 0 = 4:4:4, 1 = 4:2:2, 2 = 4:2:0.
+ *   scratch: wm_jpegcodec_scratch_bytes(B,H,W,subsampling) bytes, 16-byte aligned (decoded Y/Cb/Cr
+ *   planes between the two kernels).  coef: optional int16 buffer of scratch_bytes ELEMENTS that
+ *   receives the quantised coefficients in the same plane layout (what the entropy coder would
+ *   see), or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int64_t wm_jpegcodec_scratch_bytes(int B, int H, int W, int subsampling);
+int wm_jpegcodec(const void* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, void* y, int B, int H, int W,
+                 int quality, int subsampling, int mode, uint8_t* scratch, int16_t* coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

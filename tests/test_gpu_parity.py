@@ -828,3 +828,115 @@ def test_fused_store_epilogue_bank_is_bit_identical_to_the_unfused_bank():
         assert torch.equal(outs[0][1], outs[1][1])
         k = len(outs[0][2])
         assert md(outs[0][1], g.view(k, *shape).sum(0)) <= 1e-5
+
+
+# ================================================================ real codec (JpegTest)
+import io as _io  # noqa: E402
+import os as _os  # noqa: E402
+
+from oracle import libjpeg_oracle as LJ  # noqa: E402
+
+_LJ_GOLD = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "libjpeg_golden.npz"))
+
+
+def _pillow_roundtrip(rgb, q, s):
+    Image = pytest.importorskip("PIL.Image")
+    buf = _io.BytesIO()
+    Image.fromarray(rgb).save(buf, format="JPEG", quality=q, subsampling=s)
+    return np.array(Image.open(_io.BytesIO(buf.getvalue())), dtype=np.uint8)
+
+
+def _codec_u8(rgb_hwc, q, s, **kw):
+    x = torch.from_numpy(np.ascontiguousarray(rgb_hwc.transpose(2, 0, 1)))[None].to(DEV)
+    return WF.jpeg_codec(x, q, s, "uint8", **kw)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in _LJ_GOLD.files if k.startswith("out/")))
+def test_codec_matches_pillow_golden(key):
+    """Bit-exact against the committed Pillow/libjpeg-turbo outputs (ragged sizes, all samplings)."""
+    _, name, s, q = key.split("/")
+    y = _codec_u8(_LJ_GOLD[f"in/{name}"], int(q[1:]), int(s[1:]))
+    assert np.array_equal(y[0].permute(1, 2, 0).cpu().numpy(), _LJ_GOLD[key])
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (1080, 1920), (250, 301), (8, 8), (1, 1), (3, 700)])
+@pytest.mark.parametrize("s", [0, 1, 2])
+def test_codec_matches_pillow_live(hw, s):
+    """Frame sizes of the BASELINE configs and ragged / tiny ones against Pillow on this machine."""
+    rng = np.random.RandomState(hw[0] + s)
+    yy, xx = np.mgrid[0:hw[0], 0:hw[1]]
+    smooth = (np.sin(xx / 31.0)[..., None] * 0.3 + np.cos(yy / 17.0)[..., None] * 0.2 + 0.5) * 255
+    rgb = np.clip(smooth + rng.randint(-40, 40, (*hw, 3)), 0, 255).astype(np.uint8)
+    for q in (30, 90):
+        ref = _pillow_roundtrip(rgb, q, s)
+        got = _codec_u8(rgb, q, s)[0].permute(1, 2, 0).cpu().numpy()
+        assert np.array_equal(got, ref), (hw, s, q, int((got != ref).sum()))
+
+
+@pytest.mark.parametrize("s", [0, 1, 2])
+def test_codec_quantised_coefficients_bit_exact(s):
+    """The integers the entropy coder would see == the oracle's (north star: quantised DCT
+    coefficients bit-exact)."""
+    rng = np.random.RandomState(5 + s)
+    rgb = rng.randint(0, 256, (72, 104, 3)).astype(np.uint8)
+    q = 60
+    _, (yq, cbq, crq) = _codec_u8(rgb, q, s, return_coefficients=True)
+    hs, vs = ((1, 1), (2, 1), (2, 2))[s]
+    ql, qc = LJ.quant_tables(q)
+    y, cb, cr = LJ.rgb_to_ycc(rgb)
+    mw, mh = -(-104 // (8 * hs)), -(-72 // (8 * vs))
+    assert np.array_equal(yq[0].cpu().numpy(), LJ.quantised_plane(LJ.downsample(y, 1, 1, mh * vs, mw * hs), ql))
+    assert np.array_equal(cbq[0].cpu().numpy(), LJ.quantised_plane(LJ.downsample(cb, hs, vs, mh, mw), qc))
+    assert np.array_equal(crq[0].cpu().numpy(), LJ.quantised_plane(LJ.downsample(cr, hs, vs, mh, mw), qc))
+
+
+def test_jpegtest_module_follows_reference_steps():
+    """JpegTest.forward == the reference's steps (noise_layers/jpeg.py:21-45) with Pillow as the
+    codec: same fp32 conversions on both sides of the byte round trip, batch of ragged frames."""
+    pytest.importorskip("PIL.Image")
+    x = (rnd((3, 3, 45, 70), 11) * 2.4 - 1.2)                       # exercises the clamp
+    m = wmattack.JpegTest(50, subsample=2)
+    y = m(x.to(DEV))
+    assert y.shape == x.shape and y.dtype == torch.float32 and not y.requires_grad
+    ref = torch.zeros_like(x)
+    for i in range(x.shape[0]):
+        single = ((x[i].clamp(-1, 1).permute(1, 2, 0) + 1) / 2 * 255).to(torch.uint8).numpy()
+        dec = _pillow_roundtrip(single, 50, 2)
+        t = torch.from_numpy(dec).permute(2, 0, 1).float().div(255)
+        ref[i] = (t - 0.5) / 0.5
+    assert torch.equal(y.cpu(), ref)
+    # and the oracle's statement of the same thing
+    assert np.array_equal(y.cpu().numpy(), LJ.jpegtest_forward(x.numpy(), 50, 2))
+
+
+def test_codec_value_ranges_and_strides():
+    rgb = np.random.RandomState(3).randint(0, 256, (2, 3, 40, 64)).astype(np.uint8)
+    xu = torch.from_numpy(rgb).to(DEV)
+    yu = WF.jpeg_codec(xu, 75, 2, "uint8")
+    yf = WF.jpeg_codec(xu.float() / 255, 75, 2, "unit")
+    assert torch.equal(yf.cpu(), yu.cpu().float() / 255)          # IEEE division, as ToTensor's on the host
+    big = torch.zeros((2, 3, 48, 80), device=DEV)
+    big[:, :, 4:44, 8:72] = xu.float() / 255
+    assert torch.equal(WF.jpeg_codec(big[:, :, 4:44, 8:72], 75, 2, "unit"), yf)      # strided view, no copy
+    with pytest.raises(ValueError):
+        WF.jpeg_codec(xu, 0, 2, "uint8")
+    with pytest.raises(ValueError):
+        WF.jpeg_codec(xu, 50, 3, "uint8")
+    with pytest.raises(TypeError):
+        WF.jpeg_codec(xu.float(), 50, 2, "uint8")
+    with pytest.raises(RuntimeError):
+        WF.jpeg_codec(xu.cpu(), 50, 2, "uint8")
+    assert WF.jpeg_codec(xu[:0], 50, 2, "uint8").shape == (0, 3, 40, 64)
+
+
+def test_codec_frames_and_mcus_independent_at_4k():
+    """Size-independent property at config 5's frame size: a 4K frame decodes to the same bytes
+    alone or inside a batch, and luma of an MCU row strip does not depend on the rest."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(0, 256, (2, 3, 2160, 3840), generator=g, dtype=torch.uint8).to(DEV)
+    y = WF.jpeg_codec(x, 85, 2, "uint8")
+    assert torch.equal(WF.jpeg_codec(x[1:], 85, 2, "uint8"), y[1:])
+    y444 = WF.jpeg_codec(x[:1], 85, 0, "uint8")
+    assert torch.equal(WF.jpeg_codec(x[:1, :, 1024:1152], 85, 0, "uint8"), y444[:, :, 1024:1152])
+    ref = _pillow_roundtrip(x[0].permute(1, 2, 0).cpu().numpy(), 85, 2)
+    assert np.array_equal(y[0].permute(1, 2, 0).cpu().numpy(), ref)

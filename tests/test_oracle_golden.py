@@ -214,3 +214,55 @@ def test_crop():
     assert O.crop_box_from_rng(T("x2028").shape, np.random.RandomState(19), 0.7, 0.9) == apex19
     assert maxdiff(O.crop_resize(T("x2028").double(), apex19), T("crop/seed19/x2028/y")) <= 2e-6
     assert maxdiff(O.crop_resize(x.double(), (3, 20, 5, 31)), T("crop/apex/x32/y")) <= 2e-6
+
+
+# ------------------------------------------------------------------- real codec (JpegTest)
+import os as _os  # noqa: E402
+
+from oracle import libjpeg_oracle as LJ  # noqa: E402
+
+_LJ_GOLD = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "libjpeg_golden.npz"))
+_LJ_CASES = sorted(k for k in _LJ_GOLD.files if k.startswith("out/"))
+
+
+def test_libjpeg_golden_present():
+    assert len(_LJ_CASES) == 8 * 3 * 4
+
+
+@pytest.mark.parametrize("key", _LJ_CASES)
+def test_libjpeg_oracle_matches_pillow_golden(key):
+    """Bit-exact: the restated integer pipeline against what Pillow/libjpeg-turbo returned."""
+    _, name, s, q = key.split("/")
+    got = LJ.jpeg_roundtrip_u8(_LJ_GOLD[f"in/{name}"], int(q[1:]), int(s[1:]))
+    assert np.array_equal(got, _LJ_GOLD[key])
+
+
+@pytest.mark.parametrize("hw", [(48, 48), (31, 50), (128, 96)])
+def test_libjpeg_oracle_matches_pillow_live(hw):
+    """Same check against the Pillow of the machine the tests run on (skipped without Pillow)."""
+    Image = pytest.importorskip("PIL.Image")
+    import io
+    rng = np.random.RandomState(hw[0])
+    rgb = rng.randint(0, 256, (*hw, 3)).astype(np.uint8)
+    for s in (0, 1, 2):
+        for q in (5, 35, 60, 85, 95):
+            buf = io.BytesIO()
+            Image.fromarray(rgb).save(buf, format="JPEG", quality=q, subsampling=s)
+            ref = np.array(Image.open(io.BytesIO(buf.getvalue())), dtype=np.uint8)
+            assert np.array_equal(LJ.jpeg_roundtrip_u8(rgb, q, s), ref), (s, q)
+
+
+def test_libjpeg_quant_tables():
+    ql, qc = LJ.quant_tables(50)
+    assert np.array_equal(ql, LJ.STD_LUMA) and np.array_equal(qc, LJ.STD_CHROMA)
+    ql, qc = LJ.quant_tables(100)
+    assert ql.min() == 1 and ql.max() == 1 and qc.max() == 1
+    ql, _ = LJ.quant_tables(1)
+    assert ql.max() == 255            # force_baseline clamp
+
+
+def test_libjpeg_islow_dct_pair_is_near_identity():
+    rng = np.random.RandomState(0)
+    blk = rng.randint(0, 256, (50, 8, 8)).astype(np.int64)
+    rec = LJ.idct_islow(np.rint(LJ.fdct_islow(blk - 128) / 8).astype(np.int64))   # /8: back to true scale
+    assert np.abs(rec - blk).max() <= 2

@@ -157,3 +157,29 @@ if "bank" in which:
     def stept():
         xx.grad = None; yt.backward(gk, retain_graph=True)
     print(f"6-way bank bwd (straight-through sum over slices): {timeit(stepb):.0f} us  vs torch autograd {timeit(stept):.0f} us", flush=True)
+
+if "codec" in which:
+    # real-codec round trip (JpegTest): float frames 12 B/px in + 12 out (+3 B/px of byte planes
+    # written and read between the two kernels); byte frames 3 + 3
+    xs = x * 2 - 1
+    xu = (x * 255).to(torch.uint8)
+    for s in (2, 0):
+        us = timeit(lambda: WF.jpeg_codec(xs, 75, s, "signed"))
+        report(f"jpeg codec s={s} float q75", us, 24)
+        us = timeit(lambda: WF.jpeg_codec(xu, 75, s, "uint8"))
+        report(f"jpeg codec s={s} uint8 q75", us, 6)
+    try:
+        import io, time
+        import numpy as np
+        from PIL import Image
+        fr = xu[0].permute(1, 2, 0).cpu().numpy()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            buf = io.BytesIO(); Image.fromarray(fr).save(buf, format="JPEG", quality=75, subsampling=2)
+            dec = np.array(Image.open(io.BytesIO(buf.getvalue())))
+        dt = (time.perf_counter() - t0) / 5
+        got = WF.jpeg_codec(xu[:1], 75, 2, "uint8")[0].permute(1, 2, 0).cpu().numpy()
+        print(f"Pillow one {H}x{W} frame, in memory: {dt * 1e3:.2f} ms = {H * W / dt / 1e6:.1f} Mpix/s on one host core; "
+              f"device result identical: {bool((got == dec).all())}", flush=True)
+    except ImportError:
+        pass

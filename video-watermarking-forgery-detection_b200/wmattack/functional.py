@@ -783,6 +783,63 @@ def from_uint8(frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+# ---- real codec round trip (JpegTest, noise_layers/jpeg.py:10-45) -----------------------------------
+
+_CODEC_MODES = {"signed": 0, "unit": 1, "uint8": 2}
+
+
+def jpeg_codec(x: torch.Tensor, quality: int, subsampling: int = 2, value_range: str = "signed",
+               return_coefficients: bool = False):
+    """What ``Image.open(Image.fromarray(frame).save(quality=quality, subsampling=subsampling))``
+    returns, for every frame of x [B,3,H,W], computed on the device bit-for-bit like libjpeg
+    (entropy coding is lossless and is skipped).  Not differentiable, as upstream.
+
+    value_range: "signed" = float in [-1,1] with JpegTest's conversions (noise_layers/jpeg.py:28,38-43),
+    "unit" = float in [0,1] (8-bit rounding, /255), "uint8" = bytes in, bytes out.
+    return_coefficients: also return (Y, Cb, Cr) int16 planes of quantised DCT coefficients laid out
+    like the (block-padded) component planes — the integers the entropy coder would see."""
+    _check_cuda(x, "jpeg_codec")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"jpeg_codec: expected [B,3,H,W], got {tuple(x.shape)}")
+    if value_range not in _CODEC_MODES:
+        raise ValueError(f"jpeg_codec: value_range must be one of {sorted(_CODEC_MODES)}")
+    mode = _CODEC_MODES[value_range]
+    quality, subsampling = int(quality), int(subsampling)
+    if not 1 <= quality <= 100:
+        raise ValueError(f"jpeg_codec: quality {quality} outside 1..100")
+    if subsampling not in (0, 1, 2):
+        raise ValueError("jpeg_codec: subsampling must be 0 (4:4:4), 1 (4:2:2) or 2 (4:2:0)")
+    x = x.detach()
+    if mode == 2:
+        if x.dtype != torch.uint8:
+            raise TypeError(f"jpeg_codec: value_range='uint8' needs a uint8 tensor, got {x.dtype}")
+    else:
+        x = _f32(x)
+    if x.stride(3) != 1 or min(x.stride()) < 0:
+        x = x.contiguous()
+    b, _, h, w = x.shape
+    y = torch.empty((b, 3, h, w), device=x.device, dtype=x.dtype)
+    if b == 0 or h == 0 or w == 0:
+        return (y, None) if return_coefficients else y
+    nbytes = _lib.load().wm_jpegcodec_scratch_bytes(b, h, w, subsampling)
+    scratch = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    coef = torch.zeros(nbytes, device=x.device, dtype=torch.int16) if return_coefficients else None
+    _lib.call("wm_jpegcodec", x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), y.data_ptr(), b, h, w,
+              quality, subsampling, mode, scratch.data_ptr(), coef.data_ptr() if coef is not None else None,
+              _stream())
+    if not return_coefficients:
+        return y
+    hs, vs = ((1, 1), (2, 1), (2, 2))[subsampling]
+    mcu_rows = -(-h // (8 * vs))
+    hy, wt = mcu_rows * 8 * vs, -(-w // 256) * 256
+    hc, wc = mcu_rows * 8, wt // hs
+    ny = b * hy * wt
+    yq = coef[:ny].view(b, hy, wt)
+    cq = coef[ny:].view(2, b, hc, wc)
+    wy, wcb = -(-w // (8 * hs)) * 8 * hs, -(-w // (8 * hs)) * 8
+    return y, (yq[:, :, :wy], cq[0][:, :, :wcb], cq[1][:, :, :wcb])
+
+
 # ---- fused store epilogue: the attack kernel itself writes Quantization(x + (clamp(v) - x)) ---------
 
 def _armed(ep):

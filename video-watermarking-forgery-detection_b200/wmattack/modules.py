@@ -263,9 +263,11 @@ class JpegMask(JpegBasic):
 
 
 class JpegTest(nn.Module):
-    """noise_layers/jpeg.py:10-45: REAL libjpeg through PIL on the host (non-differentiable,
-    evaluation only, expects [-1,1] input).  Kept as a host passthrough by design — it is not
-    part of the differentiable hot path; encodes in memory instead of temp files."""
+    """noise_layers/jpeg.py:10-45: the REAL codec — upstream saves every frame through PIL/libjpeg
+    to a temp file and reads it back.  Here the same pixels (bit-identical to Pillow/libjpeg-turbo,
+    tests/test_gpu_parity.py) are computed on the device by wm_jpegcodec: entropy coding is
+    lossless, so only libjpeg's integer colour/DCT/quantisation/upsampling arithmetic remains.
+    Non-differentiable, expects [-1,1] input, like upstream; `path` is accepted and unused."""
 
     def __init__(self, Q, subsample=2, path="temp/"):
         super().__init__()
@@ -273,18 +275,7 @@ class JpegTest(nn.Module):
         self.name = "JpegTest" + str(Q)
 
     def forward(self, image):
-        import io
-        from PIL import Image
-        image = _first(image)
-        out = torch.zeros_like(image)
-        for i in range(image.shape[0]):
-            arr = ((image[i].detach().clamp(-1, 1).permute(1, 2, 0) + 1) / 2 * 255).to("cpu", torch.uint8).numpy()
-            buf = io.BytesIO()
-            Image.fromarray(arr).save(buf, format="JPEG", quality=self.Q, subsampling=self.subsample)
-            dec = np.array(Image.open(io.BytesIO(buf.getvalue())), dtype=np.uint8)
-            t = torch.from_numpy(dec).permute(2, 0, 1).float() / 255.0
-            out[i] = ((t - 0.5) / 0.5).to(image.device)
-        return out
+        return F_.jpeg_codec(_first(image), self.Q, self.subsample, "signed")
 
 
 # ---- JpegCompression (noise_layers/jpeg_compression.py) --------------------------------------
