@@ -940,3 +940,39 @@ def test_codec_frames_and_mcus_independent_at_4k():
     assert torch.equal(WF.jpeg_codec(x[:1, :, 1024:1152], 85, 0, "uint8"), y444[:, :, 1024:1152])
     ref = _pillow_roundtrip(x[0].permute(1, 2, 0).cpu().numpy(), 85, 2)
     assert np.array_equal(y[0].permute(1, 2, 0).cpu().numpy(), ref)
+
+
+# ================================================================ CUDA-graph capture of the layer calls
+@pytest.mark.parametrize("name", ["diffjpeg", "jpegcompression", "blur", "median3", "resize", "jpegss"])
+def test_cuda_graph_capture_replays_forward_and_backward(name):
+    """Every launch goes to torch's current stream and the library never allocates or synchronises,
+    so a layer's forward + backward can be captured once and replayed on new data (the trainers'
+    per-frame loops at 256x256 are launch-bound: ~100 us eager vs ~10-20 us per replay)."""
+    b, h, w = 2, 64, 128
+    rs = wmattack.Resize()
+    layer = {"diffjpeg": wmattack.DiffJPEG(True, h, w, quality=50), "jpegcompression": wmattack.JpegCompression(DEV),
+             "blur": wmattack.GaussianBlur(), "median3": wmattack.MiddleBlur(3),
+             "resize": lambda t: rs(t, resize_ratio=0.75), "jpegss": wmattack.JpegSS(50)}[name]
+    xs = rnd((b, 3, h, w), 1).to(DEV).requires_grad_(True)
+    gs = rnd((b, 3, h, w), 2).to(DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            torch.autograd.grad(layer(xs), xs, gs)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y_cap = layer(xs)
+        (gx_cap,) = torch.autograd.grad(y_cap, xs, gs)
+    for seed in (3, 5):
+        x2, g2 = rnd((b, 3, h, w), seed).to(DEV), rnd((b, 3, h, w), seed + 1).to(DEV)
+        with torch.no_grad():
+            xs.copy_(x2)
+            gs.copy_(g2)
+        graph.replay()
+        xe = x2.clone().requires_grad_(True)
+        ye = layer(xe)
+        (ge,) = torch.autograd.grad(ye, xe, g2)
+        assert torch.equal(ye, y_cap) and torch.equal(ge, gx_cap)
