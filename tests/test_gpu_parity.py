@@ -976,3 +976,32 @@ def test_cuda_graph_capture_replays_forward_and_backward(name):
         ye = layer(xe)
         (ge,) = torch.autograd.grad(ye, xe, g2)
         assert torch.equal(ye, y_cap) and torch.equal(ge, gx_cap)
+
+
+# ================================================================ half-precision inputs / autocast
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_half_precision_inputs_cast_at_the_boundary(dt):
+    """The trainers sometimes call the layers inside torch.cuda.amp.autocast()
+    (models/IRNcrop_model.py:340), so a layer can be handed fp16/bf16 activations: they are cast to
+    fp32 at the boundary, the result is the fp32 result for the same values, and autograd hands the
+    gradient back in the input's dtype."""
+    b, h, w = 2, 64, 64
+    rs = wmattack.Resize()
+    layers = [wmattack.DiffJPEG(True, h, w, quality=50), wmattack.JpegCompression(DEV), wmattack.JpegSS(50),
+              wmattack.GaussianBlur(), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5),
+              lambda t: rs(t, resize_ratio=0.75), lambda t: wmattack.Crop()(t, apex=(8, 56, 4, 60))[0],
+              wmattack.Identity()]
+    xh = rnd((b, 3, h, w), 1).to(DEV).to(dt)
+    g = rnd((b, 3, h, w), 2).to(DEV)
+    for layer in layers:
+        x1 = xh.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=dt):
+            y1 = layer(x1)
+        x2 = xh.float().requires_grad_(True)
+        y2 = layer(x2)
+        if y1 is x1:                       # Identity returns its argument
+            continue
+        assert y1.dtype == torch.float32 and torch.equal(y1, y2)
+        y1.backward(g)
+        y2.backward(g)
+        assert x1.grad.dtype == dt and torch.equal(x1.grad, x2.grad.to(dt))

@@ -19,11 +19,13 @@ fns = {
     "jpeg8": wmattack.JpegCompression("cuda"),
     "jpegss": wmattack.JpegSS(50),
     "noise": wmattack.Gaussian(),
+    "codec": lambda t: WF.jpeg_codec(t * 2 - 1, 75, 2, "signed"),
 }
 f = fns[op]
 for _ in range(3):
     y = f(x)
-    y.backward(g)
-    x.grad = None
+    if y.requires_grad:
+        y.backward(g)
+        x.grad = None
 torch.cuda.synchronize()
 print("ok")

@@ -117,7 +117,7 @@ __device__ __forceinline__ void rgb2ycc(int r, int g, int b, int& y, int& cb, in
 
 // kernel 1: tile of one MCU row (8*VS full-resolution rows x 256 columns)
 template <int HS, int VS>
-__global__ void __launch_bounds__(JC_THREADS) jc_blocks_kernel(const __grid_constant__ JCArgs a) {
+__global__ void __launch_bounds__(JC_THREADS, 5) jc_blocks_kernel(const __grid_constant__ JCArgs a) {
     constexpr int TR = 8 * VS, TW = JC_TW, CW = TW / HS;
     constexpr bool SUB = (HS * VS) > 1;
     __shared__ __align__(16) uint8_t sy[TR][TW];
