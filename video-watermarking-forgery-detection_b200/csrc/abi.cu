@@ -25,12 +25,12 @@ void arm_store_epilogue(const StoreEp& e) { g_ep = e; }
 
 StoreEp take_store_epilogue() {
     StoreEp e = g_ep;
-    g_ep = StoreEp{nullptr, 0, 0};
+    g_ep = StoreEp{nullptr, 0, 0, 0};
     return e;
 }
 bool reject_store_epilogue(const char* who) {
     if (!g_ep.x) return false;
-    g_ep = StoreEp{nullptr, 0, 0};
+    g_ep = StoreEp{nullptr, 0, 0, 0};
     set_error("%s: a store epilogue is armed but this entry point / code path does not apply one", who);
     return true;
 }
@@ -39,7 +39,7 @@ bool reject_store_epilogue(const char* who) {
 
 extern "C" int wm_set_store_epilogue(const float* x, int clamp01, int quantize) {
     WM_REQUIRE(x == nullptr || ::wm::aligned(x, 32), WM_E_ALIGN, "wm_set_store_epilogue: x must be 32-byte aligned");
-    ::wm::arm_store_epilogue(::wm::StoreEp{x, clamp01, quantize});
+    ::wm::arm_store_epilogue(::wm::StoreEp{x, clamp01, quantize, 0});
     return WM_OK;
 }
 

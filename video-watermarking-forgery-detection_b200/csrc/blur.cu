@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
                 op[c4] = acc;
             }
             if (col_ok && gy0 + r < a.H) {
-                if (a.ep.x) o = ep_apply4(o, a.ep.x + (dst - a.y) + int64_t(r) * a.W, a.ep);
+                if (a.ep.x)      // x at the output position is the centre of the staged tile row
+                    o = a.ep.from_input ? ep_apply4v(o, *reinterpret_cast<const float4*>(col + (r + R) * BT_BW), a.ep)
+                                        : ep_apply4(o, a.ep.x + (dst - a.y) + int64_t(r) * a.W, a.ep);
                 stg128(dst + int64_t(r) * a.W, o);
             }
         }
@@ -193,6 +195,7 @@ static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y,
     a.total = int64_t(N) * a.tiles_x * a.tiles_y;
     for (int i = 0; i < K; ++i) a.taps[i] = taps_host[i];
     a.ep = take_store_epilogue();
+    a.ep.from_input = a.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
     const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
     cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");

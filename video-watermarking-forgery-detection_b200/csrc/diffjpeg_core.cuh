@@ -361,6 +361,12 @@ __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, 
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int r = 2 * rp + rr;
+            float* p = yo + int64_t(r) * a.W;
+            f8 xR, xG, xB;
+            if (EP && t.active) {      // store epilogue: x at the output position, requested before the row's math
+                const float* xp = a.ep.x + (p - a.out);
+                xR = ldg256_stream(xp); xG = ldg256_stream(xp + plane); xB = ldg256_stream(xp + 2 * plane);
+            }
             float yv[8];
             scr_load_row<NT>(scr, r, yv);
             idct8(yv);
@@ -373,16 +379,7 @@ __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, 
                 oB.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tB[c >> 1]));
             }
             if (t.active) {
-                float* p = yo + int64_t(r) * a.W;
-                if (EP) {          // store epilogue: x at the output position
-                    const float* xp = a.ep.x + (p - a.out);
-                    const f8 xR = ldg256_stream(xp), xG = ldg256_stream(xp + plane), xB = ldg256_stream(xp + 2 * plane);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        oR.v[c] = ep_apply(oR.v[c], xR.v[c], a.ep); oG.v[c] = ep_apply(oG.v[c], xG.v[c], a.ep);
-                        oB.v[c] = ep_apply(oB.v[c], xB.v[c], a.ep);
-                    }
-                }
+                if (EP) { ep_apply_n<8>(oR.v, xR.v, a.ep); ep_apply_n<8>(oG.v, xG.v, a.ep); ep_apply_n<8>(oB.v, xB.v, a.ep); }
                 stg256(p, oR);
                 stg256(p + plane, oG);
                 stg256(p + 2 * plane, oB);

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
             if (clamp) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
                          v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
             if (EP) {
-                const float4 ex = ld4(ep.x, i, n);
+                const float4 ex = ep.from_input ? xv : ld4(ep.x, i, n);
                 v = make_float4(ep_apply(v.x, ex.x, ep), ep_apply(v.y, ex.y, ep), ep_apply(v.z, ex.z, ep), ep_apply(v.w, ex.w, ep));
             }
             st4(out, i, n, v);
@@ -297,7 +297,8 @@ extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean
     WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
-    const StoreEp ep = take_store_epilogue();
+    StoreEp ep = take_store_epilogue();
+    ep.from_input = ep.x == x;
     if (ep.x) gaussnoise_kernel<false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
     else gaussnoise_kernel<false, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd");

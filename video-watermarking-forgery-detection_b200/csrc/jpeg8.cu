@@ -347,6 +347,13 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
 #pragma unroll 2
     for (int i = 0; i < 4; ++i) {
         const int r = 4 * h + i;
+        const bool ok = active && (row0 + r) < a.H;
+        float* p = yo + int64_t(i) * a.W;
+        f8 xR, xG, xB;
+        if (a.ep.x && ok) {          // store epilogue: x at the output position, requested before the row's math
+            const float* xp = a.ep.x + (p - a.out);
+            xR = ldg256_stream(xp); xG = ldg256_stream(xp + plane); xB = ldg256_stream(xp + 2 * plane);
+        }
         float y[8], u[8], v[8];
         j8_scr_load<J8P_BLOCKS>(scr, r, y);
         j8_scr_load<J8P_BLOCKS>(scr + 16 * J8P_BLOCKS, r, u);
@@ -359,16 +366,7 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
             oG[c] = fmaf(a.inv[3], y[c], fmaf(a.inv[4], u[c], a.inv[5] * v[c]));
             oB[c] = fmaf(a.inv[6], y[c], fmaf(a.inv[7], u[c], a.inv[8] * v[c]));
         }
-        const bool ok = active && (row0 + r) < a.H;
-        float* p = yo + int64_t(i) * a.W;
-        if (a.ep.x && ok) {          // store epilogue: x at the output position (dense, same layout as out)
-            const float* xp = a.ep.x + (p - a.out);
-            const f8 xR = ldg256_stream(xp), xG = ldg256_stream(xp + plane), xB = ldg256_stream(xp + 2 * plane);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                oR[c] = ep_apply(oR[c], xR.v[c], a.ep); oG[c] = ep_apply(oG[c], xG.v[c], a.ep); oB[c] = ep_apply(oB[c], xB.v[c], a.ep);
-            }
-        }
+        if (a.ep.x && ok) { ep_apply_n<8>(oR, xR.v, a.ep); ep_apply_n<8>(oG, xG.v, a.ep); ep_apply_n<8>(oB, xB.v, a.ep); }   // (dense, same layout as out)
         j8_store_row<true>(p, ok, 8, oR);
         j8_store_row<true>(p + plane, ok, 8, oG);
         j8_store_row<true>(p + 2 * plane, ok, 8, oB);

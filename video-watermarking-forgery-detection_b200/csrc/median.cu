@@ -206,7 +206,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
                 }
             }
             if (col_ok && gy0 + r < a.H) {
-                if (EP) o = ep_apply4(o, a.ep.x + obase + int64_t(r) * a.W, a.ep);
+                if (EP) {   // the window's centre row is ring slot (r + 1) % 3: x is still in registers
+                    const float* c = raw[(r + 1) % 3];
+                    o = a.ep.from_input ? ep_apply4v(o, make_float4(c[1], c[2], c[3], c[4]), a.ep)
+                                        : ep_apply4(o, a.ep.x + obase + int64_t(r) * a.W, a.ep);
+                }
                 stg128(a.y + obase + int64_t(r) * a.W, o);
                 if (WANT_IDX) *reinterpret_cast<uint32_t*>(a.idx + obase + int64_t(r) * a.W) = packed;
             }
@@ -289,7 +293,8 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
                     for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[j][k];
                 const float med = median25_sorted_groups(v);
                 if (col_ok && gy0 + r < a.H) {
-                    a.y[obase + int64_t(r) * a.W] = EP ? ep_apply(med, a.ep.x[obase + int64_t(r) * a.W], a.ep) : med;
+                    a.y[obase + int64_t(r) * a.W] =
+                        EP ? ep_apply(med, a.ep.from_input ? col[(r + 2) * M5_BW + 2] : a.ep.x[obase + int64_t(r) * a.W], a.ep) : med;
                     if (WANT_IDX) {
                         float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
 #pragma unroll
@@ -476,9 +481,10 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0}};
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
         ta.ep = take_store_epilogue();
+        ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
         const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
         auto kern = ta.ep.x ? (idx ? median3_tma_kernel<true, true> : median3_tma_kernel<false, true>)
                             : (idx ? median3_tma_kernel<true, false> : median3_tma_kernel<false, false>);
@@ -495,9 +501,10 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0, StoreEp{nullptr, 0, 0}};
+        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0, StoreEp{nullptr, 0, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
         ta.ep = take_store_epilogue();
+        ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
         const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
         auto kern = ta.ep.x ? (idx ? median5_tma_kernel<true, true> : median5_tma_kernel<false, true>)
                             : (idx ? median5_tma_kernel<true, false> : median5_tma_kernel<false, false>);

@@ -292,6 +292,14 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                 float2 lo[4], hi[4];                                // columns (0,1), (2,3) of the 4 rows
 #pragma unroll
                 for (int k = 0; k < 4; ++k) lo[k] = hi[k] = make_float2(0.f, 0.f);
+                // store epilogue: x at the output positions is requested now (L2 hits: the tile was just
+                // staged from the same lines) so that its latency hides under the window loop
+                float4 xe[4];
+                if (DIR == 0 && a.ep.x) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        xe[k] = (okc && 4 * qd + k < th) ? ldg128_nc(a.ep.x + (drow - a.dst) + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int t = 0; t < BTV; ++t) {
                     const float4 v = *reinterpret_cast<const float4*>(p + t * RB_TW);
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
                         const float4 c = make_float4(__saturatef(acc.x), __saturatef(acc.y), __saturatef(acc.z), __saturatef(acc.w));
-                        if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4(c, a.ep.x + (drow - a.dst) + k * a.W, a.ep) : c);
+                        if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4v(c, xe[k], a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc.y);
