@@ -830,6 +830,25 @@ def test_fused_store_epilogue_bank_is_bit_identical_to_the_unfused_bank():
         assert md(outs[0][1], g.view(k, *shape).sum(0)) <= 1e-5
 
 
+def test_fused_store_epilogue_without_clamp_and_out_of_range_values():
+    """Quantization in the store epilogue uses a fast exact path (1.5*2^23 rounding + Newton-corrected
+    reciprocal) guarded by a range check; un-clamped values far outside [0,1] (|v*255| >= 65536, inf, NaN)
+    must take the IEEE path and still match torch's round(v*255)/255 bit for bit."""
+    x = (rnd((2, 3, 64, 128), 91) - 0.5) * 4.0
+    x[0, 0, 3, 5:9] = torch.tensor([300.0, -1000.0, 70000.0, 1e20])
+    x[1, 2, 10, 0:2] = torch.tensor([float("inf"), float("nan")])
+    xd = x.to(DEV)
+    for layer in (wmattack.Identity(), wmattack.MiddleBlur(3), wmattack.GaussianBlur()):
+        out = torch.empty_like(xd)
+        with torch.no_grad():
+            layer.forward_into(xd, out, (xd, False, True))
+            sim = layer(xd)
+            ref = torch.round((xd + (sim - xd)) * 255.0).cpu() / 255.0       # IEEE division on the host
+        o = out.cpu()
+        same = (o == ref) | (torch.isnan(o) & torch.isnan(ref))
+        assert bool(same.all()), type(layer).__name__
+
+
 # ================================================================ real codec (JpegTest, SURVEY 8f-4)
 import io as _io  # noqa: E402
 import os as _os  # noqa: E402
