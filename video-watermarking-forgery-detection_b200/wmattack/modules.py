@@ -72,6 +72,12 @@ def _rounding_mode(rounding) -> int:
                      "torch.round or a WM_ROUND_* integer")
 
 
+def _set_name(module: nn.Module, name: str) -> None:
+    """`.name` updates inside forward(): skip nn.Module.__setattr__ (4-5 us per call) when nothing changes."""
+    if module.__dict__.get("name") != name:
+        object.__setattr__(module, "name", name)
+
+
 class Identity(nn.Module):
     """noise_layers/identity.py:5-16."""
 
@@ -106,7 +112,7 @@ class Combined(nn.Module):
         if id is None or id >= len(self.list):
             id = get_random_int([0, len(self.list) - 1])
         selected = self.list[id]
-        self.name = selected.name
+        _set_name(self, selected.name)
         into = getattr(selected, "forward_into", None)
         if into is not None and into(x, out, ep):
             return True
@@ -118,7 +124,7 @@ class Combined(nn.Module):
         if id is None or id >= len(self.list):
             id = get_random_int([0, len(self.list) - 1])
         selected = self.list[id]
-        self.name = selected.name
+        _set_name(self, selected.name)
         return selected(image_and_cover)
 
 
@@ -334,11 +340,11 @@ class GaussianBlur(nn.Module):
     def forward_into(self, x, out, ep):
         ok = F_.gaussian_blur_into(x, self._taps, out, ep)
         if ok:
-            self.name = "GaussianBlur"                      # gaussian_blur.py:54 renames on first use
+            _set_name(self, "GaussianBlur")  # gaussian_blur.py:54 renames on first use
         return ok
 
     def forward(self, tensor, cover_image=None):
-        self.name = "GaussianBlur"
+        _set_name(self, "GaussianBlur")
         tensor = _first(tensor)
         if tensor.shape[1] != self.channels:
             raise RuntimeError(f"GaussianBlur built for {self.channels} channels, got {tensor.shape[1]}")
@@ -386,11 +392,11 @@ class Gaussian(nn.Module):
         self.host_rng = host_rng
 
     def forward_into(self, x, out, ep):
-        self.name = "Gaussian"
+        _set_name(self, "Gaussian")
         return F_.gaussian_noise_into(x, 0.0, 0.05, True, out, ep)
 
     def forward(self, tensor, cover_image=None, mean=0, stddev=0.05, noise=None):
-        self.name = "Gaussian"
+        _set_name(self, "Gaussian")
         tensor = _first(tensor)
         if noise is None and self.host_rng:
             noise = torch.nn.init.normal_(torch.empty(tensor.size(), device=tensor.device), mean, stddev)
@@ -460,7 +466,7 @@ class MaskDropout(nn.Module):
         self.host_rng = host_rng
 
     def forward(self, noised_image, cover_image, mask=None):
-        self.name = "Dropout"
+        _set_name(self, "Dropout")
         mask_percent = np.random.uniform(self.keep_min, self.keep_max)
         h, w = noised_image.shape[2:]
         if mask is None:
@@ -536,7 +542,7 @@ class Resize(nn.Module):
         return True
 
     def forward(self, noised_image, resize_ratio=None):
-        self.name = "Resize"
+        _set_name(self, "Resize")
         noised_image = _first(noised_image)
         h, w = noised_image.shape[2], noised_image.shape[3]
         if resize_ratio is None:
