@@ -396,8 +396,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line ("NCCL version ..." goes there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            # keep stdout to the one JSON line: "NCCL version ..." goes there when NCCL_DEBUG=VERSION comes
+            # from the environment or from an nccl.conf on the box (the environment wins over the file)
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=dev)
     out = ours(args, rank, world, dev)
     if rank == 0:
