@@ -44,7 +44,7 @@ LAYERS = ("diffjpeg", "jpegcompression", "gaussianblur", "middleblur3", "gaussia
 # algorithmic HBM bytes per (b,h,w) location, fp32 NCHW (DESIGN.md §4 / SURVEY §8d)
 ALG_BYTES = {
     "diffjpeg": (24, 36), "jpegcompression": (24, 24), "gaussianblur": (24, 24),
-    "middleblur3": (27, 27), "gaussian": (24, 36), "resize": (24, 36),
+    "middleblur3": (27, 27), "gaussian": (24, 24), "resize": (24, 36),   # gaussian: SURVEY 8d (1-bit clamp mask saved)
 }
 METRIC = "DiffJPEG+Combined fwd+bwd Mpix/s"
 WORKLOAD = ("configs[1]: DiffJPEG(q50) + Combined([JpegCompression, GaussianBlur(k3), MiddleBlur(3), "

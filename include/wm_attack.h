@@ -153,6 +153,13 @@ int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std
                       uint64_t seed, uint64_t offset, const float* inject, void* stream);
 int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
                       int clamp, uint64_t seed, uint64_t offset, const float* inject, void* stream);
+/* Training pair of the clamped layer (Gaussian, noise_layers/gaussian.py:10-17): the forward also writes one
+ * bit per value — the pass mask of torch.clamp's backward, 0 <= x + noise <= 1 — into maskbits
+ * (4 * ceil(n / 128) words, 16-byte aligned: word 4*(i/128) + j holds value i + 4*l + j at bit l), and the
+ * backward is gx = bit ? gy : 0: it reads neither x nor regenerates the noise. */
+int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
+                           uint64_t seed, uint64_t offset, const float* inject, void* stream);
+int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, float* gx, int64_t n, void* stream);
 /* SaltPepper (noise_layers/salt_pepper_noise.py:11-19) */
 int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob,
                       uint64_t seed, uint64_t offset, const float* inject, void* stream);

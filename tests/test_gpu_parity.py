@@ -830,6 +830,36 @@ def test_fused_store_epilogue_bank_is_bit_identical_to_the_unfused_bank():
         assert md(outs[0][1], g.view(k, *shape).sum(0)) <= 1e-5
 
 
+def test_gaussian_noise_mask_pair_equals_regenerating_pair():
+    """The clamped Gaussian layer's training pair (1-bit pass mask saved by the forward, backward = masked
+    copy of gy) must equal the pair that saves x and regenerates the noise — values, gradients, ragged
+    lengths, injected noise, and values exactly on the clamp bounds (torch.clamp's mask is inclusive)."""
+    for shape, seed in (((2, 3, 64, 64), 1), ((1, 3, 37, 53), 2), ((1, 1, 5, 7), 3), ((3, 3, 128, 128), 4)):
+        x = rnd(shape, seed) * 1.4 - 0.2
+        g = rnd(shape, seed + 10)
+        for noise in (None, (rnd(shape, seed + 20) - 0.5) * 0.4):
+            outs = []
+            for regen in (False, True):
+                WF._rng_calls = 0
+                torch.manual_seed(3)
+                xx = x.to(DEV).requires_grad_(True)
+                y = WF.gaussian_noise(xx, 0.0, 0.05, True, None if noise is None else noise.to(DEV), regen=regen)
+                y.backward(g.to(DEV))
+                outs.append((y.detach().cpu(), xx.grad.cpu()))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+            if noise is not None:      # against torch with the same noise
+                xr = x.clone().requires_grad_(True)
+                yr = torch.clamp(xr + noise, 0, 1)
+                yr.backward(g)
+                assert torch.equal(outs[0][0], yr.detach()) and torch.equal(outs[0][1], xr.grad)
+    # exactly on the bounds: x + noise == 0 or 1 passes the gradient
+    x = torch.tensor([0.0, 1.0, 0.5, -0.25, 1.25, 0.25] * 32).view(1, 3, 8, 8)
+    nz = torch.tensor([0.0, 0.0, 0.5, 0.25, -0.25, -0.25] * 32).view(1, 3, 8, 8)
+    xx = x.to(DEV).requires_grad_(True)
+    WF.gaussian_noise(xx, 0.0, 0.05, True, nz.to(DEV)).backward(torch.ones(1, 3, 8, 8, device=DEV))
+    assert torch.equal(xx.grad.cpu(), torch.ones(1, 3, 8, 8))
+
+
 def test_fused_store_epilogue_without_clamp_and_out_of_range_values():
     """Quantization in the store epilogue uses a fast exact path (1.5*2^23 rounding + Newton-corrected
     reciprocal) guarded by a range check; un-clamped values far outside [0,1] (|v*255| >= 65536, inf, NaN)

@@ -76,11 +76,13 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
                                                          const float* __restrict__ inject, const StoreEp ep) {
     const Philox ph(seed);
     WM_EW_LOOP(i) {
+        const float4 xv = ld4(x, i, n);             // requested first: the latency hides under Philox + Box-Muller
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BWD) gv = ld4(gy, i, n);
         float4 nz;
         if (inject) nz = ld4(inject, i, n);
         else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
                nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
-        const float4 xv = ld4(x, i, n);
         float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
         if (!BWD) {
             if (clamp) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
@@ -91,11 +93,53 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
             }
             st4(out, i, n, v);
         } else {
-            float4 g = ld4(gy, i, n);
+            float4 g = gv;
             if (clamp) { g.x = (v.x >= 0.f && v.x <= 1.f) ? g.x : 0.f; g.y = (v.y >= 0.f && v.y <= 1.f) ? g.y : 0.f;
                          g.z = (v.z >= 0.f && v.z <= 1.f) ? g.z : 0.f; g.w = (v.w >= 0.f && v.w <= 1.f) ? g.w : 0.f; }
             st4(out, i, n, g);
         }
+    }
+}
+
+// Training pair of the clamped Gaussian layer: the forward also writes ONE BIT per value (the clamp's
+// pass mask, 0 <= x + noise <= 1) and the backward is gx = bit ? gy : 0 — it reads neither x nor
+// regenerates the noise (12 + 0.4 B/px instead of 24 B/px read, no Philox / Box-Muller).
+// Layout: a warp handles 128 consecutive values per step; word 4*(i/128) + j holds, at bit l, the value
+// i + 4*l + j (one ballot per j).
+__global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                  uint32_t* __restrict__ maskbits, int64_t n, float mean,
+                                                                  float std, uint64_t seed, uint64_t offset,
+                                                                  const float* __restrict__ inject) {
+    const Philox ph(seed);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 4; base < n;
+         base += int64_t(gridDim.x) * blockDim.x * 4) {               // warp-uniform trip count (ballots below)
+        const int64_t i = base + 4 * lane;
+        const float4 xv = ld4(x, i, n);             // requested first: the latency hides under Philox + Box-Muller
+        float4 nz;
+        if (inject) nz = ld4(inject, i, n);
+        else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
+               nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
+        const float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
+        const float4 c = make_float4(__saturatef(v.x), __saturatef(v.y), __saturatef(v.z), __saturatef(v.w));
+        st4(out, i, n, c);
+        // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN, like torch.clamp's backward mask)
+        const unsigned b0 = __ballot_sync(0xffffffffu, c.x == v.x), b1 = __ballot_sync(0xffffffffu, c.y == v.y);
+        const unsigned b2 = __ballot_sync(0xffffffffu, c.z == v.z), b3 = __ballot_sync(0xffffffffu, c.w == v.w);
+        if (lane == 0) *reinterpret_cast<uint4*>(maskbits + (base >> 7) * 4) = make_uint4(b0, b1, b2, b3);
+    }
+}
+__global__ void __launch_bounds__(256) gaussnoise_mask_bwd_kernel(const float* __restrict__ gy, const uint32_t* __restrict__ maskbits,
+                                                                  float* __restrict__ gx, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 4; base < n;
+         base += int64_t(gridDim.x) * blockDim.x * 4) {
+        const int64_t i = base + 4 * lane;
+        const uint4 m = *reinterpret_cast<const uint4*>(maskbits + (base >> 7) * 4);     // one 16-byte broadcast per warp
+        float4 g = ld4(gy, i, n);
+        g.x = (m.x >> lane) & 1u ? g.x : 0.f; g.y = (m.y >> lane) & 1u ? g.y : 0.f;
+        g.z = (m.z >> lane) & 1u ? g.z : 0.f; g.w = (m.w >> lane) & 1u ? g.w : 0.f;
+        st4(gx, i, n, g);
     }
 }
 
@@ -317,6 +361,24 @@ extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int
     gaussnoise_kernel<true, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, mean, std, clamp, seed, offset, inject,
                                                                                   StoreEp{nullptr, 0, 0});
     WM_LAUNCH_CHECK("wm_gaussnoise_bwd");
+    return WM_OK;
+}
+extern "C" int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
+                                      uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
+    WM_REQUIRE(x && y && maskbits, WM_E_NULL, "wm_gaussnoise_fwd_mask: null pointer");
+    EW_ALIGN_CHECK("wm_gaussnoise_fwd_mask", x, y, inject, maskbits);
+    WM_REQUIRE(!reject_store_epilogue("wm_gaussnoise_fwd_mask"), WM_E_ARG, "wm_gaussnoise_fwd_mask: the store epilogue is a no-grad path");
+    gaussnoise_mask_fwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, maskbits, n, mean, std, seed, offset, inject);
+    WM_LAUNCH_CHECK("wm_gaussnoise_fwd_mask");
+    return WM_OK;
+}
+extern "C" int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, float* gx, int64_t n, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
+    WM_REQUIRE(gy && gx && maskbits, WM_E_NULL, "wm_gaussnoise_bwd_mask: null pointer");
+    EW_ALIGN_CHECK("wm_gaussnoise_bwd_mask", gy, gx, maskbits);
+    gaussnoise_mask_bwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, maskbits, gx, n);
+    WM_LAUNCH_CHECK("wm_gaussnoise_bwd_mask");
     return WM_OK;
 }
 extern "C" int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob, uint64_t seed, uint64_t offset,

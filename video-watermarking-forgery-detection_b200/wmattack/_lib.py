@@ -45,6 +45,8 @@ SIGNATURES = {
     "wm_median_bwd": [c_f32p, c_u8p, c_f32p, i32, i32, i32, i32, vp],
     "wm_gaussnoise_fwd": [c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_bwd": [c_f32p, c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
+    "wm_gaussnoise_fwd_mask": [c_f32p, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
+    "wm_gaussnoise_bwd_mask": [c_f32p, vp, c_f32p, i64, vp],
     "wm_saltpepper_fwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],
     "wm_saltpepper_bwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],
     "wm_dropout_elem_fwd": [c_f32p, c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],

@@ -384,37 +384,55 @@ def median_blur_with_index(x: torch.Tensor, k: int):
 # --------------------------------------------------------------------------------------
 
 class _GaussNoiseFn(torch.autograd.Function):
+    """Clamped layer with grad: the forward saves the clamp's 1-bit pass mask (0.4 B/px) and the backward is
+    a masked copy of gy.  regen=True keeps the save-x pair whose backward regenerates the noise by Philox."""
+
     @staticmethod
-    def forward(ctx, x, mean, std, clamp, noise, seed, offset):
+    def forward(ctx, x, mean, std, clamp, noise, seed, offset, regen):
         x = _flat(x, "gaussian noise")
         inj = _flat(noise, "gaussian noise (injected)") if noise is not None else None
         if inj is not None and inj.shape != x.shape:
             raise ValueError("injected noise must have the input's shape")
         y = torch.empty_like(x)
+        ctx.mode = "identity"
+        if clamp and ctx.needs_input_grad[0] and not regen:
+            n = x.numel()
+            mask = torch.empty(4 * ((n + 127) // 128), device=x.device, dtype=torch.int32)
+            _lib.call("wm_gaussnoise_fwd_mask", x.data_ptr(), y.data_ptr(), mask.data_ptr(), n, mean, std, seed, offset,
+                      _ptr(inj), _stream())
+            ctx.save_for_backward(mask)
+            ctx.mode = "mask"
+            return y
         _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, offset,
                   _ptr(inj), _stream())
         ctx.meta = (mean, std, int(clamp), seed, offset)
         if clamp:
             ctx.save_for_backward(x, inj if inj is not None else torch.empty(0, device=x.device))
+            ctx.mode = "regen"
         ctx.has_inj = inj is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        mean, std, clamp, seed, offset = ctx.meta
         gy = _flat(gy, "gaussian noise backward")
-        if not clamp:
-            return gy, None, None, None, None, None, None
-        x, inj = ctx.saved_tensors
+        if ctx.mode == "identity":
+            return gy, None, None, None, None, None, None, None
         gx = torch.empty_like(gy)
+        if ctx.mode == "mask":
+            (mask,) = ctx.saved_tensors
+            _lib.call("wm_gaussnoise_bwd_mask", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), gy.numel(), _stream())
+            return gx, None, None, None, None, None, None, None
+        mean, std, clamp, seed, offset = ctx.meta
+        x, inj = ctx.saved_tensors
         _lib.call("wm_gaussnoise_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), gy.numel(), mean, std, clamp,
                   seed, offset, inj.data_ptr() if ctx.has_inj else None, _stream())
-        return gx, None, None, None, None, None, None
+        return gx, None, None, None, None, None, None, None
 
 
-def gaussian_noise(x, mean: float = 0.0, std: float = 0.05, clamp: bool = True, noise=None):
+def gaussian_noise(x, mean: float = 0.0, std: float = 0.05, clamp: bool = True, noise=None, regen: bool = False):
+    """regen=True: save x and regenerate the noise in the backward instead of saving the 1-bit clamp mask."""
     seed, offset = next_philox_stream(x.numel()) if noise is None else (0, 0)
-    return _GaussNoiseFn.apply(x, float(mean), float(std), clamp, noise, seed, offset)
+    return _GaussNoiseFn.apply(x, float(mean), float(std), clamp, noise, seed, offset, regen)
 
 
 class _SaltPepperFn(torch.autograd.Function):
