@@ -307,8 +307,18 @@ def jpeg8_quantised(x: torch.Tensor, params: Jpeg8Params) -> torch.Tensor:
 # Gaussian blur / median
 # --------------------------------------------------------------------------------------
 
+_TAPS_CACHE: dict = {}
+
+
 def _taps_array(taps: Sequence[float]):
-    arr = (C.c_float * len(taps))(*[float(t) for t in taps])
+    """ctypes float array of the taps (read by the launcher on the host, copied into kernel arguments);
+    cached per tap tuple — building it costs several microseconds per call."""
+    key = tuple(taps)
+    arr = _TAPS_CACHE.get(key)
+    if arr is None:
+        if len(_TAPS_CACHE) > 256:
+            _TAPS_CACHE.clear()
+        arr = _TAPS_CACHE[key] = (C.c_float * len(key))(*[float(t) for t in key])
     return arr
 
 
@@ -336,7 +346,7 @@ class _BlurFn(torch.autograd.Function):
 
 def gaussian_blur(x: torch.Tensor, taps: Sequence[float], border: int = 0) -> torch.Tensor:
     """Separable blur with normalised 1-D `taps`; border 0 = zero pad, 1 = reflect."""
-    return _BlurFn.apply(x, tuple(float(t) for t in taps), border)
+    return _BlurFn.apply(x, taps if isinstance(taps, tuple) else tuple(float(t) for t in taps), border)
 
 
 class _MedianFn(torch.autograd.Function):

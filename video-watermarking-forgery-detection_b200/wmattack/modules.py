@@ -335,7 +335,7 @@ class GaussianBlur(nn.Module):
         self.name = "G_Blur"
         if kernel_size % 2 == 0:
             raise ValueError("even kernel sizes change the output size upstream; only odd sizes are supported")
-        self._taps = _gaussian_taps(kernel_size, 2.0, (kernel_size - 1) / 2.0)
+        self._taps = tuple(_gaussian_taps(kernel_size, 2.0, (kernel_size - 1) / 2.0))
 
     def forward_into(self, x, out, ep):
         ok = F_.gaussian_blur_into(x, self._taps, out, ep)
@@ -358,7 +358,7 @@ class GF(nn.Module):
     def __init__(self, sigma, kernel=7):
         super().__init__()
         self.name = "GF"
-        self._taps = _gaussian_taps(kernel, float(sigma), kernel // 2)
+        self._taps = tuple(_gaussian_taps(kernel, float(sigma), kernel // 2))
 
     def forward(self, image_and_cover):
         image = _first(image_and_cover)
