@@ -1054,3 +1054,23 @@ def test_half_precision_inputs_cast_at_the_boundary(dt):
         y1.backward(g)
         y2.backward(g)
         assert x1.grad.dtype == dt and torch.equal(x1.grad, x2.grad.to(dt))
+
+
+def test_make_graphed_callables_wraps_a_layer():
+    """torch.cuda.make_graphed_callables (separate forward / backward graphs behind an autograd
+    node) works on the layers as they are — the way to take the ~0.1 ms of eager Python + autograd
+    per call out of the trainers' per-frame loops (models/IRNcrop_model.py:357-370)."""
+    b, h, w = 1, 64, 64
+    layer = wmattack.DiffJPEG(True, h, w, quality=50)
+    sample = rnd((b, 3, h, w), 1).to(DEV).requires_grad_(True)
+    graphed = torch.cuda.make_graphed_callables(layer, (sample,))
+    for seed in (2, 3):
+        x = rnd((b, 3, h, w), seed).to(DEV)
+        g = rnd((b, 3, h, w), seed + 10).to(DEV)
+        x1 = x.clone().requires_grad_(True)
+        y1 = graphed(x1)
+        y1.backward(g)
+        x2 = x.clone().requires_grad_(True)
+        y2 = layer(x2)
+        y2.backward(g)
+        assert torch.equal(y1, y2) and torch.equal(x1.grad, x2.grad)
