@@ -248,7 +248,8 @@ int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream)
  * position — no separate pass over the attacked batch.  Consumed (and cleared) by: wm_diffjpeg_fwd,
  * wm_jpeg8_fwd (W % 8 == 0, aligned, subsample 0), wm_gaussblur (zero border, k in {3,5,7}, W % 4 == 0),
  * wm_median_fwd (TMA paths), wm_gaussnoise_fwd, wm_resize_fwd.  Their other code paths fail with
- * WM_E_ARG instead of silently ignoring it.  x = NULL disarms. */
+ * WM_E_ARG instead of silently ignoring it.  x = NULL disarms; after a call that returned non-zero, disarm
+ * explicitly (an argument check may have failed before the descriptor was consumed). */
 int wm_set_store_epilogue(const float* x, int clamp01, int quantize);
 int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                            void* stream);

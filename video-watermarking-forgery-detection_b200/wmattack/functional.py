@@ -880,6 +880,18 @@ def _disarm():
     _lib.call("wm_set_store_epilogue", None, 0, 0)
 
 
+def _call_armed(ep, name, *args):
+    """Arm the store epilogue, launch; if the launcher rejects the call before consuming the
+    descriptor, clear it so that it cannot leak into an unrelated later launch of this thread."""
+    _armed(ep)
+    try:
+        _lib.call(name, *args)
+    except BaseException:
+        if ep is not None:
+            _disarm()
+        raise
+
+
 def _out_ok(out, shape):
     return out is not None and tuple(out.shape) == tuple(shape) and out.is_contiguous() and out.dtype == torch.float32 \
         and out.data_ptr() % 32 == 0
@@ -892,8 +904,7 @@ def diffjpeg_into(x, factor, rounding, out, ep=None) -> bool:
     if c != 3 or h % 16 or w % 16 or not _out_ok(out, x.shape):
         return False
     fs, fps = _factor_args(factor, b, x.device)
-    _armed(ep)
-    _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+    _call_armed(ep, "wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
     return True
 
 
@@ -902,8 +913,7 @@ def jpeg8_into(x, params, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if c != 3 or w % 8 or params.subsample != 0 or not _out_ok(out, x.shape):
         return False
-    _armed(ep)
-    _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _stream())
+    _call_armed(ep, "wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _stream())
     return True
 
 
@@ -912,8 +922,7 @@ def gaussian_blur_into(x, taps, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if len(taps) not in (3, 5, 7) or w % 4 or sp % 4 or sh % 4 or x.data_ptr() % 16 or not _out_ok(out, x.shape):
         return False
-    _armed(ep)
-    _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, out.data_ptr(), b * c, h, w, _taps_array(taps), len(taps), 0, 0, _stream())
+    _call_armed(ep, "wm_gaussblur", x.data_ptr(), sp, sh, out.data_ptr(), b * c, h, w, _taps_array(taps), len(taps), 0, 0, _stream())
     return True
 
 
@@ -922,8 +931,7 @@ def median_blur_into(x, k, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if k not in (3, 5) or sp % 4 or sh % 4 or x.data_ptr() % 16 or (k == 3 and w % 4) or not _out_ok(out, x.shape):
         return False
-    _armed(ep)
-    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _stream())
+    _call_armed(ep, "wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _stream())
     return True
 
 
@@ -932,8 +940,7 @@ def gaussian_noise_into(x, mean, std, clamp, out, ep=None) -> bool:
     if not _out_ok(out, x.shape):
         return False
     seed, offset = next_philox_stream(x.numel())
-    _armed(ep)
-    _lib.call("wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
+    _call_armed(ep, "wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
               seed, offset, None, _stream())
     return True
 
@@ -947,8 +954,7 @@ def resize_roundtrip_into(x, mid_hw, mode, out, ep=None) -> bool:
             and x.data_ptr() % 16 == 0 and _out_ok(out, x.shape)):
         return False
     tables = _resize_tables(x.device, h, w, mid_hw, _MODES[mode])
-    _armed(ep)
-    _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, out.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], _MODES[mode],
+    _call_armed(ep, "wm_resize_fwd", x.data_ptr(), sp, sh, out.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], _MODES[mode],
               None, tables.data_ptr(), _stream())
     return True
 
