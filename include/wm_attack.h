@@ -260,6 +260,23 @@ int wm_splice_bwd(const float* gy, const float* mask, float* ga, float* gb, int6
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Crop + resize back, fast path.  Replaces Crop.forward, noise_layers/crop.py:48-53 (slice the crop
+ * rectangle, F.interpolate to H x W, align_corners=False) for UP-scaling geometries: per axis
+ * 0.45 <= in/out <= 1 (the layer's crop rates are 0.5 .. 1), Wout % 4 == 0, frame width % 4 == 0.
+ *   x: [N, Hsrc, Wsrc] planes (element strides x_sp, x_sh; 16-byte aligned base and strides), the
+ *   rectangle [h0, h0+Hin) x [w0, w0+Win) is read in place; y: dense [N, Hout, Wout].
+ *   bwd: gx dense [N, Hsrc, Wsrc], written completely (zeros outside the rectangle), deterministic.
+ *   tables: wm_cropresize_table_words(...) 4-byte words of scratch, 16-byte aligned (band tables built
+ *   by a small kernel in the same call; the rectangle changes every call).
+ * Other geometries: wm_interp_fwd / wm_interp_bwd.  mode 0 = bilinear (the layer), 1 = bicubic. */
+int wm_cropresize_ok(int Hin, int Win, int Hout, int Wout, int N, int mode);
+int64_t wm_cropresize_table_words(int Hin, int Win, int Hout, int Wout, int mode);
+int wm_cropresize_fwd(const float* x, int64_t x_sp, int64_t x_sh, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
+                      float* y, int N, int Hout, int Wout, int mode, int32_t* tables, void* stream);
+int wm_cropresize_bwd(const float* gy, float* gx, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
+                      int N, int Hout, int Wout, int mode, int32_t* tables, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Real-codec round trip.  Replaces JpegTest.forward, noise_layers/jpeg.py:21-45
  * (PIL save(format="JPEG", quality, subsampling) to a temp file + Image.open, frame by frame).
  * Entropy coding is lossless, so the decoded pixels are an integer function of the input bytes:

@@ -525,6 +525,65 @@ def test_crop():
     assert md(outs[4], T("cropped_out/seed20/x32/new_images")) == 0
 
 
+@pytest.mark.parametrize("mode", ("bilinear", "bicubic"))
+def test_crop_fast_path_geometry_sweep(mode):
+    """wm_cropresize_* (TMA source box + banded tables) over crop rectangles at every edge / corner, odd
+    origins, rates 0.46 .. 1.0, several frame sizes: forward against torch's own interpolate of the
+    slice (CPU fp32, the reference's op) and backward against autograd through it; the gradient
+    outside the rectangle must be exactly zero.  Ineligible geometries (rate < 0.45) fall back."""
+    cases = [((2, 3, 64, 128), [(0, 64, 0, 128), (0, 32, 0, 64), (31, 64, 63, 128), (5, 37, 17, 90), (0, 30, 61, 128),
+                                (13, 64, 0, 59), (1, 62, 3, 127), (7, 40, 9, 80)]),
+             ((1, 3, 200, 264), [(0, 100, 0, 132), (99, 200, 131, 264), (11, 199, 40, 263), (50, 143, 7, 131)]),
+             ((1, 2, 256, 256), [(0, 118, 0, 118), (100, 228, 37, 165), (3, 250, 5, 200)])]
+    for shape, boxes in cases:
+        x, g = rnd(shape, 31), rnd(shape, 32)
+        h, w = shape[2:]
+        for (a, b, c, d) in boxes:
+            xr = x.clone().requires_grad_(True)
+            yr = torch.nn.functional.interpolate(xr[:, :, a:b, c:d], size=[h, w], mode=mode)
+            yr.backward(g)
+            xt = x.to(DEV).requires_grad_(True)                       # the same ATen op on this device
+            yt = torch.nn.functional.interpolate(xt[:, :, a:b, c:d], size=[h, w], mode=mode)
+            yt.backward(g.to(DEV))
+            xx = x.to(DEV).requires_grad_(True)
+            y = WF.interpolate(xx, (h, w), mode, window=(a, c, b - a, d - c))
+            y.backward(g.to(DEV))
+            assert md(y, yr) <= 2e-6 and md(y, yt) <= 2e-6, (shape, (a, b, c, d))
+            # gradients: tight against the same-device op; at non-dyadic scales fp32 source coordinates that land
+            # within an ulp of an integer move a tap by one sample in ANY fp32 implementation (torch's own CPU
+            # and CUDA gradients differ from fp64 by 2.5e-5 on the 264-wide cases), hence the wider CPU bound
+            assert md(xx.grad, xt.grad) <= 5e-6, (shape, (a, b, c, d))
+            assert md(xx.grad, xr.grad) <= 5e-5, (shape, (a, b, c, d))
+            # exact adjoint of our own forward: <A x, g> == <x, A^T g>
+            lhs = float((y.detach().double() * g.to(DEV).double()).sum())
+            rhs = float((xx.grad.double() * x.to(DEV).double()).sum())
+            assert abs(lhs - rhs) <= 1e-7 * abs(lhs)          # fp32 rounding of the two sums only
+            outside = xx.grad.cpu().clone()
+            outside[:, :, a:b, c:d] = 0
+            assert float(outside.abs().max()) == 0.0
+    # the module itself, reference RNG order, at the trainers' frame size
+    np.random.seed(77)
+    xx = rnd((2, 3, 256, 256), 33).to(DEV).requires_grad_(True)
+    y, apex = wmattack.Crop()(xx)
+    h0, h1, w0, w1 = apex
+    ref = torch.nn.functional.interpolate(xx.detach().cpu()[:, :, h0:h1, w0:w1], size=[256, 256], mode="bilinear")
+    assert md(y, ref) <= 2e-6
+
+
+def test_crop_fast_path_is_used_and_deterministic():
+    import wmattack._lib as L
+    assert L.load().wm_cropresize_ok(180, 192, 256, 256, 6, 0) == 1
+    assert L.load().wm_cropresize_ok(100, 192, 256, 256, 6, 0) == 0          # rate 0.39: older kernels
+    x, g = rnd((2, 3, 128, 128), 41).to(DEV), rnd((2, 3, 128, 128), 42).to(DEV)
+    outs = []
+    for _ in range(2):
+        xx = x.clone().requires_grad_(True)
+        y = wmattack.Crop()(xx, apex=(10, 100, 20, 110))[0]
+        y.backward(g)
+        outs.append((y.detach(), xx.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 # =================================================================================== Combined
 def test_combined_matches_reference_choices():
     import random

@@ -19,6 +19,7 @@ fns = {
     "jpeg8": wmattack.JpegCompression("cuda"),
     "jpegss": wmattack.JpegSS(50),
     "noise": wmattack.Gaussian(),
+    "crop": lambda t: wmattack.Crop()(t, apex=(int(0.2 * h), int(0.2 * h) + int(0.7 * h), int(0.1 * w), int(0.1 * w) + int(0.75 * w)))[0],
     "codec": lambda t: WF.jpeg_codec(t * 2 - 1, 75, 2, "signed"),
 }
 f = fns[op]

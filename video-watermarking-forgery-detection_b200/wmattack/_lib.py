@@ -67,6 +67,8 @@ SIGNATURES = {
     "wm_resize_tables": [c_f32p, i32, i32, i32, i32, i32, vp],
     "wm_resize_fwd": [c_f32p, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, vp],
     "wm_resize_bwd": [c_f32p, vp, c_f32p, i32, i32, i32, i32, i32, i32, c_f32p, vp],
+    "wm_cropresize_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, vp, vp],
+    "wm_cropresize_bwd": [c_f32p, c_f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
     "wm_jpegcodec": [vp, i64, i64, i64, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
 }
 
@@ -75,10 +77,14 @@ KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 KERNELS_PER_CALL["wm_resize_tables"] = 4
 KERNELS_PER_CALL["wm_set_store_epilogue"] = 0
 KERNELS_PER_CALL["wm_jpegcodec"] = 2
+KERNELS_PER_CALL["wm_cropresize_fwd"] = 2
+KERNELS_PER_CALL["wm_cropresize_bwd"] = 2
 # plain (non-status) helpers: name -> (restype, argtypes)
 HELPERS = {"wm_interp_is_tiled": (C.c_int, [i32, i32, i32, i32, i32]),
            "wm_resize_is_fused": (C.c_int, [i32, i32, i32, i32, i32]),
            "wm_resize_table_floats": (C.c_int64, [i32, i32, i32, i32]),
+           "wm_cropresize_ok": (C.c_int, [i32, i32, i32, i32, i32, i32]),
+           "wm_cropresize_table_words": (C.c_int64, [i32, i32, i32, i32, i32]),
            "wm_jpegcodec_scratch_bytes": (C.c_int64, [i32, i32, i32, i32])}
 
 _lock = threading.Lock()

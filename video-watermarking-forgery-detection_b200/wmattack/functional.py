@@ -589,9 +589,28 @@ def cropout(image, cover, box):
 # interpolation: Resize / Crop
 # --------------------------------------------------------------------------------------
 
+def _crop_fast(n, window, out_hw, src_hw, mode, clamp) -> bool:
+    """Up-scaling crop geometries served by wm_cropresize_* (TMA source box, banded tables per call)."""
+    h0, w0, hin, win = window
+    return (not clamp) and src_hw[1] % 4 == 0 and bool(
+        _lib.load().wm_cropresize_ok(hin, win, out_hw[0], out_hw[1], n, mode))
+
+
+def _crop_tables(device, window, out_hw, mode):
+    words = int(_lib.load().wm_cropresize_table_words(window[2], window[3], out_hw[0], out_hw[1], mode))
+    return torch.empty(words, device=device, dtype=torch.int32)
+
+
 def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp, want_mask=False):
     h0, w0, hin, win = window
     y = torch.empty((n, out_hw[0], out_hw[1]), device=x.device, dtype=torch.float32)
+    src_hw = x.shape[-2:]
+    if (not want_mask and _crop_fast(n, window, out_hw, src_hw, mode, clamp) and sp % 4 == 0 and sh % 4 == 0
+            and x.data_ptr() % 16 == 0):
+        tables = _crop_tables(x.device, window, out_hw, mode)
+        _lib.call("wm_cropresize_fwd", x.data_ptr(), sp, sh, src_hw[0], src_hw[1], h0, w0, hin, win, y.data_ptr(), n,
+                  out_hw[0], out_hw[1], mode, tables.data_ptr(), _stream())
+        return y, None
     mask = None
     if want_mask:
         mask = torch.empty((n, out_hw[0], (out_hw[1] + 31) // 32), device=x.device, dtype=torch.int32)
@@ -603,6 +622,11 @@ def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp, want_mask=False):
 def _interp_bwd(gy, mask, n, out_hw, src_hw, window, mode):
     h0, w0, hin, win = window
     gx = torch.empty((n, src_hw[0], src_hw[1]), device=gy.device, dtype=torch.float32)
+    if mask is None and _crop_fast(n, window, out_hw, src_hw, mode, False):
+        tables = _crop_tables(gy.device, window, out_hw, mode)
+        _lib.call("wm_cropresize_bwd", gy.data_ptr(), gx.data_ptr(), src_hw[0], src_hw[1], h0, w0, hin, win, n,
+                  out_hw[0], out_hw[1], mode, tables.data_ptr(), _stream())
+        return gx
     ws = None
     if not _lib.load().wm_interp_is_tiled(hin, win, out_hw[0], out_hw[1], n):
         ws = torch.empty((n, hin, out_hw[1]), device=gy.device, dtype=torch.float32)
