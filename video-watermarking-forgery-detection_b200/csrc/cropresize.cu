@@ -68,8 +68,7 @@ __global__ void cr_fwd_tables_kernel(int* tab, CRTab L, int Hin, int Win, int Ho
 }
 
 template <int MODE>
-__global__ void cr_adj_tables_kernel(int* tab, CRTab L, int Hin, int Win, int Hout, int Wout, float sh, float sw) {
-    constexpr int BTT = CRK<MODE>::BTT;
+__global__ void cr_adj_tables_kernel(int* tab, CRTab L, int Hin, int Win, int Hout, int Wout, float sh, float sw, int BTT) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Win + Hin) return;
     const bool isx = t < Win;
@@ -175,9 +174,8 @@ struct CAArgs {
     int bw, bh;                                    // TMA box of this geometry (<= CA_BW x CA_BH)
 };
 
-template <int MODE>
+template <int BTT>
 __global__ void __launch_bounds__(CR_THREADS) cr_adj_kernel(const __grid_constant__ CUtensorMap tmap, const CAArgs a) {
-    constexpr int BTT = CRK<MODE>::BTT;
     extern __shared__ __align__(128) float sm[];
     float* G = sm;                                 // [bh][bw] cotangent region
     float* tmp = sm + a.bh * a.bw;                 // [bh][CA_TW]
@@ -324,10 +322,13 @@ extern "C" int wm_cropresize_bwd(const float* gy, float* gx, int Hsrc, int Wsrc,
     WM_REQUIRE(aligned(gy, 16) && aligned(gx, 8) && aligned(tables, 16), WM_E_ALIGN, "wm_cropresize_bwd: gy / tables 16-byte, gx 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const float sh = (float)Hin / (float)Hout, sw = (float)Win / (float)Wout;
-    const CRTab L = cr_layout(Win, Hin, mode == 0 ? 6 : 10);
-    const int btt = mode == 0 ? 6 : 10;
+    // outputs touching one source sample: at most floor(taps / slope) + 1 -> pad the adjoint bands to 4 / 6 / 8 / 10
+    const float smin = sh < sw ? sh : sw;
+    const int need = (int)floorf((mode == 0 ? 2.f : 4.f) / smin) + 1;
+    const int btt = need <= 4 ? 4 : (need <= 6 ? 6 : (need <= 8 ? 8 : 10));
     int bw = up4((int)ceilf((CA_TW - 1) / sw) + 1 + btt + 3 + 1), bh = (int)ceilf((CA_TH - 1) / sh) + 1 + btt + 1;
     bw = bw > CA_BW ? CA_BW : bw; bh = bh > CA_BH ? CA_BH : bh;
+    const CRTab L = cr_layout(Win, Hin, btt);
     CUtensorMap tm;
     if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, Hout, Wout, int64_t(Hout) * Wout, Wout, bw, bh)) {
         set_error("wm_cropresize_bwd: cuTensorMapEncodeTiled failed (%d)", rc);
@@ -339,17 +340,12 @@ extern "C" int wm_cropresize_bwd(const float* gy, float* gx, int Hsrc, int Wsrc,
     const int tb = (Win + Hin + 127) / 128;
     cudaError_t e = cudaMemsetAsync(tables + L.flag, 0, 4 * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "wm_cropresize_bwd");
-    if (mode == 0) {
-        e = cudaFuncSetAttribute(cr_adj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "wm_cropresize_bwd");
-        cr_adj_tables_kernel<0><<<tb, 128, 0, st>>>(tables, L, Hin, Win, Hout, Wout, sh, sw);
-        cr_adj_kernel<0><<<grid, CR_THREADS, smem, st>>>(tm, a);
-    } else {
-        e = cudaFuncSetAttribute(cr_adj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "wm_cropresize_bwd");
-        cr_adj_tables_kernel<1><<<tb, 128, 0, st>>>(tables, L, Hin, Win, Hout, Wout, sh, sw);
-        cr_adj_kernel<1><<<grid, CR_THREADS, smem, st>>>(tm, a);
-    }
+    if (mode == 0) cr_adj_tables_kernel<0><<<tb, 128, 0, st>>>(tables, L, Hin, Win, Hout, Wout, sh, sw, btt);
+    else cr_adj_tables_kernel<1><<<tb, 128, 0, st>>>(tables, L, Hin, Win, Hout, Wout, sh, sw, btt);
+    auto kern = btt == 4 ? cr_adj_kernel<4> : (btt == 6 ? cr_adj_kernel<6> : (btt == 8 ? cr_adj_kernel<8> : cr_adj_kernel<10>));
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_cropresize_bwd");
+    kern<<<grid, CR_THREADS, smem, st>>>(tm, a);
     WM_LAUNCH_CHECK("wm_cropresize_bwd");
     return WM_OK;
 }
