@@ -9,6 +9,7 @@
 // forward is bit-exact.  Optionally it records, per output, the raster position of the FIRST
 // window element equal to the median (uint8); the backward is a deterministic gather through it.
 #include "median_net.cuh"
+#include "median_pair_net.cuh"
 #include "tma.cuh"
 #include "wm_common.cuh"
 
@@ -223,13 +224,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
     }
 }
 
-// 5x5 fast path: same TMA ring; one lane per column, two 35-row strips per tile.  A lane keeps
-// the last 5 window rows sorted (9-comparator network per row, shared by the 5 vertically adjacent
-// outputs) and selects the median of the 5 sorted groups with the generated 67-comparator network;
-// the raw rows stay in registers for the arg-median search.  The row loop is unrolled by 5 so that
-// ring slots are compile-time indices.
-constexpr int M5_TW = 128, M5_TH = 70, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
-              M5_THREADS = 256, M5_ROWS = 35, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
+// 5x5 fast path: same TMA ring; one lane per column, two 36-row strips per tile.  A lane keeps the
+// last 6 window rows sorted (9-comparator network per row, shared by the 5 vertically adjacent
+// outputs) and produces TWO outputs per step: rows r and r+1 share four of their five window rows,
+// whose 20 values are reduced once to the six of rank 7..12 — the only ones that can be the median of
+// either window — and each output is then the median of those six and its own sorted row
+// (median_pair_net.cuh, generated: 88 + 2 x 10 min/max per pair against 2 x 110 for the single-output
+// network of median_net.cuh).  The raw rows stay in registers for the arg-median search.  The row loop
+// is unrolled by 3 pairs so that ring slots are compile-time indices.
+constexpr int M5_TW = 128, M5_TH = 72, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
+              M5_THREADS = 256, M5_ROWS = 36, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
 
 template <bool WANT_IDX, bool EP>
 __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * M5_TW + c, gy0 = ty * M5_TH + strip * M5_ROWS;
         const float* col = bufs + s * M5_STRIDE + (strip * M5_ROWS) * M5_BW + M5_HALO - 2 + c;
-        float srt[5][5], raw[WANT_IDX ? 5 : 1][5];
+        float srt[6][5], raw[WANT_IDX ? 6 : 1][5];
         auto load_row = [&](int row, int slot) {
             const float* p = col + row * M5_BW;
 #pragma unroll
@@ -281,30 +285,42 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         const bool col_ok = gx < a.W;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
 #pragma unroll 1
-        for (int r0 = 0; r0 < M5_ROWS; r0 += 5) {
+        for (int r0 = 0; r0 < M5_ROWS; r0 += 6) {
 #pragma unroll
-            for (int u = 0; u < 5; ++u) {
-                const int r = r0 + u;
-                load_row(r + 4, (u + 4) % 5);          // (r + 4) % 5 == (u + 4) % 5 since r0 % 5 == 0
-                float v[25];
+            for (int u = 0; u < 3; ++u) {
+                // outputs r and r + 1 share the window rows r+1 .. r+4 (ring slots are compile-time: r0 % 6 == 0)
+                const int r = r0 + 2 * u;
+                load_row(r + 4, (2 * u + 4) % 6);
+                load_row(r + 5, (2 * u + 5) % 6);
+                float v[20];
 #pragma unroll
-                for (int j = 0; j < 5; ++j)
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[j][k];
-                const float med = median25_sorted_groups(v);
-                if (col_ok && gy0 + r < a.H) {
-                    a.y[obase + int64_t(r) * a.W] =
-                        EP ? ep_apply(med, a.ep.from_input ? col[(r + 2) * M5_BW + 2] : a.ep.x[obase + int64_t(r) * a.W], a.ep) : med;
-                    if (WANT_IDX) {
-                        float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
+                    for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[(2 * u + 1 + j) % 6][k];
+                mid6_of_4_sorted_rows(v);                  // v[7..12]: the only shared values that can be a median
 #pragma unroll
-                        for (int j = 0; j < 15; ++j)       // window row j/5 is ring slot (u + j/5) % 5
-                            hi = fmaf(hi, 2.f, feq(raw[(u + j / 5) % 5][j % 5], med));
+                for (int o = 0; o < 2; ++o) {
+                    const int rr = r + o, own = (2 * u + (o ? 5 : 0)) % 6;
+                    float w[11];
 #pragma unroll
-                        for (int j = 15; j < 25; ++j)
-                            lo = fmaf(lo, 2.f, feq(raw[(u + j / 5) % 5][j % 5], med));
-                        const int pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
-                        a.idx[obase + int64_t(r) * a.W] = (uint8_t)pos;
+                    for (int k = 0; k < 6; ++k) w[k] = v[7 + k];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) w[6 + k] = srt[own][k];
+                    const float med = median11_sorted_6_5(w);
+                    if (col_ok && gy0 + rr < a.H) {
+                        a.y[obase + int64_t(rr) * a.W] =
+                            EP ? ep_apply(med, a.ep.from_input ? col[(rr + 2) * M5_BW + 2] : a.ep.x[obase + int64_t(rr) * a.W], a.ep) : med;
+                        if (WANT_IDX) {
+                            float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
+#pragma unroll
+                            for (int j = 0; j < 15; ++j)       // window row j/5 of output rr is ring slot (2u + o + j/5) % 6
+                                hi = fmaf(hi, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
+#pragma unroll
+                            for (int j = 15; j < 25; ++j)
+                                lo = fmaf(lo, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
+                            const int pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
+                            a.idx[obase + int64_t(rr) * a.W] = (uint8_t)pos;
+                        }
                     }
                 }
             }
