@@ -275,3 +275,46 @@ def test_resize_band_bound():
                     quad = max(int(hi[o:o + 4].max() - lo[o] + 1) for o in range(0, n, 4))   # V pass: 4 rows share a window
                     bt = window(n, nm)
                     assert need <= bt and need2 <= (10 if bt <= 10 else 14) and quad <= bt + 2, (n, nm, mode, need, need2, quad, bt)
+
+
+# ---------------------------------------------------------------- generated median networks (csrc/*.cuh)
+def _run_network(path, func, values):
+    """Execute the min/max statements of a generated network header on a python list."""
+    import re
+    src = open(path).read()
+    body = src[src.index(func + "("):]
+    body = body[:body.index("\n}")]
+    v = list(values)
+    for ln in body.split("\n"):
+        ln = ln.strip()
+        m = re.match(r"WM_CE\(v\[(\d+)\], v\[(\d+)\]\);", ln)
+        if m:
+            a, b = int(m[1]), int(m[2])
+            v[a], v[b] = min(v[a], v[b]), max(v[a], v[b])
+            continue
+        m = re.match(r"v\[(\d+)\] = (fminf|fmaxf)\(v\[(\d+)\], v\[(\d+)\]\);", ln)
+        if m:
+            f = min if m[2] == "fminf" else max
+            v[int(m[1])] = f(v[int(m[3])], v[int(m[4])])
+            continue
+        m = re.match(r"return v\[(\d+)\];", ln)
+        if m:
+            return v[int(m[1])], v
+    return None, v
+
+
+def test_generated_median_networks_select_the_median():
+    """The 5x5 kernels rely on three generated selection networks; replay their statements on random
+    inputs WITH TIES (the generator itself proves them with the 0-1 principle)."""
+    import numpy as np
+    csrc = os.path.join(ROOT, "video-watermarking-forgery-detection_b200", "csrc")
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        rows = np.sort(rng.randint(0, 12, (6, 5)), axis=1)          # six sorted window rows, many ties
+        med, _ = _run_network(os.path.join(csrc, "median_net.cuh"), "median25_sorted_groups", rows[:5].ravel())
+        assert med == np.sort(rows[:5].ravel())[12]
+        _, v = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "mid6_of_4_sorted_rows", rows[1:5].ravel())
+        assert v[7:13] == list(np.sort(rows[1:5].ravel())[7:13])
+        for own, window in ((rows[0], rows[:5]), (rows[5], rows[1:])):
+            med, _ = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "median11_sorted_6_5", v[7:13] + list(own))
+            assert med == np.sort(window.ravel())[12]
