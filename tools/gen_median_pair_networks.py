@@ -5,7 +5,9 @@ Outputs y and y+1 share four of their five window rows.  With every row already 
 shared by five outputs), the 20 shared values are reduced ONCE to the six of rank 7..12 (network A):
 a value of rank <= 6 among the 20 has rank <= 11 among the 25 and a value of rank >= 13 has rank >= 13,
 so neither can be the median (rank 12) of either window.  Each output then is the median (rank 5) of
-those six and its own sorted row (network B, 11 inputs).
+those six and its own sorted row (network B, 11 inputs).  Networks M and C split A in two levels: the
+merged row pair (r+3, r+4) of one step is the pair (r+1, r+2) of the next, so each step merges ONE new
+pair (M) and takes the middle six of two merged pairs (C).
 
 Method as in gen_median_network.py: Batcher's odd-even merge sort restricted to the real wires,
 comparators that never fire under the sortedness precondition dropped, greedy deletion with random
@@ -148,13 +150,21 @@ def main():
     na = pa.search(args.restarts, rng, "A (mid six of four sorted rows)")
     pb = Problem([6, 5], [5])
     nb = pb.search(args.restarts, rng, "B (median of sorted 6 + sorted 5)")
+    pm = Problem([5, 5], range(10))
+    nm = pm.search(args.restarts, rng, "M (merge two sorted rows)")
+    pc = Problem([10, 10], range(7, 13))
+    nc = pc.search(args.restarts, rng, "C (mid six of two merged row pairs)")
     text = f"""// GENERATED by tools/gen_median_pair_networks.py — do not edit.
 // 5x5 median, two vertically adjacent outputs per step (they share four sorted window rows):
 //   mid6_of_4_sorted_rows : v[0..19] = four ascending rows of five -> v[7..12] = their values of rank 7..12,
 //                           ascending ({len(na)} comparators, {pa.cost(na)} FMNMX), shared by both outputs;
 //   median11_sorted_6_5   : v[0..5] ascending, v[6..10] ascending -> the median of the eleven
 //                           ({len(nb)} comparators, {pb.cost(nb)} FMNMX), once per output.
-// Both verified exhaustively with the 0-1 principle over every monotone 0/1 assignment of the sorted groups.
+//   merge10_sorted_5_5    : v[0..4], v[5..9] ascending -> v[0..9] ascending ({len(nm)} comparators, {pm.cost(nm)} FMNMX);
+//   mid6_of_2_sorted_10   : v[0..9], v[10..19] ascending -> v[7..12] = rank 7..12, ascending ({len(nc)} comparators,
+//                           {pc.cost(nc)} FMNMX).  merge + mid6 replace mid6_of_4_sorted_rows when the merged row pair
+//                           (r+3, r+4) of one step is kept for the next step, where it is the pair (r+1, r+2).
+// All verified exhaustively with the 0-1 principle over every monotone 0/1 assignment of the sorted groups.
 #pragma once
 namespace wm {{
 #define WM_CE(a, b) {{ const float lo__ = fminf(a, b); b = fmaxf(a, b); a = lo__; }}
@@ -165,6 +175,12 @@ __device__ __forceinline__ float median11_sorted_6_5(float (&v)[11]) {{
 {pb.body(nb)}
     return v[5];
 }}
+__device__ __forceinline__ void merge10_sorted_5_5(float (&v)[10]) {{
+{pm.body(nm)}
+}}
+__device__ __forceinline__ void mid6_of_2_sorted_10(float (&v)[20]) {{
+{pc.body(nc)}
+}}
 #undef WM_CE
 }}  // namespace wm
 """
@@ -172,7 +188,7 @@ __device__ __forceinline__ float median11_sorted_6_5(float (&v)[11]) {{
     out = os.path.join(os.path.dirname(here), "video-watermarking-forgery-detection_b200", "csrc", "median_pair_net.cuh")
     with open(out, "w") as f:
         f.write(text)
-    print(f"wrote {out}: A {len(na)} comparators / {pa.cost(na)} ops, B {len(nb)} comparators / {pb.cost(nb)} ops")
+    print(f"wrote {out}: A {len(na)}/{pa.cost(na)}, B {len(nb)}/{pb.cost(nb)}, M {len(nm)}/{pm.cost(nm)}, C {len(nc)}/{pc.cost(nc)} (comparators/ops)")
 
 
 if __name__ == "__main__":

@@ -229,8 +229,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
 // outputs) and produces TWO outputs per step: rows r and r+1 share four of their five window rows,
 // whose 20 values are reduced once to the six of rank 7..12 — the only ones that can be the median of
 // either window — and each output is then the median of those six and its own sorted row
-// (median_pair_net.cuh, generated: 88 + 2 x 10 min/max per pair against 2 x 110 for the single-output
-// network of median_net.cuh).  The raw rows stay in registers for the arg-median search.  The row loop
+// (median_pair_net.cuh, generated; the merged row pair (r+3, r+4) of one step is reused as the pair
+// (r+1, r+2) of the next: 30 + 36 + 2 x 10 min/max per pair of outputs against 2 x 110 for the
+// single-output network of median_net.cuh).  The raw rows stay in registers for the arg-median search.  The row loop
 // is unrolled by 3 pairs so that ring slots are compile-time indices.
 constexpr int M5_TW = 128, M5_TH = 72, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
               M5_THREADS = 256, M5_ROWS = 36, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
@@ -284,6 +285,10 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         for (int j = 0; j < 4; ++j) load_row(j, j);
         const bool col_ok = gx < a.W;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
+        float mp[10];                                      // rows r+1, r+2 merged (kept from the previous step)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { mp[k] = srt[1][k]; mp[5 + k] = srt[2][k]; }
+        merge10_sorted_5_5(mp);
 #pragma unroll 1
         for (int r0 = 0; r0 < M5_ROWS; r0 += 6) {
 #pragma unroll
@@ -292,12 +297,13 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
                 const int r = r0 + 2 * u;
                 load_row(r + 4, (2 * u + 4) % 6);
                 load_row(r + 5, (2 * u + 5) % 6);
-                float v[20];
+                float mq[10], v[20];                       // rows r+3, r+4 merged: the next step's (r+1, r+2)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int k = 0; k < 5; ++k) { mq[k] = srt[(2 * u + 3) % 6][k]; mq[5 + k] = srt[(2 * u + 4) % 6][k]; }
+                merge10_sorted_5_5(mq);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) v[5 * j + k] = srt[(2 * u + 1 + j) % 6][k];
-                mid6_of_4_sorted_rows(v);                  // v[7..12]: the only shared values that can be a median
+                for (int k = 0; k < 10; ++k) { v[k] = mp[k]; v[10 + k] = mq[k]; mp[k] = mq[k]; }
+                mid6_of_2_sorted_10(v);                    // v[7..12]: the only shared values that can be a median
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
                     const int rr = r + o, own = (2 * u + (o ? 5 : 0)) % 6;
