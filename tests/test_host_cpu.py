@@ -315,6 +315,14 @@ def test_generated_median_networks_select_the_median():
         assert med == np.sort(rows[:5].ravel())[12]
         _, v = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "mid6_of_4_sorted_rows", rows[1:5].ravel())
         assert v[7:13] == list(np.sort(rows[1:5].ravel())[7:13])
+        # the two-level form the kernel uses: merge row pairs, then the middle six of two merged pairs
+        pairs = []
+        for a, b in ((1, 2), (3, 4)):
+            _, m = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "merge10_sorted_5_5", list(rows[a]) + list(rows[b]))
+            assert m == sorted(list(rows[a]) + list(rows[b]))
+            pairs += m
+        _, v2 = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "mid6_of_2_sorted_10", pairs)
+        assert v2[7:13] == v[7:13]
         for own, window in ((rows[0], rows[:5]), (rows[5], rows[1:])):
             med, _ = _run_network(os.path.join(csrc, "median_pair_net.cuh"), "median11_sorted_6_5", v[7:13] + list(own))
             assert med == np.sort(window.ravel())[12]
