@@ -428,7 +428,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
                         // q = p + (dy, dx): tile row r + R + dy = ring slot (r + R + dy) % K; p is at
                         // window position (R - dy, R - dx) of q
                         const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
-                        acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
+                        if (K == 5) {
+                            // compare + PREDICATED add (2 instructions, one on the half-rate ALU pipe) instead of the
+                            // compare + select + add the compiler emits: the 25-term gather is ALU-bound (1386 -> 866 us
+                            // at 64x3x1080x1920); the 9-term one is HBM-bound and keeps the select form
+                            asm("{\n .reg .pred p;\n setp.eq.s32 p, %1, %2;\n @p add.f32 %0, %0, %3;\n}"
+                                : "+f"(acc) : "r"(ix[slot][c4 + R + dx]), "r"(want), "f"(g[slot][c4 + R + dx]));
+                        } else {
+                            acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
+                        }
                     }
                 op[c4] = acc;
             }
