@@ -124,7 +124,7 @@ if "jpeg8" in which:
 
 if "noise" in which:
     gn = wmattack.Gaussian()
-    fwd_bwd("gaussian", lambda t: gn(t), 24, 36)
+    fwd_bwd("gaussian", lambda t: gn(t), 24, 24)      # the backward reads gy + the 1-bit clamp mask
     sp = wmattack.SaltPepper(0.01)
     fwd_bwd("saltpepper", lambda t: sp(t), 24, 24)
 
