@@ -570,6 +570,26 @@ def test_crop_fast_path_geometry_sweep(mode):
     assert md(y, ref) <= 2e-6
 
 
+def test_crop_random_rectangles_stress():
+    """Sixty random frame sizes / rectangles (rates 0.45 .. 1, odd origins and extents, widths not a
+    multiple of 4 -> older kernels) through Crop's interpolate against the same ATen op on this device."""
+    rs = np.random.RandomState(123)
+    for it in range(60):
+        h, w = int(rs.randint(12, 200)), int(rs.randint(3, 60)) * 4 + (0 if it % 5 else int(rs.randint(0, 4)))
+        hin, win = max(int(h * rs.uniform(0.45, 1.0)), 4), max(int(w * rs.uniform(0.45, 1.0)), 4)
+        a, c = int(rs.randint(0, h - hin + 1)), int(rs.randint(0, w - win + 1))
+        mode = "bilinear" if it % 3 else "bicubic"
+        x, g = rnd((1, 2, h, w), 1000 + it).to(DEV), rnd((1, 2, h, w), 2000 + it).to(DEV)
+        xt = x.clone().requires_grad_(True)
+        yt = torch.nn.functional.interpolate(xt[:, :, a:a + hin, c:c + win], size=[h, w], mode=mode)
+        yt.backward(g)
+        xx = x.clone().requires_grad_(True)
+        y = WF.interpolate(xx, (h, w), mode, window=(a, c, hin, win))
+        y.backward(g)
+        assert md(y, yt) <= 3e-6, (it, h, w, a, c, hin, win, mode)
+        assert md(xx.grad, xt.grad) <= 1e-5, (it, h, w, a, c, hin, win, mode)
+
+
 def test_crop_fast_path_is_used_and_deterministic():
     import wmattack._lib as L
     assert L.load().wm_cropresize_ok(180, 192, 256, 256, 6, 0) == 1
