@@ -6,7 +6,7 @@
 // with per-element index arithmetic (issue-bound: 44 % / 16 % of the HBM roofline fwd / bwd).  Here:
 //   * a small table kernel per call turns ATen's taps (same fp32 coordinate arithmetic, clamped
 //     indices folded) into BANDED rows: start + NT weights per output (forward), start + BTT
-//     weights per source sample (adjoint, zero padded) — the crop box changes every call;
+//     weights per source sample (adjoint; BTT = 4 / 6 / 8 / 10 by slope, zero padded) — the crop box changes every call;
 //   * the source region of a tile arrives by ONE TMA box load straight from the un-cropped frame
 //     (box start = crop origin + band start, rounded down to the 16-byte boundary TMA needs for the
 //     innermost coordinate — the taps are shifted by the remainder, so the rectangle itself is free);
@@ -29,7 +29,6 @@ constexpr float CR_SLOPE_MIN = 0.45f;
 
 template <int MODE> struct CRK {
     static constexpr int NT = MODE == 0 ? 2 : 4;        // taps per output
-    static constexpr int BTT = MODE == 0 ? 6 : 10;      // outputs touching one source sample at slope >= 0.45 (padded)
 };
 
 inline int up4(int v) { return (v + 3) & ~3; }
