@@ -148,6 +148,15 @@ int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, 
  * counter = element index / 4 + `offset`; if `inject` != NULL that device array [n] is used
  * instead (parity tests inject the reference's random tensor).
  * ------------------------------------------------------------------------------------------ */
+/* Device-resident randomness (CUDA-graph capture of the stochastic layers).  Every entry point below that
+ * takes (seed, offset) also accepts seed == WM_RNG_FROM_DEVICE with `offset` = a DEVICE pointer (cast to
+ * uint64_t) to two uint64 {seed, offset}.  wm_rng_reserve copies a device-resident generator state
+ * {seed, next offset} into such a slot and advances the state by `count` Philox counters (one counter =
+ * four values) in the same stream: a captured forward then draws fresh numbers at every replay and its
+ * backward, given the same slot, regenerates exactly those numbers. */
+#define WM_RNG_FROM_DEVICE 0xFFFFFFFFFFFFFFFFull
+int wm_rng_reserve(uint64_t* state, uint64_t* slot, uint64_t count, void* stream);
+
 /* Gaussian (noise_layers/gaussian.py:10-17, clamp=1) and GN (noise_layers/gaussian_noise.py:13-16, clamp=0) */
 int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
                       uint64_t seed, uint64_t offset, const float* inject, void* stream);

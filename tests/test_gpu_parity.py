@@ -1153,3 +1153,46 @@ def test_make_graphed_callables_wraps_a_layer():
         y2 = layer(x2)
         y2.backward(g)
         assert torch.equal(y1, y2) and torch.equal(x1.grad, x2.grad)
+
+
+def test_device_rng_makes_stochastic_layers_graph_capturable():
+    """With the Philox state on the device (functional.device_rng) a captured Gaussian / SaltPepper call
+    draws FRESH numbers at every replay, and its captured backward regenerates exactly the forward's
+    numbers (gradient mask consistent with the output); the host counter is untouched afterwards."""
+    try:
+        WF.device_rng(True, seed=1234)
+        for make, check in ((lambda: wmattack.Gaussian(), "gauss"), (lambda: wmattack.SaltPepper(0.3), "sp")):
+            layer = make()
+            xs = (rnd((2, 3, 32, 64), 1) * 0.6 + 0.2).to(DEV).requires_grad_(True)
+            gs = torch.ones(2, 3, 32, 64, device=DEV)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    torch.autograd.grad(layer(xs), xs, gs)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y = layer(xs)
+                (gx,) = torch.autograd.grad(y, xs, gs)
+            outs = []
+            for _ in range(3):
+                graph.replay()
+                torch.cuda.synchronize()
+                outs.append((y.clone(), gx.clone()))
+            assert not torch.equal(outs[0][0], outs[1][0]) and not torch.equal(outs[1][0], outs[2][0])
+            for yy, gg in outs:
+                if check == "gauss":            # gradient 1 exactly where the clamp passed
+                    noise = yy - xs.detach()
+                    assert 0.03 < float(noise.std()) < 0.07
+                    inside = (yy > 0) & (yy < 1)
+                    assert bool((gg[inside] == 1).all())
+                else:                           # salt & pepper: gradient 1 where the pixel was left alone
+                    untouched = yy == xs.detach()
+                    assert bool((gg[untouched] == 1).all()) and bool((gg[~untouched] == 0).all())
+                    assert 0.2 < float((~untouched).float().mean()) < 0.4
+    finally:
+        WF.device_rng(False)
+    a = wmattack.Gaussian()(torch.zeros(1, 3, 8, 8, device=DEV) + 0.5)
+    assert torch.isfinite(a).all()

@@ -25,6 +25,21 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 };
+
+// Device-resident randomness (CUDA-graph capture): when seed == WM_RNG_FROM_DEVICE the `offset` argument is
+// a device pointer to {seed, offset} — written by wm_rng_reserve in the same stream — so that a captured
+// launch draws fresh numbers at every replay and its backward regenerates exactly the same ones.
+__device__ __forceinline__ void resolve_rng(uint64_t& seed, uint64_t& offset) {
+    if (seed == WM_RNG_FROM_DEVICE) {
+        const uint64_t* p = reinterpret_cast<const uint64_t*>(offset);
+        seed = __ldg(p); offset = __ldg(p + 1);
+    }
+}
+__global__ void rng_reserve_kernel(uint64_t* state, uint64_t* slot, uint64_t count) {
+    slot[0] = state[0]; slot[1] = state[1];
+    state[1] += count;
+}
+
 // uniform in [0,1) with 24 bits (same support as torch.rand float32)
 __device__ __forceinline__ float u01(uint32_t r) { return (r >> 8) * (1.0f / 16777216.0f); }
 
@@ -74,6 +89,7 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
                                                          float* __restrict__ out, int64_t n, float mean, float std,
                                                          int clamp, uint64_t seed, uint64_t offset,
                                                          const float* __restrict__ inject, const StoreEp ep) {
+    resolve_rng(seed, offset);
     const Philox ph(seed);
     WM_EW_LOOP(i) {
         const float4 xv = ld4(x, i, n);             // requested first: the latency hides under Philox + Box-Muller
@@ -110,6 +126,7 @@ __global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* _
                                                                   uint32_t* __restrict__ maskbits, int64_t n, float mean,
                                                                   float std, uint64_t seed, uint64_t offset,
                                                                   const float* __restrict__ inject) {
+    resolve_rng(seed, offset);
     const Philox ph(seed);
     const int lane = threadIdx.x & 31;
     for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 4; base < n;
@@ -152,6 +169,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) saltpepper_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n,
                                                          float p0, float p1, uint64_t seed, uint64_t offset,
                                                          const float* __restrict__ inject) {
+    resolve_rng(seed, offset);
     const Philox ph(seed);
     WM_EW_LOOP(i) {
         const float4 r = inject ? ld4(inject, i, n) : uniform4(ph, (uint64_t)(i >> 2) + offset);
@@ -171,6 +189,7 @@ __global__ void __launch_bounds__(256) dropout_elem_kernel(const float* __restri
                                                            float* __restrict__ o1, float* __restrict__ o2, int64_t n,
                                                            float prob, uint64_t seed, uint64_t offset,
                                                            const float* __restrict__ inject) {
+    resolve_rng(seed, offset);
     const Philox ph(seed);
     WM_EW_LOOP(i) {
         const float4 r = inject ? ld4(inject, i, n) : uniform4(ph, (uint64_t)(i >> 2) + offset);
@@ -210,6 +229,7 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) bernoulli_kernel(float* __restrict__ mask, int64_t n, float keep,
                                                         uint64_t seed, uint64_t offset) {
+    resolve_rng(seed, offset);
     const Philox ph(seed);
     WM_EW_LOOP(i) {
         const float4 r = uniform4(ph, (uint64_t)(i >> 2) + offset);
@@ -379,6 +399,13 @@ extern "C" int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits,
     EW_ALIGN_CHECK("wm_gaussnoise_bwd_mask", gy, gx, maskbits);
     gaussnoise_mask_bwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, maskbits, gx, n);
     WM_LAUNCH_CHECK("wm_gaussnoise_bwd_mask");
+    return WM_OK;
+}
+extern "C" int wm_rng_reserve(uint64_t* state, uint64_t* slot, uint64_t count, void* stream) {
+    WM_REQUIRE(state && slot, WM_E_NULL, "wm_rng_reserve: null pointer");
+    WM_REQUIRE(aligned(state, 8) && aligned(slot, 8), WM_E_ALIGN, "wm_rng_reserve: pointers must be 8-byte aligned");
+    rng_reserve_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, slot, count);
+    WM_LAUNCH_CHECK("wm_rng_reserve");
     return WM_OK;
 }
 extern "C" int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob, uint64_t seed, uint64_t offset,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "wm_gaussnoise_bwd": [c_f32p, c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_fwd_mask": [c_f32p, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_bwd_mask": [c_f32p, vp, c_f32p, i64, vp],
+    "wm_rng_reserve": [vp, vp, u64, vp],
     "wm_saltpepper_fwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],
     "wm_saltpepper_bwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],
     "wm_dropout_elem_fwd": [c_f32p, c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],

@@ -95,11 +95,42 @@ _rng_lock = threading.Lock()
 _rng_calls = 0
 
 
-def next_philox_stream(n_elems: int) -> Tuple[int, int]:
+RNG_FROM_DEVICE = 0xFFFFFFFFFFFFFFFF
+_dev_rng = {"on": False, "state": {}, "slots": []}
+
+
+def device_rng(enabled: bool = True, seed: Optional[int] = None) -> None:
+    """Keep the Philox state of the stochastic layers ON THE DEVICE (one {seed, next offset} pair per GPU,
+    advanced by a 1-thread kernel in the launching stream) instead of in this module's host counter.
+    Needed to capture Gaussian / SaltPepper / Dropout calls in a CUDA graph: with the host counter a
+    replay would repeat the captured (seed, offset), i.e. the same noise.  Call once before capturing."""
+    _dev_rng["on"] = bool(enabled)
+    _dev_rng["state"].clear()
+    _dev_rng["seed"] = seed
+
+
+def _device_rng_slot(device, n_elems: int) -> torch.Tensor:
+    key = str(device)
+    st = _dev_rng["state"].get(key)
+    if st is None:
+        seed = _dev_rng.get("seed")
+        seed = (torch.initial_seed() if seed is None else int(seed)) & 0x7FFFFFFFFFFFFFFF
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        st = _dev_rng["state"][key] = torch.tensor([seed, rank << 44], dtype=torch.int64, device=device)
+    slot = torch.empty(2, dtype=torch.int64, device=device)
+    _lib.call("wm_rng_reserve", st.data_ptr(), slot.data_ptr(), (n_elems + 3) // 4 + 1, _stream())
+    return slot
+
+
+def next_philox_stream(n_elems: int, device=None):
     """(seed, offset) for an in-kernel Philox draw of n_elems values: seeded by
     torch.initial_seed(), advanced per call so that successive layers decorrelate.
-    Per-rank decorrelation under DDP comes from each rank's own call sequence + rank offset."""
+    Per-rank decorrelation under DDP comes from each rank's own call sequence + rank offset.
+    With device_rng(True) and a device given: (RNG_FROM_DEVICE, slot) where slot is a device tensor
+    {seed, offset} reserved in the current stream (its address goes where the offset would)."""
     global _rng_calls
+    if _dev_rng["on"] and device is not None:
+        return RNG_FROM_DEVICE, _device_rng_slot(device, n_elems)
     with _rng_lock:
         off = _rng_calls
         _rng_calls += (n_elems + 3) // 4 + 1
@@ -107,6 +138,11 @@ def next_philox_stream(n_elems: int) -> Tuple[int, int]:
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         rank = torch.distributed.get_rank()
     return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, (off + (rank << 44)) & 0xFFFFFFFFFFFFFFFF
+
+
+def _off(offset):
+    """offset argument for the C ABI: a python int, or the address of a reserved device slot."""
+    return offset.data_ptr() if torch.is_tensor(offset) else offset
 
 
 # --------------------------------------------------------------------------------------
@@ -408,12 +444,12 @@ class _GaussNoiseFn(torch.autograd.Function):
         if clamp and ctx.needs_input_grad[0] and not regen:
             n = x.numel()
             mask = torch.empty(4 * ((n + 127) // 128), device=x.device, dtype=torch.int32)
-            _lib.call("wm_gaussnoise_fwd_mask", x.data_ptr(), y.data_ptr(), mask.data_ptr(), n, mean, std, seed, offset,
+            _lib.call("wm_gaussnoise_fwd_mask", x.data_ptr(), y.data_ptr(), mask.data_ptr(), n, mean, std, seed, _off(offset),
                       _ptr(inj), _stream())
             ctx.save_for_backward(mask)
             ctx.mode = "mask"
             return y
-        _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, offset,
+        _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, _off(offset),
                   _ptr(inj), _stream())
         ctx.meta = (mean, std, int(clamp), seed, offset)
         if clamp:
@@ -435,13 +471,13 @@ class _GaussNoiseFn(torch.autograd.Function):
         mean, std, clamp, seed, offset = ctx.meta
         x, inj = ctx.saved_tensors
         _lib.call("wm_gaussnoise_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), gy.numel(), mean, std, clamp,
-                  seed, offset, inj.data_ptr() if ctx.has_inj else None, _stream())
+                  seed, _off(offset), inj.data_ptr() if ctx.has_inj else None, _stream())
         return gx, None, None, None, None, None, None, None
 
 
 def gaussian_noise(x, mean: float = 0.0, std: float = 0.05, clamp: bool = True, noise=None, regen: bool = False):
     """regen=True: save x and regenerate the noise in the backward instead of saving the 1-bit clamp mask."""
-    seed, offset = next_philox_stream(x.numel()) if noise is None else (0, 0)
+    seed, offset = next_philox_stream(x.numel(), x.device) if noise is None else (0, 0)
     return _GaussNoiseFn.apply(x, float(mean), float(std), clamp, noise, seed, offset, regen)
 
 
@@ -451,7 +487,7 @@ class _SaltPepperFn(torch.autograd.Function):
         x = _flat(x, "salt & pepper")
         inj = _flat(rdn, "salt & pepper (injected)") if rdn is not None else None
         y = torch.empty_like(x)
-        _lib.call("wm_saltpepper_fwd", x.data_ptr(), y.data_ptr(), x.numel(), prob, seed, offset, _ptr(inj), _stream())
+        _lib.call("wm_saltpepper_fwd", x.data_ptr(), y.data_ptr(), x.numel(), prob, seed, _off(offset), _ptr(inj), _stream())
         ctx.meta = (prob, seed, offset)
         ctx.inj = inj
         return y
@@ -461,12 +497,12 @@ class _SaltPepperFn(torch.autograd.Function):
         prob, seed, offset = ctx.meta
         gy = _flat(gy, "salt & pepper backward")
         gx = torch.empty_like(gy)
-        _lib.call("wm_saltpepper_bwd", gy.data_ptr(), gx.data_ptr(), gy.numel(), prob, seed, offset, _ptr(ctx.inj), _stream())
+        _lib.call("wm_saltpepper_bwd", gy.data_ptr(), gx.data_ptr(), gy.numel(), prob, seed, _off(offset), _ptr(ctx.inj), _stream())
         return gx, None, None, None, None
 
 
 def salt_pepper(x, prob: float, rdn=None):
-    seed, offset = next_philox_stream(x.numel()) if rdn is None else (0, 0)
+    seed, offset = next_philox_stream(x.numel(), x.device) if rdn is None else (0, 0)
     return _SaltPepperFn.apply(x, float(prob), rdn, seed, offset)
 
 
@@ -480,7 +516,7 @@ class _DropoutElemFn(torch.autograd.Function):
         inj = _flat(rdn, "dropout (injected)") if rdn is not None else None
         y = torch.empty_like(image)
         _lib.call("wm_dropout_elem_fwd", image.data_ptr(), cover.data_ptr(), y.data_ptr(), image.numel(), prob,
-                  seed, offset, _ptr(inj), _stream())
+                  seed, _off(offset), _ptr(inj), _stream())
         ctx.meta = (prob, seed, offset)
         ctx.inj = inj
         return y
@@ -492,13 +528,13 @@ class _DropoutElemFn(torch.autograd.Function):
         gi = torch.empty_like(gy) if ctx.needs_input_grad[0] else None
         gc = torch.empty_like(gy) if ctx.needs_input_grad[1] else None
         if gi is not None or gc is not None:
-            _lib.call("wm_dropout_elem_bwd", gy.data_ptr(), _ptr(gi), _ptr(gc), gy.numel(), prob, seed, offset,
+            _lib.call("wm_dropout_elem_bwd", gy.data_ptr(), _ptr(gi), _ptr(gc), gy.numel(), prob, seed, _off(offset),
                       _ptr(ctx.inj), _stream())
         return gi, gc, None, None, None, None
 
 
 def dropout_elementwise(image, cover, prob: float, rdn=None):
-    seed, offset = next_philox_stream(image.numel()) if rdn is None else (0, 0)
+    seed, offset = next_philox_stream(image.numel(), image.device) if rdn is None else (0, 0)
     return _DropoutElemFn.apply(image, cover, float(prob), rdn, seed, offset)
 
 
@@ -535,8 +571,8 @@ def dropout_mask(noised, cover, mask_hw):
 
 def bernoulli_mask(h: int, w: int, keep: float, device) -> torch.Tensor:
     m = torch.empty((h, w), device=device, dtype=torch.float32)
-    seed, offset = next_philox_stream(h * w)
-    _lib.call("wm_bernoulli_mask", m.data_ptr(), h * w, float(keep), seed, offset, _stream())
+    seed, offset = next_philox_stream(h * w, device)
+    _lib.call("wm_bernoulli_mask", m.data_ptr(), h * w, float(keep), seed, _off(offset), _stream())
     return m
 
 
@@ -963,9 +999,9 @@ def gaussian_noise_into(x, mean, std, clamp, out, ep=None) -> bool:
     x = _flat(x, "gaussian noise")
     if not _out_ok(out, x.shape):
         return False
-    seed, offset = next_philox_stream(x.numel())
+    seed, offset = next_philox_stream(x.numel(), x.device)
     _call_armed(ep, "wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
-              seed, offset, None, _stream())
+              seed, _off(offset), None, _stream())
     return True
 
 
