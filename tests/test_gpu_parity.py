@@ -590,6 +590,31 @@ def test_crop_random_rectangles_stress():
         assert md(xx.grad, xt.grad) <= 1e-5, (it, h, w, a, c, hin, win, mode)
 
 
+def test_crop_full_frame_sizes_adjoint_and_reference():
+    """Config-3 / config-5 frame sizes: Crop's resize against the same-device ATen op, the exact-adjoint
+    property <A x, g> = <x, A^T g>, zero gradient outside the rectangle, run-to-run determinism."""
+    for (h, w, box) in ((1080, 1920, (100, 900, 240, 1700)), (2160, 3840, (1000, 2160, 0, 2000))):
+        a, b, c, d = box
+        x, g = rnd((1, 3, h, w), 5).to(DEV), rnd((1, 3, h, w), 6).to(DEV)
+        xt = x.clone().requires_grad_(True)
+        yt = torch.nn.functional.interpolate(xt[:, :, a:b, c:d], size=[h, w], mode="bilinear")
+        yt.backward(g)
+        outs = []
+        for _ in range(2):
+            xx = x.clone().requires_grad_(True)
+            y = wmattack.Crop()(xx, apex=box)[0]
+            y.backward(g)
+            outs.append((y.detach(), xx.grad))
+        y, gx = outs[0]
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert md(y, yt) <= 2e-6 and md(gx, xt.grad) <= 1e-5
+        lhs, rhs = float((y.double() * g.double()).sum()), float((gx.double() * x.double()).sum())
+        assert abs(lhs - rhs) <= 1e-7 * abs(lhs)
+        outside = gx.clone()
+        outside[:, :, a:b, c:d] = 0
+        assert float(outside.abs().max()) == 0.0
+
+
 def test_crop_fast_path_is_used_and_deterministic():
     import wmattack._lib as L
     assert L.load().wm_cropresize_ok(180, 192, 256, 256, 6, 0) == 1
