@@ -249,7 +249,8 @@ int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, i
  *   bwd: ga = gy * (1 - mask), gb = gy * mask (either may be NULL).
  * ------------------------------------------------------------------------------------------ */
 /* 8-bit frames -> [0,1] float32, dst[i] = src[i] / 255 (data format on the host side of the path:
- * upload bytes, convert on the device; same values as torch's u8.float() / 255). */
+ * upload bytes, convert on the device; the correctly rounded quotient, i.e. the values numpy / CPU torch
+ * give for u8.astype(float32) / 255). */
 int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream);
 /* Store epilogue, fused: arms the epilogue above for the NEXT forward launch issued from the calling
  * host thread; that kernel then writes  Quantization( x + (clamp(v, 0, 1) - x) )  instead of its own

@@ -332,8 +332,9 @@ __global__ void __launch_bounds__(256) u8_to_unit_float_kernel(const uint8_t* __
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<float4*>(dst + i + 4 * k) =
-                    make_float4(__fdiv_rn(float(ws[k] & 0xff), 255.f), __fdiv_rn(float((ws[k] >> 8) & 0xff), 255.f),
-                                __fdiv_rn(float((ws[k] >> 16) & 0xff), 255.f), __fdiv_rn(float(ws[k] >> 24), 255.f));
+                    // div255: reciprocal + one Newton step == the IEEE quotient for these integers (wm_common.cuh)
+                    make_float4(div255(float(ws[k] & 0xff)), div255(float((ws[k] >> 8) & 0xff)),
+                                div255(float((ws[k] >> 16) & 0xff)), div255(float(ws[k] >> 24)));
         } else {
             for (int64_t j = i; j < n; ++j) dst[j] = __fdiv_rn(float(src[j]), 255.f);
         }
