@@ -243,9 +243,10 @@ __global__ void __launch_bounds__(256) quantize8_kernel(const float* __restrict_
         float4 v = ld4(x, i, n);
         if (clamp01) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
                        v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
-        // true division by 255 keeps bit-parity with torch's `/ 255.`
-        st4(y, i, n, make_float4(__fdiv_rn(rintf(v.x * 255.f), 255.f), __fdiv_rn(rintf(v.y * 255.f), 255.f),
-                                 __fdiv_rn(rintf(v.z * 255.f), 255.f), __fdiv_rn(rintf(v.w * 255.f), 255.f)));
+        // correctly rounded quotient: bit-parity with torch's `/ 255.` (quant255_n, wm_common.cuh)
+        float q[4] = {v.x, v.y, v.z, v.w};
+        quant255_n<4>(q);
+        st4(y, i, n, make_float4(q[0], q[1], q[2], q[3]));
     }
 }
 
@@ -275,8 +276,10 @@ __global__ void __launch_bounds__(256) attack_epilogue_kernel(const float* __res
                                                               float* __restrict__ out, int64_t n, int clamp01, int quant) {
     WM_EW_LOOP(i) {
         const float4 a = ld4(x, i, n), b = ld4(sim, i, n);
-        st4(out, i, n, make_float4(epilogue1(a.x, b.x, clamp01, quant), epilogue1(a.y, b.y, clamp01, quant),
-                                   epilogue1(a.z, b.z, clamp01, quant), epilogue1(a.w, b.w, clamp01, quant)));
+        float q[4] = {epilogue1(a.x, b.x, clamp01, 0), epilogue1(a.y, b.y, clamp01, 0),
+                      epilogue1(a.z, b.z, clamp01, 0), epilogue1(a.w, b.w, clamp01, 0)};
+        if (quant) quant255_n<4>(q);
+        st4(out, i, n, make_float4(q[0], q[1], q[2], q[3]));
     }
 }
 // out[i] = sum_k g[k * n + i]   (straight-through backward of the K-way bank: every slice passes gy to x)

@@ -96,8 +96,22 @@ __device__ __forceinline__ float div255(float n) {
     const float q0 = n * r;
     return fmaf(fmaf(-q0, 255.f, n), r, q0);
 }
-// N values at once: one range check (and branch) for the whole group.  Fast path: 1.5 * 2^23 trick for
-// round-half-even (exact for |t| < 2^22) + div255; anything out of range takes rintf + IEEE division.
+// round(v * 255) / 255 for N values at once, bit-identical to torch's (v * 255.).round() / 255.: one range
+// check (and branch) for the whole group.  Fast path: the 1.5 * 2^23 trick for round-half-even (exact for
+// |t| < 2^22) + div255; anything out of range takes rintf + the IEEE division.
+template <int N>
+__device__ __forceinline__ void quant255_n(float* v) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { v[i] = __fmul_rn(v[i], 255.f); m = fmaxf(m, fabsf(v[i])); }
+    if (m < 65536.f) {                   // (a NaN propagates through either path)
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = div255(__fsub_rn(__fadd_rn(v[i], 12582912.f), 12582912.f));
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __fdiv_rn(rintf(v[i]), 255.f);
+    }
+}
 template <int N>
 __device__ __forceinline__ void ep_apply_n(float* v, const float* x, const StoreEp& e) {
     if (e.clamp01) {
@@ -106,18 +120,7 @@ __device__ __forceinline__ void ep_apply_n(float* v, const float* x, const Store
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = __fadd_rn(x[i], __fsub_rn(v[i], x[i]));   // same fp32 operation order as the reference
-    if (e.quant) {
-        float m = 0.f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { v[i] = __fmul_rn(v[i], 255.f); m = fmaxf(m, fabsf(v[i])); }
-        if (m < 65536.f) {                   // (a NaN propagates through either path)
-#pragma unroll
-            for (int i = 0; i < N; ++i) v[i] = div255(__fsub_rn(__fadd_rn(v[i], 12582912.f), 12582912.f));
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) v[i] = __fdiv_rn(rintf(v[i]), 255.f);
-        }
-    }
+    if (e.quant) quant255_n<N>(v);
 }
 __device__ __forceinline__ float ep_apply(float v, float x, const StoreEp& e) {
     ep_apply_n<1>(&v, &x, e);
