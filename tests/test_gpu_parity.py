@@ -1221,3 +1221,29 @@ def test_device_rng_makes_stochastic_layers_graph_capturable():
         WF.device_rng(False)
     a = wmattack.Gaussian()(torch.zeros(1, 3, 8, 8, device=DEV) + 0.5)
     assert torch.isfinite(a).all()
+
+
+def test_quantization_bit_exact_on_boundary_values():
+    """Quantization (models/modules/Quantization.py:7-14; the clamp is commented out upstream): round(x*255)/255
+    bit-for-bit against torch on the host for every 8-bit level, every half-way point +- 1 ulp
+    (round-half-even), random values outside [0,1], the clamped variant, and values far outside the fast
+    quantiser's range (up to 1e6, inf, nan)."""
+    k = torch.arange(256, dtype=torch.float32)
+    levels = k / 255
+    halves = (k[:-1] + 0.5) / 255
+    pts = torch.cat([levels, halves, torch.nextafter(halves, torch.tensor(2.0)), torch.nextafter(halves, torch.tensor(-1.0)),
+                     torch.nextafter(levels, torch.tensor(2.0)), torch.nextafter(levels, torch.tensor(-1.0)),
+                     rnd((4096,), 3) * 3 - 1])
+    pts = pts[: pts.numel() // 4 * 4].view(1, 1, -1, 4)
+    assert torch.equal(wmattack.Quantization()(pts.to(DEV)).cpu(), torch.round(pts * 255.0) / 255.0)
+    assert torch.equal(wmattack.Quantization(clamp01=True)(pts.to(DEV)).cpu(),
+                       torch.round(torch.clamp(pts, 0, 1) * 255.0) / 255.0)
+    wild = torch.cat([pts.flatten(), torch.tensor([300.0, -2e3, 7e4, 1e6, float("inf"), float("nan"), -0.0, 1e-40])])
+    wild = wild[: wild.numel() // 4 * 4].view(1, 1, -1, 4).to(DEV)
+    out = torch.empty_like(wild)
+    with torch.no_grad():
+        wmattack.Identity().forward_into(wild, out, (wild, False, True))          # un-clamped quantiser path
+    wc = wild.cpu()
+    ref = torch.round((wc + (wc - wc)) * 255.0) / 255.0                           # straight-through form: inf -> nan
+    o = out.cpu()
+    assert bool(((o == ref) | (torch.isnan(o) & torch.isnan(ref))).all())
