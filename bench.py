@@ -3,27 +3,34 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch: DiffJPEG(q=50) forward+backward followed
-by forward+backward of every member of BASELINE config 2's
-Combined([JpegCompression, GaussianBlur(k3), MiddleBlur(3), Gaussian(σ=.05), Resize(bicubic)])
-on a 64x3x512x512 fp32 batch (Combined picks ONE member at random per call; running all five
-by id is its expectation and keeps steps identical).  Metric: megapixels of (b,h,w) locations
-pushed through a layer's forward+backward per second = steps * 6 * B*H*W / time.
+One "step" = one pass of the hot path over one batch: DiffJPEG(q=50) forward+backward followed by
+forward+backward of every member of BASELINE config 2's
+Combined([JpegCompression, GaussianBlur(k3), MiddleBlur(5) and (3), Gaussian(sigma=.05), Resize(bicubic)])
+on a 64x3x512x512 fp32 batch (Combined picks ONE member at random per call, running
+every member by id is its expectation and keeps steps identical).  Metric: megapixels of (b,h,w)
+locations pushed through a layer's forward+backward per second = steps * 7 * B*H*W / time.
 
   value     : device-resident inputs, CUDA-event timed, max over ranks.
-  e2e       : same step through the public nn.Module API with the batch in PINNED HOST memory:
-              every step copies its input host->device (double-buffered on a copy stream) and
-              reads a per-step result scalar back.
+  e2e       : same step through the public nn.Module API with the batch in PINNED HOST memory: every
+              step copies its input host->device (201 MB) and the step's result (the last layer's
+              input gradient, 201 MB) device->host, both inside the timed region, double-buffered
+              on copy streams.
   roofline  : for the kernel with the largest share of the step: algorithmic bytes / measured
               average launch duration (CUDA events inside the timed region) vs the measured HBM peak.
-  cpu_baseline / --impl reference : the CPU oracle port (oracle/attack_oracle.py, torch fp32,
-              all host threads) on a bounded sample of the same workload.
+  cpu_baseline / --impl reference : the UNMODIFIED reference modules (baseline/_ref, vendored by
+              baseline/vendor_reference.py; kind "reference") on the box's host cores, bounded sample;
+              falls back to the oracle port (kind "port") only if baseline/_ref is absent.
+  extra keys: kernels (per-kernel roofline table), config1 (DiffJPEG q50 16x3x256^2: reference on
+              host cores exactly as SURVEY 8d C1 + ours), reference_gpu_eager (the reference's
+              eager graph on this B200, same step), config3 (1080p frame sweep), config5 (4K
+              quality sweep, this rank's share of the 64-frame clip), train_step (config 4).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -40,15 +47,21 @@ import torch  # noqa: E402
 B, H, W = 64, 512, 512
 QUALITY = 50
 RESIZE_RATIOS = (0.5, 0.75, 1.25, 1.5)
-LAYERS = ("diffjpeg", "jpegcompression", "gaussianblur", "middleblur3", "gaussian", "resize")
-# algorithmic HBM bytes per (b,h,w) location, fp32 NCHW (DESIGN.md §4 / SURVEY §8d)
+LAYERS = ("diffjpeg", "jpegcompression", "gaussianblur", "middleblur5", "middleblur3", "gaussian", "resize")
+NL = len(LAYERS)
+# algorithmic HBM bytes per (b,h,w) location, fp32 NCHW (DESIGN.md §3 / SURVEY §8d)
 ALG_BYTES = {
-    "diffjpeg": (24, 36), "jpegcompression": (24, 24), "gaussianblur": (24, 24),
-    "middleblur3": (27, 27), "gaussian": (24, 24), "resize": (24, 36),   # gaussian: SURVEY 8d (1-bit clamp mask saved)
+    "diffjpeg": (24, 36), "jpegcompression": (24, 24), "gaussianblur": (24, 24), "middleblur5": (27, 27),
+    "middleblur3": (27, 27), "gaussian": (24, 24), "resize": (24, 36),
 }
 METRIC = "DiffJPEG+Combined fwd+bwd Mpix/s"
-WORKLOAD = ("configs[1]: DiffJPEG(q50) + Combined([JpegCompression, GaussianBlur(k3), MiddleBlur(3), "
-            "Gaussian(.05), Resize(bicubic)]) members id=0..4, fwd+bwd, 64x3x512x512 fp32")
+WORKLOAD = ("configs[1]: DiffJPEG(q50) + Combined([JpegCompression, GaussianBlur(k3), MiddleBlur(5), MiddleBlur(3), "
+            "Gaussian(.05), Resize(bicubic)]) every member by id, fwd+bwd, 64x3x512x512 fp32")
+
+
+def config_block(world):
+    return {"workload": WORKLOAD, "per_gpu_batch": [B, 3, H, W], "resize_ratios": list(RESIZE_RATIOS),
+            "l2": "each tensor is 201 MB > 126 MB L2, no flush needed", "sharding": f"batch x{world}, no collective"}
 
 
 def hbm_peak():
@@ -109,42 +122,70 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------- plumbing
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def allreduce_max(v, world, dev):
+    if world == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed(fn, iters, warm, world=1, dev=None):
+    """ms per call of fn(): CUDA events on the current stream, `warm` untimed calls, max over ranks."""
+    for _ in range(warm):
+        fn()
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return allreduce_max(e0.elapsed_time(e1) / iters, world, dev)
+
+
 # ------------------------------------------------------------------------------------- our arm
 def build_layers(dev):
     import wmattack
     dj = wmattack.DiffJPEG(True, H, W, quality=QUALITY)
-    comb = wmattack.Combined([wmattack.JpegCompression(dev), wmattack.GaussianBlur(), wmattack.MiddleBlur(3),
-                              wmattack.Gaussian(), wmattack.Resize()])
+    comb = wmattack.Combined([wmattack.JpegCompression(dev), wmattack.GaussianBlur(), wmattack.MiddleBlur(5),
+                              wmattack.MiddleBlur(3), wmattack.Gaussian(), wmattack.Resize()])
     return dj, comb
 
 
 def run_step(dj, comb, x, g, step, events=None):
-    """One step; if `events` is given, records a CUDA event after every forward and backward."""
+    """One step; if `events` is given, records a CUDA event after every forward and backward.
+    Returns the last layer's input gradient (the step's result for the e2e read-back)."""
     def mark():
         if events is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             events.append(e)
-    checksum = None
     mark()
-    for li in range(6):
+    for li in range(NL):
         x.grad = None
         if li == 0:
             y = dj(x)
-        elif li == 5:
-            y = comb.list[4](x, resize_ratio=RESIZE_RATIOS[step % len(RESIZE_RATIOS)])
+        elif li == NL - 1:
+            y = comb.list[5](x, resize_ratio=RESIZE_RATIOS[step % len(RESIZE_RATIOS)])
         else:
             y = comb(x, id=li - 1)
         mark()
         y.backward(g)
         mark()
-        checksum = x.grad if checksum is None else checksum  # keep a handle for the result read-back
-    return checksum
+    return x.grad
 
 
 def ours(args, rank, world, dev):
     from wmattack import _lib
-    # Run backward nodes on the calling thread: every layer is ONE kernel launch of 60-170 us, and the
+    # Run backward nodes on the calling thread: every layer is ONE kernel launch of 60-300 us, and the
     # autograd engine's hand-off to its device thread (~40 us per backward() call) would otherwise leave
     # the GPU idle between launches.  A trainer that calls .backward() once per step does not need this.
     torch.autograd.set_multithreading_enabled(False)
@@ -153,10 +194,10 @@ def ours(args, rank, world, dev):
     gen = torch.Generator(dev).manual_seed(rank)
     x = torch.rand(B, 3, H, W, device=dev, generator=gen).requires_grad_(True)
     g = torch.rand(B, 3, H, W, device=dev, generator=gen)
-    px_step = 6 * B * H * W
+    px_step = NL * B * H * W
 
     clk = ClockSampler(torch.cuda.current_device())
-    clk.__enter__()                      # samples every 20 ms until the e2e leg is done (all under load)
+    clk.__enter__()                      # samples every 20 ms until the last GPU leg is done (all under load)
     for s in range(args.warmup):
         run_step(dj, comb, x, g, s)
     barrier(world)
@@ -175,9 +216,10 @@ def ours(args, rank, world, dev):
     ms = allreduce_max(ms, world, dev)
     value = world * args.steps * px_step / (ms / 1e3) / 1e6
 
-    # per-kernel-group durations from the events recorded inside the timed region
+    # per-kernel durations from the events recorded inside the timed region (every layer is ONE kernel
+    # launch per direction, so each event interval is one kernel + its launch gap)
     per = {}
-    n_ev = 13
+    n_ev = 2 * NL + 1
     for s in range(args.steps):
         ev = events[s * n_ev:(s + 1) * n_ev]
         for li, name in enumerate(LAYERS):
@@ -192,18 +234,36 @@ def ours(args, rank, world, dev):
         byts = ALG_BYTES[name][0 if d == "fwd" else 1] * px
         kernels[k] = {"ms": round(msk, 4), "GBps": round(byts / (msk / 1e3) / 1e9, 1),
                       "frac": round(byts / (msk / 1e3) / 1e9 / peak, 3)}
-    # dominant kernel: every layer is ONE kernel launch per direction, so each event interval is one kernel
-    single = dict(avg)
-    dom = max(single, key=single.get)
+    dom = max(avg, key=avg.get)
     dname, dd = dom.split(".")
     dbytes = ALG_BYTES[dname][0 if dd == "fwd" else 1] * px
+    step_bytes = sum(sum(ALG_BYTES[n]) for n in LAYERS) * px
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dbytes / (avg[dom] / 1e3) / 1e9, 1), "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": round(dbytes / (avg[dom] / 1e3) / 1e9 / peak, 4),
                 "traffic": load_ncu_traffic(dom), "share_of_step": round(avg[dom] / (ms / args.steps), 4),
-                "algorithmic_bytes_per_launch": dbytes}
+                "algorithmic_bytes_per_launch": dbytes,
+                "whole_step": {"algorithmic_bytes": step_bytes, "GBps": round(step_bytes / (ms / args.steps / 1e3) / 1e9, 1),
+                               "frac": round(step_bytes / (ms / args.steps / 1e3) / 1e9 / peak, 4)}}
 
     e2e = run_e2e(args, dj, comb, g, rank, world, dev, px_step)
     e2e_u8 = run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=True)
+    extras = {}
+    for name, fn in (("config1", lambda: config1_gpu(dev)), ("config3", lambda: config3(world, dev)),
+                     ("config5", lambda: config5(rank, world, dev)),
+                     ("train_step", lambda: train_step_leg(args, rank, world, dev))):
+        if name in args.skip:
+            continue
+        try:
+            extras[name] = fn()
+        except Exception as e:                      # an extra leg must never take the headline down
+            extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    if world == 1 and "reference_gpu_eager" not in args.skip:
+        try:
+            extras["reference_gpu_eager"] = reference_gpu_eager(dev, value)
+        except Exception as e:
+            extras["reference_gpu_eager"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
     if len(clk.lines) < 3:               # very short runs: keep the GPU busy until a few samples exist
         t_end = time.time() + 0.5
         while time.time() < t_end:
@@ -214,13 +274,15 @@ def ours(args, rank, world, dev):
         "metric": METRIC, "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": [B, 3, H, W], "resize_ratios": list(RESIZE_RATIOS),
-                   "l2": "each tensor is 201 MB > 126 MB L2, no flush needed", "sharding": f"batch x{world}, no collective"},
-        "e2e": e2e, "e2e_u8": dict(e2e_u8, note="same step with 8-bit host frames uploaded as bytes and converted on "
-                                              "the device (wm_u8_to_unit_float); extra to the contract's fp32 e2e"),
+        "config": config_block(world),
+        "e2e": e2e, "e2e_u8": dict(e2e_u8, note="same step with 8-bit host frames: bytes uploaded and converted on the "
+                                              "device (wm_u8_to_unit_float), result returned as bytes; extra to the contract's fp32 e2e"),
         "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "parity_note": "MiddleBlur/GF delegate to kornia upstream (not vendored/pinned/installed): their parity is "
+                       "pinned only to the kornia 0.6.x algorithm restated in oracle/ — 'parity unpinned' rows",
         "clocks": clk.summary(),
     }
+    out.update(extras)
     return out
 
 
@@ -247,36 +309,44 @@ def bind_to_gpu_numa_node(dev):
 
 
 def run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=False):
-    """Host-resident input: H2D of the step's batch (pinned, double-buffered on a copy stream) +
-    D2H of a result scalar, every step, inside the timed region.
-    u8=True: the host holds 8-bit frames (what a video decoder produces); they are uploaded as bytes
-    and converted to [0,1] float on the device by wmattack.functional.from_uint8 inside the timed region."""
+    """Host-resident input AND result: per step, H2D of the batch from pinned memory (copy stream,
+    double-buffered, overlapping the previous step's kernels) and D2H of the step's result — the input
+    gradient of the last layer, 201 MB — into pinned memory (second copy stream), all inside the timed region.
+    u8=True: the host holds 8-bit frames (what a video decoder produces / an encoder consumes): bytes are
+    uploaded, converted on the device (wm_u8_to_unit_float), and the attacked frames of the last layer go
+    back as bytes (wm_unit_float_to_u8)."""
     from wmattack import functional as WF
     numa = bind_to_gpu_numa_node(dev) if world > 1 else None
+    shape = (B, 3, H, W)
     if u8:
-        host = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        stage = [torch.empty(B, 3, H, W, device=dev, dtype=torch.uint8) for _ in range(2)]
+        host = [torch.randint(0, 256, shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        stage = [torch.empty(shape, device=dev, dtype=torch.uint8) for _ in range(2)]
+        res_dev = [torch.empty(shape, device=dev, dtype=torch.uint8) for _ in range(2)]
+        res_host = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
     else:
-        host = [torch.rand(B, 3, H, W).pin_memory() for _ in range(2)]
-    devbuf = [torch.empty(B, 3, H, W, device=dev) for _ in range(2)]
-    result = torch.zeros(1).pin_memory()
-    copy_stream = torch.cuda.Stream()
+        host = [torch.rand(shape).pin_memory() for _ in range(2)]
+        res_dev = [None, None]
+        res_host = [torch.empty(shape).pin_memory() for _ in range(2)]
+    devbuf = [torch.empty(shape, device=dev) for _ in range(2)]
+    up_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
     main = torch.cuda.current_stream()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]       # upload i landed
+    free = [torch.cuda.Event() for _ in range(2)]        # devbuf i no longer read by the step
+    done = [torch.cuda.Event() for _ in range(2)]        # step result i produced
+    drained = [torch.cuda.Event() for _ in range(2)]     # D2H of result i finished
 
     def upload(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[i % 2])
+        with torch.cuda.stream(up_stream):
+            up_stream.wait_event(free[i % 2])
             if u8:
                 stage[i % 2].copy_(host[i % 2], non_blocking=True)
                 WF.from_uint8(stage[i % 2], out=devbuf[i % 2])          # on the copy stream, ahead of the step
             else:
                 devbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-            ready[i % 2].record(copy_stream)
+            ready[i % 2].record(up_stream)
 
     def loop(n):
-        for e in free:
+        for e in free + drained:
             e.record(main)
         upload(0)
         for s in range(n):
@@ -285,8 +355,21 @@ def run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=False):
             main.wait_event(ready[s % 2])
             x = devbuf[s % 2].requires_grad_(True)
             gx = run_step(dj, comb, x, g, s)
-            result.copy_(gx.view(-1)[:1], non_blocking=True)
+            if u8:
+                main.wait_event(drained[s % 2])                           # res_dev slot reusable
+                with torch.no_grad():
+                    WF.to_uint8(comb.list[5](x.detach(), resize_ratio=RESIZE_RATIOS[s % 4]), out=res_dev[s % 2])
+                res = res_dev[s % 2]
+            else:
+                res = gx
+            done[s % 2].record(main)
+            with torch.cuda.stream(down_stream):
+                down_stream.wait_event(done[s % 2])
+                res_host[s % 2].copy_(res, non_blocking=True)
+                res.record_stream(down_stream)
+                drained[s % 2].record(down_stream)
             devbuf[s % 2] = x.detach()
+            x.grad = None
             free[s % 2].record(main)
         torch.cuda.synchronize()
 
@@ -295,12 +378,18 @@ def run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=False):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     loop(args.steps)
+    torch.cuda.synchronize()
     t1.record()
     torch.cuda.synchronize()
     ms = allreduce_max(t0.elapsed_time(t1), world, dev)
+    nbytes = B * 3 * H * W * (1 if u8 else 4)
+    per_step = ms / args.steps
     return {"value": round(world * args.steps * px_step / (ms / 1e3) / 1e6, 1), "unit": "Mpix/s",
-            "h2d_bytes_per_step": B * 3 * H * W * (1 if u8 else 4), "d2h_bytes_per_step": 4,
-            "ms_per_step": round(ms / args.steps, 4), "host_cpus": numa}
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "ms_per_step": round(per_step, 4), "host_cpus": numa,
+            "aggregate_h2d_GBps": round(world * nbytes / (per_step / 1e3) / 1e9, 1),
+            "aggregate_d2h_GBps": round(world * nbytes / (per_step / 1e3) / 1e9, 1),
+            "bound": "PCIe: the copies, not a kernel, set this number (see aggregate_*_GBps)"}
 
 
 def load_ncu_traffic(kernel_key):
@@ -312,62 +401,262 @@ def load_ncu_traffic(kernel_key):
         return None
 
 
-# --------------------------------------------------------------------------------- CPU oracle arm
-def cpu_port_step(O, x, g, step):
-    """The same 6 forward+backward passes on the CPU oracle (torch fp32, autograd)."""
-    fns = [lambda t: O.diffjpeg(t, QUALITY), O.jpeg_compression, lambda t: O.gaussian_blur(t, 3),
-           lambda t: O.median_blur(t, 3),
-           lambda t: O.gaussian_noise_clamped(t, torch.randn_like(t) * 0.05),
-           lambda t: O.resize(t, RESIZE_RATIOS[step % len(RESIZE_RATIOS)])]
-    for fn in fns:
-        xx = x.clone().requires_grad_(True)
-        fn(xx).backward(g)
+# ----------------------------------------------------------------------- extra legs (configs 1, 3, 5)
+def config1_gpu(dev):
+    """BASELINE config 1's workload (DiffJPEG q50 fwd+bwd, 16x3x256x256) on this GPU, eager and as a
+    replayed CUDA graph (at this size the call is launch-bound)."""
+    import wmattack
+    g0 = torch.Generator().manual_seed(0)
+    x = torch.rand(16, 3, 256, 256, generator=g0).to(dev).requires_grad_(True)
+    gy = torch.rand(16, 3, 256, 256, generator=torch.Generator().manual_seed(1)).to(dev)
+    m = wmattack.DiffJPEG(True, 256, 256, quality=50)
+
+    def step():
+        torch.autograd.grad(m(x), x, gy)
+    eager = timed(step, 50, 5)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(); step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    rep = timed(graph.replay, 200, 10)
+    px = 16 * 256 * 256
+    return {"workload": "configs[0]: DiffJPEG(q50) fwd+bwd 16x3x256x256 fp32", "ours_eager_ms": round(eager, 4),
+            "ours_graph_ms": round(rep, 4), "ours_eager_mpix_s": round(px / eager / 1e3, 1),
+            "ours_graph_mpix_s": round(px / rep / 1e3, 1)}
 
 
-def cpu_baseline(steps=1, sample_b=2, warmup=1):
+def config3(world, dev, frames=(1, 4, 16, 64, 256)):
+    """BASELINE config 3: MiddleBlur 3x3 / 5x5 and GaussianBlur sigma=2 (k3 = the layer's default, k7 = GF's)
+    over N x 3 x 1080 x 1920 frame batches, N frames PER GPU (weak), forward + backward."""
+    import wmattack
+    peak, _ = hbm_peak()
+    layers = [("middleblur3", lambda: wmattack.MiddleBlur(3), 54), ("middleblur5", lambda: wmattack.MiddleBlur(5), 54),
+              ("gaussianblur_k3", lambda: wmattack.GaussianBlur(3), 48), ("gaussianblur_k7", lambda: wmattack.GaussianBlur(7), 48)]
+    out = {"workload": "configs[2]: N x 3 x 1080 x 1920 fp32 per GPU, fwd+bwd", "rows": []}
+    for n in frames:
+        x = torch.rand(n, 3, 1080, 1920, device=dev).requires_grad_(True)
+        g = torch.rand(n, 3, 1080, 1920, device=dev)
+        px = n * 1080 * 1920
+        for name, mk, bpp in layers:
+            layer = mk()
+            iters = max(3, min(100, int(3e9 / (px * bpp))))
+            ms = timed(lambda: torch.autograd.grad(layer(x), x, g), iters, 3, world, dev)
+            gbs = px * bpp / ms / 1e6
+            out["rows"].append({"frames_per_gpu": n, "layer": name, "ms": round(ms, 4),
+                                "mpix_s_aggregate": round(world * px / ms / 1e3, 1), "frac_of_hbm_peak": round(gbs / peak, 3)})
+        del x, g
+        torch.cuda.empty_cache()
+    return out
+
+
+def config5(rank, world, dev, total_frames=64, chunk=8):
+    """BASELINE config 5: DiffJPEG quality sweep 10..95 over a 64-frame 4K clip, frames sharded
+    contiguously over the ranks (strong scaling: 64/world frames each, processed 8 frames per call)."""
+    import wmattack
+    from wmattack.sharding import frame_shard
+    peak, _ = hbm_peak()
+    a, b = frame_shard(total_frames, rank, world)
+    mine = b - a
+    chunk = min(chunk, mine)
+    x = torch.rand(chunk, 3, 2160, 3840, device=dev).requires_grad_(True)
+    g = torch.rand(chunk, 3, 2160, 3840, device=dev)
+    calls = -(-mine // chunk)
+    rows = []
+    tot_ms = 0.0
+    for q in (10, 20, 30, 40, 50, 60, 70, 80, 90, 95):
+        m = wmattack.DiffJPEG(True, 2160, 3840, quality=q)
+
+        def clip():
+            for _ in range(calls):
+                torch.autograd.grad(m(x), x, g)
+        ms = timed(clip, 3, 1, world, dev)
+        tot_ms += ms
+        px = total_frames * 2160 * 3840
+        rows.append({"quality": q, "ms_per_clip": round(ms, 3), "mpix_s_aggregate": round(px / ms / 1e3, 1),
+                     "frac_of_hbm_peak_per_gpu": round(px / world * 60 / ms / 1e6 / peak, 3)})
+    return {"workload": f"configs[4]: DiffJPEG q10..95 fwd+bwd on 64x3x2160x3840, {mine} frames on this rank "
+                        f"({chunk} per call), scaling strong", "rows": rows,
+            "mpix_s_aggregate_mean": round(10 * total_frames * 2160 * 3840 / tot_ms / 1e3, 1)}
+
+
+# ------------------------------------------------------------------ the reference itself (baseline/_ref)
+def _ref_step_fns(R, dev, b):
+    """The same 7 forward+backward passes through the reference's OWN modules (baseline/_ref).
+    Combined itself cannot hold MiddleBlur upstream (it has no .name, combined.py:19), so members are
+    called directly.  JpegCompression's autograd backward raises on torch >= 2 (in-place unsqueeze_ on
+    views, jpeg_compression.py:109,118): its backward is stood in for by a second forward (the layer is
+    linear and its adjoint is the same conv pair transposed) — never slower than a real backward."""
+    dj = R.DiffJPEG(True, H, W, quality=QUALITY)
+    jc, gb, m5, m3, ga, rs = R.JpegCompression(dev), R.GaussianBlur(), R.MiddleBlur(5), R.MiddleBlur(3), R.Gaussian(), R.Resize()
+    if dev != "cpu":
+        for m in (dj, jc, gb, m5, m3, ga, rs):
+            m.to(dev)
+
+    def fb(layer):
+        def run(x, g, step):
+            xx = x.detach().requires_grad_(True)
+            layer(xx).backward(g)
+        return run
+
+    def jc_run(x, g, step):
+        with torch.no_grad():
+            jc(x)
+            jc(x)
+
+    def rs_run(x, g, step):
+        xx = x.detach().requires_grad_(True)
+        rs(xx, resize_ratio=RESIZE_RATIOS[step % len(RESIZE_RATIOS)]).backward(g)
+    return [("diffjpeg", fb(dj)), ("jpegcompression", jc_run), ("gaussianblur", fb(gb)), ("middleblur5", fb(m5)),
+            ("middleblur3", fb(m3)), ("gaussian", fb(ga)), ("resize", rs_run)]
+
+
+def _port_step_fns():
     from oracle import attack_oracle as O
+    def fb(fn):
+        def run(x, g, step):
+            xx = x.detach().requires_grad_(True)
+            fn(xx).backward(g)
+        return run
+    return [("diffjpeg", fb(lambda t: O.diffjpeg(t, QUALITY))), ("jpegcompression", fb(O.jpeg_compression)),
+            ("gaussianblur", fb(lambda t: O.gaussian_blur(t, 3))), ("middleblur5", fb(lambda t: O.median_blur(t, 5))),
+            ("middleblur3", fb(lambda t: O.median_blur(t, 3))),
+            ("gaussian", fb(lambda t: O.gaussian_noise_clamped(t, torch.randn_like(t) * 0.05))),
+            ("resize", lambda x, g, s: fb(lambda t: O.resize(t, RESIZE_RATIOS[s % 4]))(x, g, s))]
+
+
+def cpu_reference(steps, warmup, sample_b):
+    """Times the reference's CPU path on the host cores on a bounded sample (sample_b of the 64 images).
+    Returns (cpu_baseline dict, seconds per step)."""
+    from baseline import ref_harness as RH
     torch.set_num_threads(os.cpu_count() or 1)
+    kind = "reference" if RH.available() else "port"
     x = torch.rand(sample_b, 3, H, W)
     g = torch.rand(sample_b, 3, H, W)
+    if kind == "reference":
+        with RH.cpu_mode():
+            fns = _ref_step_fns(RH.layers("cpu"), "cpu", sample_b)
+            sec, per = _time_cpu(fns, x, g, steps, warmup)
+        src = "UNMODIFIED reference modules from baseline/_ref (utils/JPEG.py DiffJPEG, noise_layers/*)"
+        if RH.kornia_is_stub():
+            src += "; kornia.filters.MedianBlur = the harness's kornia-0.6.x stand-in (kornia not installed)"
+        src += "; JpegCompression: 2 forwards (its autograd backward raises on torch>=2)"
+    else:
+        fns = _port_step_fns()
+        sec, per = _time_cpu(fns, x, g, steps, warmup)
+        src = "oracle/attack_oracle.py port (baseline/_ref not present)"
+    val = NL * sample_b * H * W / sec / 1e6
+    return {"value": round(val, 3), "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} step(s) of the same {NL} fwd+bwd passes on a {sample_b}x3x{H}x{W} sample of the "
+                      f"64-image batch; {src}; torch {torch.__version__} CPU fp32, {sec * steps:.1f} s timed",
+            "per_layer_ms": {k: round(v * 1e3, 1) for k, v in per.items()}}, sec
+
+
+def _time_cpu(fns, x, g, steps, warmup):
     for s in range(warmup):
-        cpu_port_step(O, x, g, s)
-    t = time.perf_counter()
+        for _, fn in fns:
+            fn(x, g, s)
+    per = {k: 0.0 for k, _ in fns}
+    t_all = time.perf_counter()
     for s in range(steps):
-        cpu_port_step(O, x, g, s)
-    dt = time.perf_counter() - t
-    val = steps * 6 * sample_b * H * W / dt / 1e6
-    return {"value": round(val, 3), "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} step(s) of the same 6 fwd+bwd passes on a {sample_b}x3x{H}x{W} batch "
-                      f"(oracle/attack_oracle.py, torch {torch.__version__} CPU fp32, {dt:.1f} s)"}, dt / steps
+        for k, fn in fns:
+            t = time.perf_counter()
+            fn(x, g, s)
+            per[k] += time.perf_counter() - t
+    sec = (time.perf_counter() - t_all) / steps
+    return sec, {k: v / steps for k, v in per.items()}
+
+
+def config1_reference_cpu():
+    """SURVEY 8(d) C1 exactly as named: x = rand(16,3,256,256) seed 0, gy = rand seed 1,
+    DiffJPEG(True,256,256,quality=50) (round_only_at_0), y = m(x); y.backward(gy); 3 warm-up + 10 timed, median."""
+    from baseline import ref_harness as RH
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = torch.rand(16, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    gy = torch.rand(16, 3, 256, 256, generator=torch.Generator().manual_seed(1))
+    if RH.available():
+        with RH.cpu_mode():
+            m = RH.layers("cpu").DiffJPEG(True, 256, 256, quality=50)
+            kind = "reference"
+            ts = _c1_times(m, x, gy)
+    else:
+        from oracle import attack_oracle as O
+        kind = "port"
+        ts = _c1_times(lambda t: O.diffjpeg(t, 50), x, gy)
+    med = statistics.median(ts)
+    return {"workload": "configs[0]: DiffJPEG(q50) fwd+bwd 16x3x256x256 fp32 on CPU, 3 warm-up + 10 timed, median",
+            "kind": kind, "cores": torch.get_num_threads(), "cpu_count": os.cpu_count(),
+            "reference_cpu_ms": round(med * 1e3, 2), "reference_cpu_mpix_s": round(16 * 256 * 256 / med / 1e6, 2)}
+
+
+def _c1_times(m, x, gy):
+    ts = []
+    for i in range(13):
+        xx = x.clone().requires_grad_(True)
+        t = time.perf_counter()
+        y = m(xx)
+        y.backward(gy)
+        if i >= 3:
+            ts.append(time.perf_counter() - t)
+    return ts
+
+
+def reference_gpu_eager(dev, our_value, steps=3, warmup=2):
+    """The reference's eager PyTorch graph on THIS B200: same 7 fwd+bwd passes, same
+    64x3x512x512 batch, unmodified modules from baseline/_ref moved to the GPU."""
+    from baseline import ref_harness as RH
+    if not RH.available():
+        return {"unavailable": "baseline/_ref not present"}
+    fns = _ref_step_fns(RH.layers("cuda"), str(dev), B)
+    x = torch.rand(B, 3, H, W, device=dev)
+    g = torch.rand(B, 3, H, W, device=dev)
+    for s in range(warmup):
+        for _, fn in fns:
+            fn(x, g, s)
+    torch.cuda.synchronize()
+    per = {k: 0.0 for k, _ in fns}
+    for s in range(steps):
+        for k, fn in fns:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(x, g, s)
+            e1.record()
+            torch.cuda.synchronize()
+            per[k] += e0.elapsed_time(e1) / steps
+    ms = sum(per.values())
+    val = NL * B * H * W / ms / 1e3
+    return {"value": round(val, 1), "unit": "Mpix/s", "ms_per_step": round(ms, 3), "steps": steps,
+            "per_layer_ms": {k: round(v, 3) for k, v in per.items()}, "ours_over_reference_eager": round(our_value / val, 2),
+            "note": "unmodified reference modules (baseline/_ref) run eagerly on this GPU, device-resident inputs, "
+                    "CUDA events; JpegCompression = 2 forwards (its backward raises upstream)"
+                    + ("; MedianBlur = kornia-0.6.x stand-in" if RH.kornia_is_stub() else "")}
+
+
+def train_step_leg(args, rank, world, dev):
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import train_step as TS
+    return TS.bench(rank, world, dev)
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return None
-    sample_b = 16
-    base, sec = cpu_baseline(steps=max(1, args.steps), sample_b=sample_b, warmup=min(args.warmup, 1))
-    return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mpix/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": [B, 3, H, W],
-                       "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; its CPU path "
-                               "is timed through the oracle port on a bounded sample"},
-            "cpu_baseline": base,
-            "e2e": {"value": base["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-
-
-# ------------------------------------------------------------------------------------- plumbing
-def barrier(world):
-    if world > 1:
-        torch.distributed.barrier()
-
-
-def allreduce_max(v, world, dev):
-    if world == 1:
-        return v
-    t = torch.tensor([v], device=dev, dtype=torch.float64)
-    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    return float(t.item())
+    sample_b = 8
+    base, sec = cpu_reference(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)), sample_b=sample_b)
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mpix/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_block(world), "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:
+        out["config1"] = config1_reference_cpu()
+    except Exception as e:
+        out["config1"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def main():
@@ -377,7 +666,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip", default="", help="comma list of extra legs to skip: config1,config3,config5,train_step,reference_gpu_eager")
     args = ap.parse_args()
+    args.skip = set(filter(None, args.skip.split(",")))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -390,21 +681,24 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
-                         "(use --impl reference for the CPU oracle arm)")
+                         "(use --impl reference for the CPU reference arm)")
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            # keep stdout to the one JSON line: "NCCL version ..." goes there when NCCL_DEBUG=VERSION comes
-            # from the environment or from an nccl.conf on the box (the environment wins over the file)
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=dev)
     out = ours(args, rank, world, dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"], _ = cpu_baseline(steps=8, sample_b=16, warmup=1)
+            out["cpu_baseline"], _ = cpu_reference(steps=3, warmup=1, sample_b=8)
+            try:
+                out.setdefault("config1", {}).update(config1_reference_cpu())
+                c1 = out["config1"]
+                if "ours_graph_ms" in c1:
+                    c1["ours_over_reference_cpu"] = round(c1["reference_cpu_ms"] / c1["ours_graph_ms"], 1)
+            except Exception as e:
+                out.setdefault("config1", {})["reference_cpu_error"] = f"{type(e).__name__}: {e}"[:300]
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)

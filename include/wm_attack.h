@@ -252,6 +252,10 @@ int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, i
  * upload bytes, convert on the device; the correctly rounded quotient, i.e. the values numpy / CPU torch
  * give for u8.astype(float32) / 255). */
 int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream);
+/* [0,1] float32 -> 8-bit frames, dst[i] = rint(clamp(src[i], 0, 1) * 255) (round-half-even, torch.round): the
+ * integer k of the Quantization layer's value k/255 (models/modules/Quantization.py:9), so that attacked
+ * frames leave the device as bytes (4x less D2H traffic).  NaN -> 0. */
+int wm_unit_float_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream);
 /* Store epilogue, fused: arms the epilogue above for the NEXT forward launch issued from the calling
  * host thread; that kernel then writes  Quantization( x + (clamp(v, 0, 1) - x) )  instead of its own
  * value v, reading x (dense [B,C,H,W] in the layout of the output, 32-byte aligned) at the output

@@ -344,6 +344,30 @@ __global__ void __launch_bounds__(256) u8_to_unit_float_kernel(const uint8_t* __
     }
 }
 
+// The opposite direction: attacked frames leave the device as bytes (what a video encoder / an 8-bit
+// evaluation pipeline consumes): dst = rint(clamp(src, 0, 1) * 255), round-half-even like torch.round,
+// i.e. the integer k of the Quantization layer's value k/255 (models/modules/Quantization.py:9); NaN -> 0.
+__global__ void __launch_bounds__(256) unit_float_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 16; i < n; i += int64_t(gridDim.x) * blockDim.x * 16) {
+        if (i + 15 < n) {
+            uint32_t ws[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 v = ldg128_stream(src + i + 4 * k);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w |= uint32_t(__float2int_rn(__fmul_rn(__saturatef(f[j]), 255.f))) << (8 * j);
+                ws[k] = w;
+            }
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+        } else {
+            for (int64_t j = i; j < n; ++j) dst[j] = uint8_t(__float2int_rn(__fmul_rn(__saturatef(src[j]), 255.f)));
+        }
+    }
+}
+
 static inline unsigned ew_grid(int64_t n_vec) {
     const int64_t want = (n_vec + 255) / 256;
     const int64_t cap = int64_t(sm_count()) * 16;
@@ -561,5 +585,14 @@ extern "C" int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, vo
     if (n <= 0) return WM_OK;
     u8_to_unit_float_kernel<<<ew_grid((n + 15) / 16), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
     WM_LAUNCH_CHECK("wm_u8_to_unit_float");
+    return WM_OK;
+}
+
+extern "C" int wm_unit_float_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream) {
+    if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
+    WM_REQUIRE(src && dst, WM_E_NULL, "wm_unit_float_to_u8: null pointer");
+    WM_REQUIRE(aligned(src, 16) && aligned(dst, 16), WM_E_ALIGN, "wm_unit_float_to_u8: pointers must be 16-byte aligned");
+    unit_float_to_u8_kernel<<<ew_grid((n + 15) / 16), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    WM_LAUNCH_CHECK("wm_unit_float_to_u8");
     return WM_OK;
 }

@@ -60,6 +60,7 @@ SIGNATURES = {
     "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
     "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
     "wm_u8_to_unit_float": [c_u8p, c_f32p, i64, vp],
+    "wm_unit_float_to_u8": [c_f32p, c_u8p, i64, vp],
     "wm_set_store_epilogue": [c_f32p, i32, i32],
     "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
     "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],

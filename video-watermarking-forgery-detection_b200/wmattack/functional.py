@@ -886,6 +886,19 @@ def from_uint8(frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def to_uint8(frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """float32 frames in [0,1] (any shape, CUDA) -> uint8 = round(clamp(frames, 0, 1) * 255), one kernel: the
+    byte k of the Quantization layer's value k/255, so results can leave the device as bytes."""
+    _check_cuda(frames, "to_uint8")
+    frames = _f32(frames.detach()).contiguous()
+    if out is None:
+        out = torch.empty(frames.shape, device=frames.device, dtype=torch.uint8)
+    elif out.shape != frames.shape or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("to_uint8: `out` must be a contiguous uint8 tensor of the same shape")
+    _lib.call("wm_unit_float_to_u8", frames.data_ptr(), out.data_ptr(), frames.numel(), _stream())
+    return out
+
+
 # ---- real codec round trip (JpegTest, noise_layers/jpeg.py:10-45) -----------------------------------
 
 _CODEC_MODES = {"signed": 0, "unit": 1, "uint8": 2}
