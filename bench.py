@@ -493,9 +493,10 @@ def _ref_step_fns(R, dev, b):
     linear and its adjoint is the same conv pair transposed) — never slower than a real backward."""
     dj = R.DiffJPEG(True, H, W, quality=QUALITY)
     jc, gb, m5, m3, ga, rs = R.JpegCompression(dev), R.GaussianBlur(), R.MiddleBlur(5), R.MiddleBlur(3), R.Gaussian(), R.Resize()
-    if dev != "cpu":
-        for m in (dj, jc, gb, m5, m3, ga, rs):
-            m.to(dev)
+    # utils/JPEG.py keeps its quantisation tables as MODULE-LEVEL nn.Parameters shared by every instance:
+    # .to() moves them in place, so always move explicitly (the CPU leg may run after the GPU-eager leg)
+    for m in (dj, jc, gb, m5, m3, ga, rs):
+        m.to(dev)
 
     def fb(layer):
         def run(x, g, step):
@@ -691,7 +692,10 @@ def main():
     out = ours(args, rank, world, dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"], _ = cpu_reference(steps=3, warmup=1, sample_b=8)
+            try:
+                out["cpu_baseline"], _ = cpu_reference(steps=3, warmup=1, sample_b=8)
+            except Exception as e:
+                out["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
                 out.setdefault("config1", {}).update(config1_reference_cpu())
                 c1 = out["config1"]

@@ -149,7 +149,7 @@ def run(attack, nets, rank, world, dev, clips=64, frames=8, size=256, steps=5, w
     for s in range(steps):
         loss = one()
         if verbose and rank == 0:
-            print(f"step {s}: loss {float(loss):.4f}", flush=True)
+            print(f"step {s}: loss {float(loss.detach()):.4f}", flush=True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -157,7 +157,7 @@ def run(attack, nets, rank, world, dev, clips=64, frames=8, size=256, steps=5, w
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
-    desc, lossv = model.nets_desc, float(loss)
+    desc, lossv = model.nets_desc, float(loss.detach())
     del model, net, opt, x, prev, mask
     torch.cuda.empty_cache()
     return ms, desc, lossv
