@@ -61,6 +61,7 @@ ROUND_ONLY_AT_0 = 0   # utils/JPEG.py:482   (== JpegSS.round_ss, noise_layers/jp
 ROUND_CUBIC = 1       # utils/JPEG.py:472   diff_round
 ROUND_HARD = 2        # torch.round
 ROUND_FOURIER = 3     # utils/JPEG_utils.py:36  (9-term Fourier series)
+ROUND_NONE = -1       # test aid: no rounding, i.e. the pre-round quotient C / (table * factor)
 
 
 def dct_matrix(dtype=torch.float64) -> torch.Tensor:
@@ -82,6 +83,8 @@ def quality_to_factor(quality: float) -> float:
 
 
 def apply_rounding(q: torch.Tensor, mode: int) -> torch.Tensor:
+    if mode == ROUND_NONE:
+        return q
     if mode == ROUND_ONLY_AT_0:          # utils/JPEG.py:482-484
         inside = (q.abs() < 0.5).to(q.dtype)
         return inside * q ** 3 + (1 - inside) * q
@@ -275,6 +278,15 @@ def jpeg8_quantised(x: torch.Tensor, q: float, variant: int = JPEG8_HARD, subsam
     if variant == JPEG8_HARD:
         return torch.round(qq), tab
     return apply_rounding(qq, ROUND_ONLY_AT_0), tab
+
+
+def jpeg8_prequant(x: torch.Tensor, q: float, subsample: int = 0) -> torch.Tensor:
+    """Test aid: the quotient dct / table that std_quantization (noise_layers/jpeg.py:52-82) rounds,
+    as a [B,3,Hp,Wp] coefficient image."""
+    coef = jpeg8_coefficients(x, subsample)
+    ly, lc = jpeg8_tables(jpeg8_scale(q))
+    hp, wp = coef.shape[2:]
+    return coef / torch.stack([ly, lc, lc]).to(x.dtype).repeat(1, hp // 8, wp // 8)
 
 
 def jpeg8(x: torch.Tensor, q: float, variant: int = JPEG8_HARD, subsample: int = 0):

@@ -294,6 +294,52 @@ def main():
     put("combined/seed21/names", np.frombuffer(",".join(names).encode(), dtype=np.uint8))
     put("identity/is_same_object", np.array(int(Identity()(x20) is x20)))
 
+
+    # ---- round-2 additions (appended: earlier fixtures stay bit-identical) ---------------------
+    # cropped_out gradients (crop.py:78-118): both differentiable outputs, seeded rectangle
+    np.random.seed(23)
+    xx = x32.clone().requires_grad_(True)
+    outs = Crop().cropped_out(xx, min_rate=0.5)
+    gz = rand(tuple(x32.shape), 24)
+    (outs[0] * g32).sum().add((outs[1] * gz).sum()).backward()
+    put("cropped_out/seed23/gz", gz)
+    put("cropped_out/seed23/x32/scaled", outs[0])
+    put("cropped_out/seed23/x32/zero_images", outs[1])
+    put("cropped_out/seed23/x32/apex", np.array(outs[3], dtype=np.float64))
+    put("cropped_out/seed23/x32/gx", xx.grad)
+    # ... and with a caller-supplied fractional apex (models/IRN_model.py:1569 passes one)
+    xx = x32.clone().requires_grad_(True)
+    outs = Crop().cropped_out(xx, apex=(0.125, 0.75, 0.25, 0.9375), min_rate=0.5)
+    (outs[0] * g32).sum().add((outs[1] * gz).sum()).backward()
+    put("cropped_out/apex/x32/scaled", outs[0])
+    put("cropped_out/apex/x32/zero_images", outs[1])
+    put("cropped_out/apex/x32/gx", xx.grad)
+    # cropped_for_outpainting (crop.py:57-76): pure slicing with two seeded rectangles
+    np.random.seed(25)
+    real_h = rand((2, 3, 32, 32), 26)
+    put("outpainting/real_H", real_h)
+    a, b, c = Crop().cropped_for_outpainting(x32, real_h)
+    put("outpainting/seed25/x32/new_images", a.contiguous())
+    put("outpainting/seed25/x32/zero_images", b.contiguous())
+    put("outpainting/seed25/x32/GT", c.contiguous())
+    # utils/compression.py + utils/decompression.py: size passed at CALL time (decompression.py:162)
+    from utils import compression as RC, decompression as RD
+    for rn, rf in roundings.items():
+        comp = RC.compress_jpeg(rounding=rf, factor=RJ.quality_to_factor(40))
+        dec = RD.decompress_jpeg(rounding=rf, factor=RJ.quality_to_factor(40))
+        cy, ccb, ccr = comp(x4832)
+        put(f"codec_calltime/q40/{rn}/x4832/coef_y", cy)
+        put(f"codec_calltime/q40/{rn}/x4832/coef_cb", ccb)
+        put(f"codec_calltime/q40/{rn}/x4832/coef_cr", ccr)
+        put(f"codec_calltime/q40/{rn}/x4832/y", dec(cy, ccb, ccr, 48, 32).contiguous())
+    # Fourier-series rounding surrogate (utils/JPEG_utils.py:36-41) through DiffJPEG
+    from utils import JPEG_utils as RU
+    m = RJ.DiffJPEG(True, 32, 32, quality=50, rounding=RU.diff_round)
+    for xn, x in (("x32", x32), ("xs32", xs32)):
+        y, gx = fwd_bwd(m, x, g32)
+        put(f"diffjpeg/q50/fourier/{xn}/y", y.contiguous())
+        put(f"diffjpeg/q50/fourier/{xn}/gx", gx)
+
     np.savez_compressed(args.out, **G)
     print(f"wrote {args.out}: {len(G)} arrays, {os.path.getsize(args.out) / 1e6:.2f} MB")
 

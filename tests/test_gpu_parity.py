@@ -5,10 +5,16 @@ plus size-independent properties at BASELINE.json's full sizes.
 
 Tolerances (north star): pixels and gradients <= 1e-5 max-abs in fp32; integer-valued
 quantised coefficients bit-exact except on fp64-verified rounding ties; selection / where-type
-layers bit-exact.  Gradients of the |q| < 1/2 surrogate are discontinuous at |q| = 1/2: a
-coefficient within fp32 noise of the break flips branch in ANY fp32 implementation (the
-reference's own fp32 gradients differ from fp64 by up to 2.5e-5 at quality 95, see
-tests/test_oracle_golden.py), so those cases use the stated wider bound plus a <0.1% outlier cap.
+layers bit-exact.
+
+No test here allows a FRACTION of wrong elements.  Where the arithmetic has a step (a rounding
+quantiser, the |q| < 1/2 switch of round_only_at_0, a clamp's pass-through mask) a value within fp32
+noise of the step may land on either side in ANY fp32 implementation; tests/parity_util.py builds, from
+the fp64 oracle's pre-round / pre-clamp values, the set of such FRAGILE positions and their influence
+region, and every element outside that region must meet the bound: every mismatch is counted and explained.
+Above the BASELINE quality (q > 50) the quantisation steps shrink and fp32 rounding of the level-shifted
+DCT input is amplified into the gradient; there the bound is calibrated per case against the SAME formulas
+evaluated by torch in fp32 on the CPU (`fp32_noise`): ours must stay within 2x that, never a hand-set table.
 """
 import numpy as np
 import pytest
@@ -17,6 +23,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import attack_oracle as O  # noqa: E402
+from tests import parity_util as P  # noqa: E402
 from tests.golden_util import GOLD, T, text  # noqa: E402
 
 import wmattack  # noqa: E402
@@ -48,17 +55,29 @@ def oracle_fwd_bwd(fn, x, g):
     return y.detach(), xx.grad.detach()
 
 
-def grad_tol(q, mode=0):
-    """Max-abs gradient bound vs the fp64 oracle.  1e-5 at the BASELINE quality (<= 50).  Above it
-    the quantisation step table*factor shrinks, q = C/(table*factor) amplifies the ~1e-5 absolute
-    fp32 rounding of the level-shifted DCT input (ulp(128) = 1.5e-5), and d(round)/dq = 3q^2 or
-    3(q - rint q)^2 inherits it: the SAME formulas evaluated by torch in fp32 on the CPU are off by
-    4e-6 / 2e-5 (round_only_at_0, q75 / q95) and 9e-6 / 6e-5 (cubic) on these inputs."""
-    if q <= 50:
-        return 1e-5
-    if mode == 1:
-        return 3e-5 if q <= 75 else 2e-4
-    return 2e-5 if q <= 75 else 1e-4
+def grad_tol(q, fn=None, x=None, g=None, influence=None):
+    """Max-abs gradient bound vs the fp64 oracle: the north star's 1e-5 at the BASELINE quality and below.
+    Above it the bound scales with the inverse of the smallest quantisation step: q = C / (table * factor), the
+    luminance table's minimum is 10 (utils/JPEG.py:98-104), so at quality 50 (factor 1) the ~1e-5..1e-4 absolute
+    fp32 rounding of a level-shifted DCT coefficient (|C| <= 1024, ulp 6e-5) is divided by >= 10; at factor f < 1 it
+    is divided by 10 f only, and d round'(q)/dq <= 3 passes it on to the gradient: bound = 1e-5 / factor
+    (2e-5 at quality 75, 1e-4 at quality 95).  When the oracle callable is given, the bound is cross-checked
+    against the SAME formulas evaluated by torch in fp32 on the CPU: that implementation's own distance to fp64
+    must fit under it too (the bound describes fp32, not our kernel)."""
+    tol = 1e-5 * max(1.0, 1.0 / O.quality_to_factor(q))
+    if fn is not None and q > 50:
+        _, dg = P.fp32_noise(fn, x, g)
+        if influence is not None:
+            dg = dg[~influence]
+        assert (float(dg.max()) if dg.numel() else 0.0) <= tol, "torch's own fp32 evaluation exceeds the fp32 bound"
+    return tol
+
+
+def coord_tol(h, w, r, base):
+    """Bound for a resize GRADIENT against a comparator that evaluates source coordinates differently (fp64 oracle,
+    or torch on another device): ATen computes scale * (o + 0.5) - 0.5 in fp32, so tap weights carry an error of
+    ~ulp(coordinate) that differs between correct fp32 builds (FMA contraction): base + 2 * ulp(largest coordinate)."""
+    return base + 2 * 2.0 ** (np.floor(np.log2(max(h, w) * max(1.0, 1.0 / r))) - 23)
 
 
 # =============================================================================== DiffJPEG
@@ -69,19 +88,22 @@ DJ_CASES = [(q, rn, xn) for q in (10, 50, 75, 95) for rn in ROUND for xn in ("x3
 @pytest.mark.parametrize("q,rn,xn", DJ_CASES)
 def test_diffjpeg_vs_golden(q, rn, xn):
     m = wmattack.DiffJPEG(True, 32, 32, quality=q, rounding=ROUND[rn])
-    y, gx = fwd_bwd(m, T(xn), T("g32"))
+    x, g = T(xn), T("g32")
+    y, gx = fwd_bwd(m, x, g)
     yref, gref = T(f"diffjpeg/q{q}/{rn}/{xn}/y"), T(f"diffjpeg/q{q}/{rn}/{xn}/gx")
+    infl, n_fragile = P.diffjpeg_influence(x, O.quality_to_factor(q), ROUND[rn])
+    assert n_fragile <= 2                                     # the fixtures hold (almost) no rounding ties
+    P.assert_explained(y, yref, 1e-5, infl, "y vs reference")
     if rn == "hard":
-        # a rounding tie that flips moves one coefficient by a whole step: allow isolated blocks
-        bad = (y - yref).abs() > 1e-5
-        assert float(bad.float().mean()) < 0.02
-        assert md(gx, gref) == 0.0
-    else:
-        assert md(y, yref) <= 1e-5
-        # the golden gradient is the reference's own fp32 result: its distance to the fp64 oracle
-        # (2e-5; 5e-5 at q95, tests/test_oracle_golden.py) adds to ours (test_diffjpeg_vs_oracle)
-        err = (gx - gref).abs()
-        assert float(err.max()) <= grad_tol(q, ROUND[rn]) + (5e-5 if q == 95 else 2e-5)
+        assert md(gx, gref) == 0.0                            # torch.round: zero gradient, exactly
+        return
+    # the golden gradient is the reference's own fp32 result: ITS distance to the fp64 oracle (measured here) adds to ours
+    fn = lambda t: O.diffjpeg(t, q, ROUND[rn])
+    _, go = oracle_fwd_bwd(fn, x, g)
+    P.assert_explained(gx, go, grad_tol(q, fn, x, g, infl), infl, "gx vs fp64 oracle")
+    ref_err = float((gref.double() - go).abs()[~infl].max())
+    tol = grad_tol(q, fn, x, g, infl) + ref_err
+    P.assert_explained(gx, gref, tol, infl, "gx vs reference")
 
 
 @pytest.mark.parametrize("shape", [(1, 16, 16), (3, 64, 96), (5, 48, 272), (2, 128, 128)])
@@ -90,20 +112,38 @@ def test_diffjpeg_vs_golden(q, rn, xn):
 def test_diffjpeg_vs_oracle(shape, q, mode):
     b, h, w = shape
     x, g = rnd((b, 3, h, w), 100 + h + q), rnd((b, 3, h, w), 200 + w + q)
-    if mode == 3 and (q != 50 or b > 2):
-        pytest.skip("Fourier rounding (utils/JPEG_utils.py) checked on a subset")
     m = wmattack.DiffJPEG(True, h, w, quality=q, rounding=mode)
     y, gx = fwd_bwd(m, x, g)
-    yo, go = oracle_fwd_bwd(lambda t: O.diffjpeg(t, q, mode), x, g)
-    tol_y = 1e-5 if mode != 3 else 5e-5
-    assert md(y, yo) <= tol_y
-    err = (gx.double() - go).abs()
-    if mode == 3:       # 9-term Fourier surrogate: |gx| reaches ~20, compare relatively
+    fn = lambda t: O.diffjpeg(t, q, mode)
+    yo, go = oracle_fwd_bwd(fn, x, g)
+    infl, n_fragile = P.diffjpeg_influence(x, O.quality_to_factor(q), mode)
+    assert n_fragile <= 1e-3 * x.numel() + 2                  # fragile coefficients are rare on random input
+    if mode == 3:
+        # 9-term Fourier surrogate (utils/JPEG_utils.py:36): smooth, but its derivative reaches ~19 and its second
+        # derivative ~2*pi*sum(n) = 280, so fp32 noise in q shows up amplified: bound = 2x the oracle's own fp32 noise
+        # (argument 2*pi*n*q in fp32): bound = 1e-3 of the gradient's range, and torch's own fp32 evaluation of the
+        # same series must sit in the same band (the bound describes fp32, not our kernel)
+        dy, dg = P.fp32_noise(fn, x, g)
         scale = max(1.0, float(go.abs().max()))
-        assert float(err.max()) <= 1e-3 * scale and float((err > 1e-4 * scale).float().mean()) < 0.05
-    else:
-        assert float(err.max()) <= grad_tol(q, mode)
-        assert float((err > grad_tol(q, mode) / 2).float().mean()) < 3e-2
+        assert md(y, yo) <= 5e-5 and float(dy.max()) <= 5e-5
+        assert md(gx, go) <= 1e-3 * scale and float(dg.max()) <= 1e-3 * scale
+        assert md(gx, go) <= 4 * float(dg.max()) + 1e-5                       # same order as torch's fp32 result
+        return
+    P.assert_explained(y, yo, 1e-5, infl, "y")
+    P.assert_explained(gx, go, grad_tol(q, fn, x, g, infl), infl, "gx")
+
+
+def test_diffjpeg_fourier_vs_golden():
+    """utils/JPEG_utils.py:36-41 diff_round (9-term Fourier series) through the reference's own DiffJPEG."""
+    m = wmattack.DiffJPEG(True, 32, 32, quality=50, rounding=3)
+    for xn in ("x32", "xs32"):
+        x, g = T(xn), T("g32")
+        y, gx = fwd_bwd(m, x, g)
+        fn = lambda t: O.diffjpeg(t, 50, 3)
+        gref = T(f"diffjpeg/q50/fourier/{xn}/gx")
+        assert md(y, T(f"diffjpeg/q50/fourier/{xn}/y")) <= 5e-5
+        # both the reference's fp32 gradient and ours sit within 1e-3 of the gradient's range of fp64 (see above)
+        assert md(gx, gref) <= 2e-3 * max(1.0, float(gref.abs().max()))
 
 
 def test_diffjpeg_nonsquare_saturated_and_name():
@@ -213,10 +253,12 @@ def test_diffjpeg_full_size_properties():
         assert torch.equal(crop.grad, xx.grad[bi:bi + 1, :, r0:r0 + hh, c0:c0 + ww])
     # spot-check a random subset of images against the fp64 oracle
     for bi in (3, 40):
-        yo, go = oracle_fwd_bwd(lambda t: O.diffjpeg(t, 50), x[bi:bi + 1].cpu(), g[bi:bi + 1].cpu())
-        assert md(y[bi:bi + 1], yo) <= 1e-5
-        err = (xx.grad[bi:bi + 1].cpu().double() - go).abs()
-        assert float(err.max()) <= 2e-5 and float((err > 1e-5).float().mean()) < 1e-4
+        xi, gi = x[bi:bi + 1].cpu(), g[bi:bi + 1].cpu()
+        yo, go = oracle_fwd_bwd(lambda t: O.diffjpeg(t, 50), xi, gi)
+        infl, n_fragile = P.diffjpeg_influence(xi, 1.0, 0)
+        assert n_fragile <= 1e-4 * xi.numel()
+        P.assert_explained(y[bi:bi + 1], yo, 1e-5, infl, "y")
+        P.assert_explained(xx.grad[bi:bi + 1], go, 1e-5, infl, "gx")
     # determinism
     assert torch.equal(m(x), y.detach())
 
@@ -231,18 +273,27 @@ J8 = {"jpeg": ("Jpeg", O.JPEG8_HARD), "jpegss": ("JpegSS", O.JPEG8_SS), "jpegmas
 @pytest.mark.parametrize("xn,gn", (("x20", "g20"), ("xs32", "g32")))
 def test_jpeg8_vs_golden(cn, q, sub, xn, gn):
     m = getattr(wmattack, J8[cn][0])(q, subsample=sub)
-    y, gx = fwd_bwd(m, T(xn), T(gn))
+    x, g = T(xn), T(gn)
+    y, gx = fwd_bwd(m, x, g)
     ref = T(f"{cn}/q{q}/s{sub}/{xn}/y")
+    if cn == "jpegmask":                                       # linear: no step anywhere
+        assert md(y, ref) <= 1e-5 and md(gx, T(f"{cn}/q{q}/s{sub}/{xn}/gx")) <= 1e-5
+        return
+    mode = O.ROUND_HARD if cn == "jpeg" else O.ROUND_ONLY_AT_0
+    infl, n_fragile = P.jpeg8_influence(x, q, mode, sub)
+    assert n_fragile <= 2
+    P.assert_explained(y, ref, 1e-5, infl, "y vs reference")
     if cn == "jpeg":
-        bad = (y - ref).abs() > 1e-5
-        assert float(bad.float().mean()) < 0.02
         assert float(gx.abs().max()) == 0.0
-    else:
-        assert md(y, ref) <= 1e-5
-        # golden = the reference's own fp32 gradient (off by up to 2e-5 from fp64 for JpegSS)
-        err = (gx - T(f"{cn}/q{q}/s{sub}/{xn}/gx")).abs()
-        assert float(err.max()) <= (1e-5 if cn == "jpegmask" else 1e-4)
-        assert float((err > 5e-5).float().mean()) < 1e-3
+        return
+    # golden = the reference's own fp32 gradient: ITS distance to the fp64 oracle (measured here) adds to ours
+    fn = lambda t: O.jpeg8(t, q, J8[cn][1], sub)
+    _, go = oracle_fwd_bwd(fn, x, g)
+    gref = T(f"{cn}/q{q}/s{sub}/{xn}/gx")
+    P.assert_explained(gx, go, grad_tol(q, fn, x, g, infl), infl, "gx vs fp64 oracle")
+    tol = grad_tol(q, fn, x, g, infl) + float((gref.double() - go).abs()[~infl].max())
+    P.assert_explained(gx, gref, tol, infl, "gx vs reference")
+    assert tol <= 1e-4
 
 
 @pytest.mark.parametrize("cn", list(J8))
@@ -255,15 +306,19 @@ def test_jpeg8_vs_oracle_any_shape(cn, shape, sub):
     q = 50
     m = getattr(wmattack, J8[cn][0])(q, subsample=sub)
     y, gx = fwd_bwd(m, x, g)
+    if cn == "jpegmask":
+        yo, go = oracle_fwd_bwd(lambda t: O.jpeg8(t, q, J8[cn][1], sub), x, g)
+        assert md(y, yo) <= 1e-5 and md(gx, go) <= 1e-5
+        return
+    mode = O.ROUND_HARD if cn == "jpeg" else O.ROUND_ONLY_AT_0
+    infl, n_fragile = P.jpeg8_influence(x, q, mode, sub)
+    assert n_fragile <= 1e-4 * x.numel() + 2
     if cn == "jpeg":
-        yo = O.jpeg8(x.double(), q, J8[cn][1], sub)
-        assert float(((y.double() - yo).abs() > 1e-5).float().mean()) < 0.02
+        P.assert_explained(y, O.jpeg8(x.double(), q, J8[cn][1], sub), 1e-5, infl, "y")
         return
     yo, go = oracle_fwd_bwd(lambda t: O.jpeg8(t, q, J8[cn][1], sub), x, g)
-    assert md(y, yo) <= 1e-5
-    err = (gx.double() - go).abs()
-    assert float(err.max()) <= (1e-5 if cn == "jpegmask" else 5e-5)
-    assert float((err > 1e-5).float().mean()) < 1e-3
+    P.assert_explained(y, yo, 1e-5, infl, "y")
+    P.assert_explained(gx, go, 1e-5, infl, "gx")
 
 
 def test_jpeg8_quantised_integers():
@@ -459,13 +514,24 @@ def test_resize_vs_golden(mode, r):
     assert m.name == "Resize"
 
 
+def _assert_resize_grad(gx, g_ref, x, ratio, mode, tol, what, mid=None):
+    """Resize gradient check: every mismatch must lie in the support of the transposed round-trip operator
+    applied to the clamp-FRAGILE outputs (fp64 pre-clamp value within 1e-5 of 0 or 1)."""
+    h, w = x.shape[2:]
+    mid = mid or O.resize_mid_size(h, w, ratio)
+    infl, n_fragile, _ = P.resize_grad_influence(x, mid, mode)
+    P.assert_explained(gx, g_ref, tol, infl, what)
+    return n_fragile
+
+
 def test_resize_saturated_random_ratio_and_large():
     m = wmattack.Resize()
     y, gx = fwd_bwd(lambda t: m(t, resize_ratio=0.8), T("xsat"), T("g32"))
     assert md(y, T("resize/bicubic/r0.8/xsat/y")) <= 1e-5
-    yref = T("resize/bicubic/r0.8/xsat/y")
-    err = (gx - T("resize/bicubic/r0.8/xsat/gx")).abs()
-    assert float((err > 1e-5).float().mean()) < 5e-3        # clamp-boundary flips only
+    # binary input: the bicubic round trip overshoots [0,1] almost everywhere, so the clamp mask decides most of the
+    # gradient; no pre-clamp value of this fixture is within 1e-5 of a bound, hence NO mismatch is tolerated
+    n = _assert_resize_grad(gx, T("resize/bicubic/r0.8/xsat/gx"), T("xsat"), 0.8, "bicubic", 1e-5, "xsat gx vs reference")
+    assert n == 0
     np.random.seed(17)
     assert md(m(T("x32").to(DEV)), T("resize/random/x32/y")) <= 1e-5
     # larger, non-square, against torch's own fp32 CPU interpolate (the reference's op)
@@ -480,8 +546,8 @@ def test_resize_saturated_random_ratio_and_large():
     y, gx = fwd_bwd(lambda t: m(t, resize_ratio=0.77), x, g)
     yo, go = oracle_fwd_bwd(lambda t: O.resize(t, 0.77), x, g)
     assert md(y, yo) <= 2e-5
-    err = (gx.double() - go).abs()
-    assert float((err > 2e-5).float().mean()) < 2e-3
+    n = _assert_resize_grad(gx, go, x, 0.77, "bicubic", coord_tol(96, 160, 0.77, 1e-5), "gx vs fp64 oracle")
+    assert n <= 1e-3 * x.numel()
 
 
 def test_interp_untiled_fallback_scales():
@@ -493,7 +559,7 @@ def test_interp_untiled_fallback_scales():
             y, gx = fwd_bwd(lambda t: m(t, resize_ratio=r), x, g)
             yo, go = oracle_fwd_bwd(lambda t: O.resize(t, r, mode), x, g)
             assert md(y, yo) <= 1e-5
-            assert float(((gx.double() - go).abs() > 2e-5).float().mean()) < 5e-3
+            _assert_resize_grad(gx, go, x, r, mode, coord_tol(40, 56, r, 1e-5), f"untiled r={r} {mode}")
     y, apex = wmattack.Crop()(x.to(DEV), apex=(4, 14, 6, 20))          # 4x upsampling
     assert md(y, O.crop_resize(x.double(), (4, 14, 6, 20))) <= 1e-5
     xx = x.to(DEV).requires_grad_(True)
@@ -694,7 +760,10 @@ def test_stencils_and_resize_on_clip_slices():
             y.backward(g.to(DEV))
             yo, go = oracle_fwd_bwd(ref, xs.contiguous(), g)
             assert md(y, yo) <= 2e-5
-            assert float(((xx.grad.cpu().double() - go).abs() > 2e-5).float().mean()) < 2e-3
+            if layer.__class__.__name__ == "function":                  # the Resize lambda: clamp mask
+                _assert_resize_grad(xx.grad, go, xs.contiguous(), 0.8, "bicubic", coord_tol(48, 160, 0.8, 1e-5), "clip slice resize gx")
+            else:
+                assert md(xx.grad, go) <= 2e-5
     assert _resize_tables_overflow() == 0
 
 
@@ -723,15 +792,9 @@ def test_fused_resize_geometry_sweep(mode):
                 yo = pre.clamp(0, 1)
                 yo.backward(g.to(dev))
                 assert md(y, yo) <= tol_y, (h, w, r, dev)
-                # gradient: where a pre-clamp value is within fp32 noise of a clamp bound the
-                # pass-through decision of ANY fp32 implementation is arbitrary: bound the fraction
-                pd = pre.detach()
-                frag = bool(((pd.abs() < tol_y) | ((pd - 1).abs() < tol_y)).any())
-                err = (xx.grad.cpu().double() - xo.grad.cpu().double()).abs()
-                if not frag:
-                    assert float(err.max()) <= tol_g, (h, w, r, dev)
-                else:
-                    assert float((err > tol_g).float().mean()) < 5e-3, (h, w, r, dev)
+                # gradient: where the fp64 pre-clamp value is within fp32 noise of a clamp bound the pass-through
+                # decision of ANY fp32 implementation is arbitrary: every mismatch must trace back to such an output
+                _assert_resize_grad(xx.grad, xo.grad, x, r, mode, tol_g, f"{(h, w, r, dev)}", mid=mid)
     assert _resize_tables_overflow() == 0
 
 
@@ -772,9 +835,12 @@ def test_diffjpeg_4k_quality_sweep_mcu_independence():
             xc = x[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double().requires_grad_(True)
             yo = O.diffjpeg(xc, q)
             yo.backward(g[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double())
-            assert md(y[:, :, r0:r0 + 64, c0:c0 + 96], yo) <= 1e-5
-            err = (xx.grad[:, :, r0:r0 + 64, c0:c0 + 96].cpu().double() - xc.grad).abs()
-            assert float((err > grad_tol(q)).float().mean()) < 1e-3
+            xcrop, gcrop = x[:, :, r0:r0 + 64, c0:c0 + 96].cpu(), g[:, :, r0:r0 + 64, c0:c0 + 96].cpu()
+            infl, n_fragile = P.diffjpeg_influence(xcrop, O.quality_to_factor(q), 0)
+            assert n_fragile <= 1e-3 * xcrop.numel() + 2
+            P.assert_explained(y[:, :, r0:r0 + 64, c0:c0 + 96], yo, 1e-5, infl, "4K y")
+            tol = grad_tol(q, lambda t: O.diffjpeg(t, q), xcrop, gcrop, infl)
+            P.assert_explained(xx.grad[:, :, r0:r0 + 64, c0:c0 + 96], xc.grad, tol, infl, "4K gx")
 
 
 # ======================================================= SURVEY 8f "next" rows: epilogue, bank, splice
@@ -1247,3 +1313,122 @@ def test_quantization_bit_exact_on_boundary_values():
     ref = torch.round((wc + (wc - wc)) * 255.0) / 255.0                           # straight-through form: inf -> nan
     o = out.cpu()
     assert bool(((o == ref) | (torch.isnan(o) & torch.isnan(ref))).all())
+
+
+# ================================================================ round 2: gaps named by the round-1 review
+def _cropped_out_influence(x, box, eps=1e-5):
+    """Influence region (on the input gradient) of the two clamps of Crop.cropped_out (crop.py:96-107):
+    only `scaled_images` = clamp(bicubic_up(crop)) carries gradient (the scaled-back term is detached)."""
+    h0, h1, w0, w1 = box
+    hh, ww = x.shape[2:]
+    x64 = x.double()
+    pre = O.interpolate(x64[:, :, h0:h1, w0:w1], (hh, ww), "bicubic")
+    fr = P.clamp_fragile(pre, eps)
+    a_h, a_w = O.interp_matrix(h1 - h0, hh, "bicubic"), O.interp_matrix(w1 - w0, ww, "bicubic")
+    infl = torch.zeros(x.shape, dtype=torch.bool)
+    infl[:, :, h0:h1, w0:w1] = P.interp_influence(fr, a_h, a_w)
+    return infl, int(fr.sum())
+
+
+def test_cropped_out_values_and_gradients_vs_reference():
+    """Crop.cropped_out (noise_layers/crop.py:78-118): all five outputs and the gradient of BOTH differentiable
+    outputs (scaled_images through bicubic + clamp, zero_images through the paste; the dual-reshape term is
+    detached upstream) against the reference's own autograd — seeded rectangle and caller-supplied fractional apex."""
+    x, g, gz = T("x32"), T("g32"), T("cropped_out/seed23/gz")
+    for key, kw in (("seed23", dict(min_rate=0.5)), ("apex", dict(apex=(0.125, 0.75, 0.25, 0.9375), min_rate=0.5))):
+        np.random.seed(23)
+        xx = x.to(DEV).requires_grad_(True)
+        outs = wmattack.Crop().cropped_out(xx, **kw)
+        ((outs[0] * g.to(DEV)).sum() + (outs[1] * gz.to(DEV)).sum()).backward()
+        assert md(outs[0], T(f"cropped_out/{key}/x32/scaled")) <= 1e-5
+        assert md(outs[1], T(f"cropped_out/{key}/x32/zero_images")) <= 1e-5
+        if key == "seed23":
+            assert np.allclose(np.array(outs[3]), GOLD["cropped_out/seed23/x32/apex"])
+        box = tuple(int(round(v * 32)) for v in outs[3])
+        infl, n_fragile = _cropped_out_influence(x, box)
+        assert n_fragile <= 8
+        P.assert_explained(xx.grad, T(f"cropped_out/{key}/x32/gx"), 1e-5, infl, f"cropped_out[{key}] gx")
+        assert float(xx.grad.abs().max()) > 0
+
+
+def test_cropped_for_outpainting_vs_reference():
+    """Crop.cropped_for_outpainting (crop.py:57-76): pure slicing with two seeded rectangles — bit-exact,
+    and the same two rectangles drawn from the same RNG calls."""
+    x, real_h = T("x32"), T("outpainting/real_H")
+    np.random.seed(25)
+    a, b, c = wmattack.Crop().cropped_for_outpainting(x.to(DEV), real_h.to(DEV))
+    assert torch.equal(a.cpu(), T("outpainting/seed25/x32/new_images"))
+    assert torch.equal(b.cpu(), T("outpainting/seed25/x32/zero_images"))
+    assert torch.equal(c.cpu(), T("outpainting/seed25/x32/GT"))
+    xx = x.to(DEV).requires_grad_(True)
+    np.random.seed(25)
+    a, b, c = wmattack.Crop().cropped_for_outpainting(xx, real_h.to(DEV))
+    (a.sum() + 2 * b.sum()).backward()                       # slices: gradient is an indicator sum
+    ref = x.clone().requires_grad_(True)
+    np.random.seed(25)
+    ra = GOLD["outpainting/seed25/x32/new_images"].shape
+    assert tuple(a.shape) == tuple(ra) and float(xx.grad.max()) in (1.0, 2.0, 3.0)
+
+
+@pytest.mark.parametrize("rn", list(ROUND))
+def test_codec_modules_with_call_time_size(rn):
+    """utils/compression.py:147 compress_jpeg + utils/decompression.py:140-190 decompress_jpeg whose forward takes
+    (y, cb, cr, height, width) at CALL time — non-square 48x32 frame, quality 40, all three rounding functions."""
+    x = T("x4832")
+    f = wmattack.quality_to_factor(40)
+    comp = wmattack.compress_jpeg(rounding=ROUND[rn], factor=f)
+    dec = wmattack.decompress_jpeg(rounding=ROUND[rn], factor=f)            # no size at construction
+    cy, ccb, ccr = comp(x.to(DEV))
+    refs = [T(f"codec_calltime/q40/{rn}/x4832/coef_{k}") for k in ("y", "cb", "cr")]
+    for got, ref in zip((cy, ccb, ccr), refs):
+        assert tuple(got.shape) == tuple(ref.shape)
+        if rn == "hard":
+            assert torch.equal(got.cpu(), ref)                              # integers: bit-exact (no tie in this fixture)
+        else:
+            assert md(got, ref) <= 2e-4                                     # coefficients are O(100): 1e-6 relative
+    y = dec(cy, ccb, ccr, 48, 32)
+    assert md(y, T(f"codec_calltime/q40/{rn}/x4832/y")) <= 1e-5
+    # the reference's own coefficients through our decompress: isolates the decoder half
+    y2 = dec(*[r.to(DEV) for r in refs], 48, 32)
+    assert md(y2, T(f"codec_calltime/q40/{rn}/x4832/y")) <= 1e-5
+    with pytest.raises(ValueError):
+        dec(cy, ccb, ccr, 32, 48 + 16)                                       # size that does not match the coefficients
+
+
+def test_rounding_ties_are_counted_not_excused():
+    """A constructed worst case for the fragile-set logic: flat gray 129/255 puts EVERY luminance DC quotient at
+    8*(129-128)/16 = 0.5 (+- fp32 noise of the colour matrix), a torch.round tie.  The fp64 oracle flags exactly those
+    coefficients; our integer coefficients may differ from the oracle's by one step there and nowhere else."""
+    x = torch.full((1, 3, 32, 32), 129.0 / 255.0)
+    x[:, :, 16:, :] = rnd((1, 3, 16, 32), 5)                               # lower half: ordinary content
+    m = wmattack.DiffJPEG(True, 32, 32, quality=50, rounding=2)
+    cy, ccb, ccr = m.compress(x.to(DEV))
+    qy, qcb, qcr = O.diffjpeg_compress(x.double(), 1.0, O.ROUND_NONE)
+    ty, tc = O.diffjpeg_tables(1.0)
+    fy = P.fragile_quotients(qy, ty, O.ROUND_HARD)
+    assert int(fy.sum()) == 8 and bool(fy[0, :8, 0, 0].all())              # the 8 DC terms of the flat half, only those
+    dy = (cy.cpu().double() - torch.round(qy)).abs()
+    assert float(dy[~fy].max()) == 0.0 and float(dy[fy].max()) <= 1.0
+    for got, q in ((ccb, qcb), (ccr, qcr)):
+        fr = P.fragile_quotients(q, tc, O.ROUND_HARD)
+        d = (got.cpu().double() - torch.round(q)).abs()
+        assert float(d[~fr].max()) == 0.0 and float(d.max()) <= 1.0
+    # and the pixel-level influence region covers exactly the flat half's luminance blocks
+    infl, n = P.diffjpeg_influence(x, 1.0, O.ROUND_HARD)
+    assert bool(infl[:, :, :16].all()) and n >= 8
+    y = m(x.to(DEV))
+    P.assert_explained(y, O.diffjpeg(x.double(), 50, O.ROUND_HARD), 1e-5, infl, "tie image")
+
+
+def test_crop_rejects_or_clamps_out_of_range_rectangles():
+    """A caller-supplied apex is clamped like the reference's slicing (image[:, :, a:b, c:d]); a window handed to
+    the functional layer directly must lie inside the source (the kernels read it in place)."""
+    x = rnd((1, 3, 32, 48), 3).to(DEV)
+    y, apex = wmattack.Crop()(x, apex=(8, 40, 10, 60))                      # h_end, w_end beyond the frame
+    ref = torch.nn.functional.interpolate(x[:, :, 8:40, 10:60], size=[32, 48], mode="bilinear")
+    assert md(y, ref) <= 2e-6 and apex == (8, 40, 10, 60)
+    with pytest.raises(ValueError):
+        wmattack.Crop()(x, apex=(20, 10, 0, 48))                            # empty rectangle
+    for bad in ((-1, 0, 8, 8), (0, 0, 33, 8), (30, 40, 8, 9), (0, 0, 0, 8)):
+        with pytest.raises(ValueError):
+            WF.interpolate(x, (32, 48), "bilinear", window=bad)

@@ -716,7 +716,24 @@ def interpolate(x, size, mode: str = "bilinear", window=None, clamp: bool = Fals
     h, w = x.shape[2:]
     if window is None:
         window = (0, 0, h, w)
-    return _InterpFn.apply(x, tuple(int(v) for v in window), (int(size[0]), int(size[1])), _MODES[mode], clamp)
+    h0, w0, hin, win = (int(v) for v in window)
+    if h0 < 0 or w0 < 0 or hin <= 0 or win <= 0 or h0 + hin > h or w0 + win > w:
+        # the kernels read the window in place: an out-of-range rectangle would be an out-of-bounds device read
+        raise ValueError(f"interpolate: window (h0={h0}, w0={w0}, h={hin}, w={win}) does not lie inside the "
+                         f"{h}x{w} source (use slice_window() for Python-slice clamping)")
+    return _InterpFn.apply(x, (h0, w0, hin, win), (int(size[0]), int(size[1])), _MODES[mode], clamp)
+
+
+def slice_window(shape, h_start, h_end, w_start, w_end):
+    """(h0, w0, hin, win) of image[:, :, h_start:h_end, w_start:w_end] with Python's slice semantics
+    (silent clamping, negative indices) — what the reference's slicing does with a caller-supplied apex
+    (noise_layers/crop.py:45, models/IRNcrop_model.py:541-543 reuses one apex across tensors)."""
+    h0, h1, _ = slice(int(h_start), int(h_end)).indices(shape[2])
+    w0, w1, _ = slice(int(w_start), int(w_end)).indices(shape[3])
+    if h1 <= h0 or w1 <= w0:
+        raise ValueError(f"crop rectangle [{h_start}:{h_end}, {w_start}:{w_end}] is empty on a "
+                         f"{shape[2]}x{shape[3]} image")
+    return h0, w0, h1 - h0, w1 - w0
 
 
 _RESIZE_TABLES: dict = {}      # (device, H, W, Hm, Wm, mode) -> device tensor of band tables (tiny, LRU-capped)

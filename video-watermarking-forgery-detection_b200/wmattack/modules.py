@@ -582,7 +582,7 @@ class Crop(nn.Module):
             h_start, h_end, w_start, w_end = apex
         else:
             h_start, h_end, w_start, w_end = self.get_random_rectangle_inside(image.shape, self.height_ratio, self.width_ratio)
-        window = (h_start, w_start, h_end - h_start, w_end - w_start)
+        window = F_.slice_window(image.shape, h_start, h_end, w_start, w_end)     # clamps like image[:, :, a:b, c:d]
         scaled = F_.interpolate(image, image.shape[2:], "bilinear", window=window)   # crop.py:48-53
         return scaled, (h_start, h_end, w_start, w_end)
 
@@ -617,9 +617,9 @@ class Crop(nn.Module):
         mask = torch.ones_like(image)
         mask[:, :, h0:h1, w0:w1] = 0
         zero_images = image * (1 - mask)
-        window = (h0, w0, h1 - h0, w1 - w0)
+        window = F_.slice_window(image.shape, h0, h1, w0, w1)
         scaled_images = F_.interpolate(image, (H, W), "bicubic", window=window, clamp=True)
-        scaled_back = F_.interpolate(scaled_images, (h1 - h0, w1 - w0), "bicubic", clamp=True)
+        scaled_back = F_.interpolate(scaled_images, (window[2], window[3]), "bicubic", clamp=True)
         zero_images_gt = torch.zeros_like(image)
         zero_images_gt[:, :, h0:h1, w0:w1] = scaled_back
         dual_reshape_diff = (zero_images_gt - zero_images).clone().detach()
