@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WM_ABI_VERSION 1
+#define WM_ABI_VERSION 2
 
 #define WM_OK 0
 #define WM_E_NULL (-1)      /* required pointer is NULL */
@@ -44,6 +44,20 @@ extern "C" {
 int wm_version(void);
 const char* wm_last_error(void);
 
+/* Store epilogue (models/IRNp_model.py:674-680): an OPTIONAL argument of the forward entry
+ * points marked "ep" below.  When ep != NULL and ep->x != NULL the kernel writes
+ *     Quantization( x + (clamp(v, 0, 1) - x) )       [clamp only if clamp01, Quantization only if quantize]
+ * instead of its own value v, reading x (dense [B,C,H,W] in the layout of the output, 32-byte aligned) at the output
+ * position - no separate pass over the attacked batch, and `y` may be a slice of a K-way batch.  The struct lives in
+ * HOST memory and is copied into the launch.  A code path that cannot apply it fails with WM_E_ARG instead of
+ * silently ignoring it: wm_jpeg8_fwd (needs W % 8 == 0, aligned, subsample 0), wm_gaussblur (zero border,
+ * k in {3,5,7}, W % 4 == 0), wm_median_fwd (TMA paths), wm_resize_fwd, wm_diffjpeg_fwd, wm_gaussnoise_fwd. */
+typedef struct wm_store_epilogue {
+    const float* x;
+    int clamp01;
+    int quantize;
+} wm_store_epilogue;
+
 /* ------------------------------------------------------------------------------------------
  * DiffJPEG  —  utils/JPEG.py:501-540 (compress_jpeg :256-291, decompress_jpeg :431-469)
  *   x: [B,3,H,W] in [0,1], strides (x_sb, x_sc, x_sh) in elements, multiples of 8, base
@@ -53,7 +67,8 @@ const char* wm_last_error(void);
  * ------------------------------------------------------------------------------------------ */
 int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                     float* y, int B, int H, int W,
-                    float factor, const float* factor_per_sample, int rounding, void* stream);
+                    float factor, const float* factor_per_sample, int rounding,
+                    const wm_store_epilogue* ep, void* stream);
 
 /* gx = d<gy, DiffJPEG(x)>/dx, recomputed from x (nothing saved by the forward).
  * Replaces autograd over the ~30 saved activations of the reference graph. */
@@ -107,7 +122,8 @@ typedef struct wm_jpeg8_params {
 } wm_jpeg8_params;
 
 int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
-                 float* y, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+                 float* y, int B, int H, int W, const wm_jpeg8_params* params_host,
+                 const wm_store_epilogue* ep, void* stream);
 int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                  const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
                  float* gx, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
@@ -132,7 +148,8 @@ int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
  * it is the same filter.
  * ------------------------------------------------------------------------------------------ */
 int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
-                 const float* taps_host, int k, int border, int adjoint, void* stream);
+                 const float* taps_host, int k, int border, int adjoint,
+                 const wm_store_epilogue* ep, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * k x k median, zero padding, k in {3,5}  (MiddleBlur, noise_layers/middle_filter.py:5-13 ->
@@ -140,7 +157,7 @@ int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, in
  * the window of the FIRST element equal to the median; wm_median_bwd routes gy through it.
  * ------------------------------------------------------------------------------------------ */
 int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
-                  int N, int H, int W, int k, void* stream);
+                  int N, int H, int W, int k, const wm_store_epilogue* ep, void* stream);
 int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -159,7 +176,8 @@ int wm_rng_reserve(uint64_t* state, uint64_t* slot, uint64_t count, void* stream
 
 /* Gaussian (noise_layers/gaussian.py:10-17, clamp=1) and GN (noise_layers/gaussian_noise.py:13-16, clamp=0) */
 int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
-                      uint64_t seed, uint64_t offset, const float* inject, void* stream);
+                      uint64_t seed, uint64_t offset, const float* inject,
+                      const wm_store_epilogue* ep, void* stream);
 int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
                       int clamp, uint64_t seed, uint64_t offset, const float* inject, void* stream);
 /* Training pair of the clamped layer (Gaussian, noise_layers/gaussian.py:10-17): the forward also writes one
@@ -198,7 +216,8 @@ int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t pla
  * upsample_bilinear2d / upsample_bicubic2d A=-0.75) over N = B*C planes.
  *   mode 0 = bilinear, 1 = bicubic.  The source window (h0, w0, Hin, Win) addresses a crop of
  *   a [N, Hsrc, Wsrc] plane stack (plane stride x_sp, row stride x_sh) so that
- *   Crop (noise_layers/crop.py:48-53) needs no copy.  clamp01: clamp the result to [0,1]
+ *   Crop (noise_layers/crop.py:48-53) needs no copy; the window must lie inside the plane
+ *   (0 <= h0, h0 + Hin <= Hsrc, likewise for w: WM_E_SHAPE otherwise - it is read in place).  clamp01: clamp the result to [0,1]
  *   (Resize, noise_layers/resize.py:53); maskbits (optional, uint32 [N, Hout, ceil(Wout/32)])
  *   receives bit (ox & 31) of word (ox >> 5) = 1 where 0 <= pre-clamp value <= 1.
  * wm_interp_bwd is the exact transpose as a deterministic gather (no atomics): gx is the dense
@@ -207,7 +226,7 @@ int wm_cropout_fwd(const float* image, const float* cover, float* y, int64_t pla
  *   (torch.clamp backward).  workspace: device scratch of N*Hin*Wout floats, only needed when
  *   wm_interp_is_tiled(...) == 0 (scale factors outside [0.4, 2.2]).
  * ------------------------------------------------------------------------------------------ */
-int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0, int w0, int Hin, int Win,
+int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
                   float* y, int N, int Hout, int Wout, int mode, int clamp01,
                   uint32_t* maskbits, void* stream);
 int wm_interp_bwd(const float* gy, const float* pre, const uint32_t* maskbits, int N, int Hout, int Wout,
@@ -224,6 +243,10 @@ int wm_interp_is_tiled(int Hin, int Win, int Hout, int Wout, int N);
  * tables: device workspace of wm_resize_table_floats(H, W, Hm, Wm) floats filled once per
  *   geometry by wm_resize_tables (band starts + weights of the per-axis operators U*D and
  *   their transposes); it may be cached and shared by any number of fwd/bwd calls.
+ *   wm_resize_tables also PROVES the geometry: its last 4-byte word (index table_floats - 4, as int32) is 0
+ *   iff every band fits the kernel's register / shared-memory windows for both directions; a caller must
+ *   read it once per new geometry (after the stream reaches that point) and use wm_interp_fwd / wm_interp_bwd
+ *   twice when it is non-zero.
  * maskbits (optional, uint32 [N, H, ceil(W/128), 4], 16-byte aligned): word k of a (row, 128-column
  *   tile) holds in bit l the flag 0 <= pre-clamp value <= 1 of column 128*tile + 4*l + k.
  * wm_resize_bwd is the exact adjoint gx = D^T U^T (gy .* mask) (gy, gx dense), deterministic.
@@ -232,7 +255,7 @@ int wm_resize_is_fused(int H, int W, int Hm, int Wm, int N);
 int64_t wm_resize_table_floats(int H, int W, int Hm, int Wm);
 int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int mode, void* stream);
 int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
-                  int mode, uint32_t* maskbits, const float* tables, void* stream);
+                  int mode, uint32_t* maskbits, const float* tables, const wm_store_epilogue* ep, void* stream);
 int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
                   int mode, const float* tables, void* stream);
 
@@ -256,15 +279,27 @@ int wm_u8_to_unit_float(const uint8_t* src, float* dst, int64_t n, void* stream)
  * integer k of the Quantization layer's value k/255 (models/modules/Quantization.py:9), so that attacked
  * frames leave the device as bytes (4x less D2H traffic).  NaN -> 0. */
 int wm_unit_float_to_u8(const float* src, uint8_t* dst, int64_t n, void* stream);
-/* Store epilogue, fused: arms the epilogue above for the NEXT forward launch issued from the calling
- * host thread; that kernel then writes  Quantization( x + (clamp(v, 0, 1) - x) )  instead of its own
- * value v, reading x (dense [B,C,H,W] in the layout of the output, 32-byte aligned) at the output
- * position — no separate pass over the attacked batch.  Consumed (and cleared) by: wm_diffjpeg_fwd,
- * wm_jpeg8_fwd (W % 8 == 0, aligned, subsample 0), wm_gaussblur (zero border, k in {3,5,7}, W % 4 == 0),
- * wm_median_fwd (TMA paths), wm_gaussnoise_fwd, wm_resize_fwd.  Their other code paths fail with
- * WM_E_ARG instead of silently ignoring it.  x = NULL disarms; after a call that returned non-zero, disarm
- * explicitly (an argument check may have failed before the descriptor was consumed). */
-int wm_set_store_epilogue(const float* x, int clamp01, int quantize);
+/* Shared-read bank ("read the input tile once, emit K attacked variants"): the 3x3-neighbourhood
+ * members of a K-way attack bank computed from ONE staged tile of x, each finished by the epilogue above (with x = the
+ * input itself) and written into its own slice.  12 + 12 K' B/px instead of 24 K' for K' members.  Every slice is
+ * bit-identical to the member's own forward entry point called with the same store epilogue.
+ *   x: N planes [H, W] (plane stride x_sp, row stride x_sh; 16-byte aligned, strides multiples of 4), W % 4 == 0;
+ *   a NULL output pointer switches that member off; outputs are dense [N, H, W], 16-byte aligned.
+ *   y_blur     GaussianBlur(kernel_size=3) (noise_layers/gaussian_blur.py:53-56), zero padding, taps blur_taps
+ *   y_median   MiddleBlur(3) (noise_layers/middle_filter.py:11-13)
+ *   y_noise    Gaussian (noise_layers/gaussian.py:10-17): clamp01(x + mean + std * N(0,1)) if noise_clamp, Philox
+ *              (seed, offset) with the counter convention of wm_gaussnoise_fwd on the DENSE [N,H,W] element index
+ *   y_identity Identity (noise_layers/identity.py): the epilogue of x itself                                      */
+typedef struct wm_bank3_desc {
+    float* y_blur; float blur_taps[3];
+    float* y_median;
+    float* y_noise; float noise_mean, noise_std; int noise_clamp; uint64_t seed, offset;
+    float* y_identity;
+    int clamp01, quantize;
+} wm_bank3_desc;
+int wm_bank3_ok(int N, int H, int W);
+int wm_bank3_fwd(const float* x, int64_t x_sp, int64_t x_sh, int N, int H, int W,
+                 const wm_bank3_desc* desc_host, void* stream);
 int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                            void* stream);
 int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream);

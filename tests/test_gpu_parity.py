@@ -231,7 +231,7 @@ def test_diffjpeg_errors():
         wmattack.DiffJPEG(True, 32, 32, 50)(torch.rand(1, 1, 32, 32, device=DEV))
     from wmattack import _lib
     with pytest.raises(_lib.WMAttackError):
-        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None)
+        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
 
 
 def test_diffjpeg_full_size_properties():
@@ -723,7 +723,10 @@ def test_combined_matches_reference_choices():
 
 # ==================================================== round-1 additions: TMA stencils / fused resize
 def _resize_tables_overflow():
-    """1 if any fused-resize launch so far lost a band weight (window too small) — must stay 0."""
+    """1 if any fused-resize geometry used so far lost a band weight (window too small) — must stay 0.  Every
+    geometry is proven on a blank plane before it enters the cache (functional._resize_tables); one that does not
+    fit would be listed in _RESIZE_UNFUSED and served by the two-call path: the sweeps below must not produce any."""
+    assert not WF._RESIZE_UNFUSED, f"geometries outside the band bound: {sorted(WF._RESIZE_UNFUSED)[:5]}"
     return max((int(t[-4:].view(torch.int32)[0]) for t in WF._RESIZE_TABLES.values()), default=0)
 
 
@@ -968,7 +971,7 @@ def test_degenerate_shapes():
 
 def test_fused_store_epilogue_bank_is_bit_identical_to_the_unfused_bank():
     """The attack kernels applying clamp + straight-through + Quantization in their own stores
-    (wm_set_store_epilogue) must give exactly the values of: plain kernel, then the stand-alone
+    (the wm_store_epilogue argument of the forward entry points) must give exactly the values of: plain kernel, then the stand-alone
     epilogue kernel — for every layer that has a fused path, on aligned and ragged shapes."""
     import random
     for shape, seed in (((2, 3, 64, 96), 81), ((1, 3, 48, 132), 82), ((2, 3, 40, 56), 83)):
@@ -1432,3 +1435,115 @@ def test_crop_rejects_or_clamps_out_of_range_rectangles():
     for bad in ((-1, 0, 8, 8), (0, 0, 33, 8), (30, 40, 8, 9), (0, 0, 0, 8)):
         with pytest.raises(ValueError):
             WF.interpolate(x, (32, 48), "bilinear", window=bad)
+
+
+def test_nan_propagates_through_the_clamps_like_torch():
+    """torch.clamp / torch.min / torch.max propagate NaN; a saturating instruction returns 0.  A diverging encoder
+    must stay visible downstream: DiffJPEG's final clamp (per 16x16 MCU), quality = 100 (factor 0, NaN
+    upstream: utils/JPEG.py:229 divides by table * 0), the clamped Gaussian layer, Resize's clamp, the epilogue."""
+    x = rnd((1, 3, 32, 48), 1)
+    x[0, 1, 5, 20] = float("nan")
+    y = wmattack.DiffJPEG(True, 32, 48, quality=50)(x.to(DEV)).cpu()
+    assert bool(torch.isnan(y[:, :, 0:16, 16:32]).all())                     # the whole MCU, all channels
+    rest = y.clone(); rest[:, :, 0:16, 16:32] = 0
+    assert bool(torch.isfinite(rest).all())
+    y100 = wmattack.DiffJPEG(True, 32, 48, quality=100)(rnd((1, 3, 32, 48), 2).to(DEV))
+    assert bool(torch.isnan(y100).all())                                     # as upstream: 0 * inf
+    xg = x.to(DEV).requires_grad_(True)
+    yg = wmattack.Gaussian()(xg)
+    assert bool(torch.isnan(yg[0, 1, 5, 20])) and int(torch.isnan(yg).sum()) == 1
+    assert bool(torch.isnan(wmattack.Gaussian()(x.to(DEV))[0, 1, 5, 20]))     # no-grad kernel too
+    yr = wmattack.Resize()(x.to(DEV), resize_ratio=0.75)
+    ref = torch.clamp(torch.nn.functional.interpolate(torch.nn.functional.interpolate(x, size=[24, 36], mode="bicubic"),
+                                                      size=[32, 48], mode="bicubic"), 0, 1)
+    # the fused kernel applies the composite band U*D with zero-padded windows (0 * NaN = NaN), so its NaN footprint
+    # covers torch's two-pass footprint and may be a few columns / rows wider, never narrower
+    ours_nan, ref_nan = torch.isnan(yr).cpu(), torch.isnan(ref)
+    assert bool((ours_nan | ~ref_nan).all()) and int(ours_nan.sum()) <= 4 * int(ref_nan.sum())
+    assert bool(torch.isfinite(yr.cpu()[~ours_nan]).all())
+    out = wmattack.AttackEpilogue()(rnd((1, 3, 32, 48), 3).to(DEV), x.to(DEV))
+    assert bool(torch.isnan(out[0, 1, 5, 20])) and int(torch.isnan(out).sum()) == 1
+    q = wmattack.Quantization(clamp01=True)(x.to(DEV))
+    assert bool(torch.isnan(q[0, 1, 5, 20]))
+
+
+def test_jpegtest_consumes_the_reference_rng_stream():
+    """JpegTest draws one 16-character temp-file name per frame from python's `random` upstream (noise_layers/jpeg.py:
+    17-18, 32); ours consumes the same numbers, so seeded Combined choices after a JpegTest call stay aligned."""
+    import random
+    import string
+    x = (rnd((3, 3, 16, 16), 4) * 2 - 1).to(DEV)
+    random.seed(99)
+    wmattack.JpegTest(50)(x)
+    after = random.random()
+    random.seed(99)
+    for _ in range(3):
+        random.sample(string.ascii_letters + string.digits, 16)
+    assert after == random.random()
+
+
+def test_bank3_shared_read_is_bit_identical_and_reads_x_once():
+    """the 3x3-neighbourhood members of a bank (GaussianBlur(3), MiddleBlur(3), Gaussian, Identity) come
+    from ONE kernel that stages each tile of x once (wm_bank3_fwd).  Every slice must equal, bit for bit, the member's own
+    kernel with the store epilogue (shared_read=False) — ragged tiles, partial membership, duplicates, no clamp / no
+    quantisation — and the launch count must drop accordingly."""
+    import random
+    from wmattack import _lib
+    def members():
+        return [wmattack.GaussianBlur(), wmattack.Identity(), wmattack.JpegMask(50), wmattack.MiddleBlur(3), wmattack.Gaussian(),
+                wmattack.GaussianBlur(), wmattack.MiddleBlur(5)]          # second GaussianBlur(3): own kernel
+    for shape, seed, flags in (((2, 3, 64, 128), 1, (True, True)), ((1, 3, 70, 132), 2, (True, True)), ((3, 3, 33, 36), 3, (False, True)),
+                               ((1, 3, 130, 260), 4, (True, False)), ((2, 1, 17, 8), 5, (False, False))):
+        x = rnd(shape, seed) * 1.3 - 0.15
+        outs, launches = [], []
+        for shared in (True, False):
+            np.random.seed(5); random.seed(5); torch.manual_seed(5)
+            WF._rng_calls = 0
+            layers = members() if shape[1] == 3 else [wmattack.GaussianBlur(channels=1), wmattack.MiddleBlur(3), wmattack.Gaussian()]
+            bank = wmattack.AttackBank(layers, clamp=flags[0], quantize=flags[1])
+            bank.shared_read = shared
+            xx = x.to(DEV).requires_grad_(True)
+            n0 = _lib.launch_count
+            y = bank(xx)
+            launches.append(_lib.launch_count - n0)
+            y.backward(torch.ones_like(y))
+            outs.append((y.detach().cpu(), xx.grad.cpu(), list(bank.names)))
+        assert outs[0][2] == outs[1][2]
+        assert torch.equal(outs[0][0], outs[1][0]), shape
+        assert torch.equal(outs[0][1], outs[1][1])
+        n_shared = 4 if shape[1] == 3 else 3
+        assert launches[1] - launches[0] >= n_shared - 1                    # K' member kernels (or more: a member whose
+        # slice is not 32-byte aligned needs kernel + epilogue kernel on its own) became one
+    # two-member minimum: a lone member keeps its own kernel
+    bank = wmattack.AttackBank([wmattack.MiddleBlur(3), wmattack.JpegMask(50)])
+    n0 = _lib.launch_count
+    bank(rnd((1, 3, 32, 32), 9).to(DEV))
+    assert _lib.launch_count - n0 == 2
+
+
+def test_fused_resize_band_proof_covers_every_ratio_the_layer_can_draw():
+    """Resize draws an arbitrary ratio in [0.5, 1.5] per call; the mid size int(r * n) takes n + 1 values.  Every one
+    of them, at the trainers' 256 px and the BASELINE's 512 px frames (square and 2:1), must PASS the band proof that
+    wm_resize_tables runs (rb_prove_kernel: the fused kernel's own window arithmetic over all tile positions, both
+    directions) — none may need the two-call path, and the proof must not flag a geometry the kernel handles."""
+    WF._RESIZE_UNFUSED.clear()
+    for h, w in ((256, 256), (512, 512), (256, 512)):
+        for mode in (WF.BICUBIC, WF.BILINEAR):
+            for mh in range(h // 2, h + h // 2 + 1, 1 if h == 256 else 3):
+                mw = int(mh * w / h)
+                assert WF._lib.load().wm_resize_is_fused(h, w, mh, mw, 3) == 1
+                assert WF._resize_tables(torch.device(DEV), h, w, (mh, mw), mode) is not None, (h, w, mh, mw, mode)
+    assert not WF._RESIZE_UNFUSED
+    # spot-check that proven geometries really are right at the extremes of the window sizes
+    x, g = rnd((1, 3, 256, 256), 3), rnd((1, 3, 256, 256), 4)
+    for r in (0.5, 0.501, 0.666, 0.999, 1.0, 1.499, 1.5):
+        xx = x.to(DEV).requires_grad_(True)
+        y = wmattack.Resize()(xx, resize_ratio=r)
+        y.backward(g.to(DEV))
+        xt = x.to(DEV).requires_grad_(True)
+        mid = [int(r * 256)] * 2
+        Fi = torch.nn.functional.interpolate
+        yt = Fi(Fi(xt, size=mid, mode="bicubic"), size=[256, 256], mode="bicubic").clamp(0, 1)
+        yt.backward(g.to(DEV))
+        assert md(y, yt) <= 1e-5, r
+        _assert_resize_grad(xx.grad, xt.grad, x, r, "bicubic", 2e-5, f"r={r}")

@@ -38,25 +38,36 @@ def test_library_exports_every_header_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"libwmattack.so does not export {n}"
     assert set(_lib.SIGNATURES) | set(_lib.HELPERS) == names - {"wm_version", "wm_last_error"}
-    assert lib.wm_version() == 1
+    assert lib.wm_version() == 2
     assert isinstance(lib.wm_last_error(), bytes)
 
 
 def test_invalid_arguments_fail_loudly_without_a_gpu(lib):
     # argument validation happens before any CUDA call, so it is testable on a CPU box
     with pytest.raises(_lib.WMAttackError, match="null"):
-        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None)
+        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="multiples of 16"):
-        _lib.call("wm_diffjpeg_fwd", 256, 8, 8, 8, 256, 1, 24, 24, 1.0, None, 0, None)
+        _lib.call("wm_diffjpeg_fwd", 256, 8, 8, 8, 256, 1, 24, 24, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="aligned"):
-        _lib.call("wm_diffjpeg_fwd", 260, 8, 8, 8, 256, 1, 32, 32, 1.0, None, 0, None)
+        _lib.call("wm_diffjpeg_fwd", 260, 8, 8, 8, 256, 1, 32, 32, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="kernel size"):
-        _lib.call("wm_median_fwd", 256, 0, 0, 256, None, 1, 8, 8, 4, None)
+        _lib.call("wm_median_fwd", 256, 0, 0, 256, None, 1, 8, 8, 4, None, None)
     with pytest.raises(_lib.WMAttackError, match="odd"):
         taps = (_lib.f32 * 4)(0.25, 0.25, 0.25, 0.25)
-        _lib.call("wm_gaussblur", 256, 64, 8, 256, 1, 8, 8, taps, 4, 0, 0, None)
+        _lib.call("wm_gaussblur", 256, 64, 8, 256, 1, 8, 8, taps, 4, 0, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="mode"):
-        _lib.call("wm_interp_fwd", 256, 64, 8, 0, 0, 8, 8, 256, 1, 4, 4, 7, 0, None, None)
+        _lib.call("wm_interp_fwd", 256, 64, 8, 8, 8, 0, 0, 8, 8, 256, 1, 4, 4, 7, 0, None, None)
+    with pytest.raises(_lib.WMAttackError, match="outside"):       # crop window beyond the source plane
+        _lib.call("wm_interp_fwd", 256, 64, 8, 8, 8, 4, 0, 8, 8, 256, 1, 4, 4, 0, 0, None, None)
+    # the store epilogue is an explicit argument: a misaligned x, or a code path that cannot apply it, is an error
+    ep = _lib.StoreEpilogue(260, 1, 1)
+    import ctypes
+    with pytest.raises(_lib.WMAttackError, match="epilogue"):
+        _lib.call("wm_diffjpeg_fwd", 256, 3072, 1024, 32, 256, 1, 32, 32, 1.0, None, 0, ctypes.byref(ep), None)
+    ep = _lib.StoreEpilogue(256, 1, 1)
+    with pytest.raises(_lib.WMAttackError, match="does not apply"):
+        taps = (_lib.f32 * 9)(*([1 / 9] * 9))                      # k = 9: generic blur path
+        _lib.call("wm_gaussblur", 256, 64, 8, 256, 1, 8, 8, taps, 9, 0, 0, ctypes.byref(ep), None)
     assert lib.wm_interp_is_tiled(512, 512, 256, 256, 192) == 1 and lib.wm_interp_is_tiled(512, 512, 64, 64, 3) == 0
 
 

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
 
 template <int K>
 static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
-                           const float* taps_host, cudaStream_t st) {
+                           const float* taps_host, const wm_store_epilogue* ep, cudaStream_t st) {
     constexpr int R = K / 2, S = bt_stages<K>();
     CUtensorMap tm;
     if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, BT_BW, BT_TH + 2 * R)) {
@@ -194,7 +194,7 @@ static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y,
     a.tiles_x = (W + BT_TW - 1) / BT_TW; a.tiles_y = (H + BT_TH - 1) / BT_TH;
     a.total = int64_t(N) * a.tiles_x * a.tiles_y;
     for (int i = 0; i < K; ++i) a.taps[i] = taps_host[i];
-    a.ep = take_store_epilogue();
+    a.ep = make_store_ep(ep);
     a.ep.from_input = a.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
     const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
     cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(256) gaussblur_reflect_adjoint_kernel(const Bl
 using namespace wm;
 
 extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
-                            const float* taps_host, int k, int border, int adjoint, void* stream) {
+                            const float* taps_host, int k, int border, int adjoint,
+                            const wm_store_epilogue* ep, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && taps_host, WM_E_NULL, "wm_gaussblur: null pointer");
     WM_REQUIRE(k >= 1 && k <= BL_MAXK && (k & 1), WM_E_ARG, "wm_gaussblur: kernel size must be odd and <= %d (got %d)", BL_MAXK, k);
@@ -254,7 +255,7 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
     for (int i = 0; i < k; ++i) a.taps[i] = taps_host[i];
     cudaStream_t st = (cudaStream_t)stream;
     if (border == 1 && adjoint) {
-        if (reject_store_epilogue("wm_gaussblur (reflect adjoint)")) return WM_E_ARG;
+        WM_EP_REJECT(ep, "wm_gaussblur (reflect adjoint)");
         const int64_t total = int64_t(N) * H * W;
         const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 16;
         gaussblur_reflect_adjoint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a);
@@ -262,11 +263,12 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
         return WM_OK;
     }
     if (border == 0 && (k == 3 || k == 5 || k == 7) && W % 4 == 0 && aligned(y, 16) && tmap_ok(x, x_sp, x_sh, 4)) {
-        if (k == 3) return launch_blur_tma<3>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
-        if (k == 5) return launch_blur_tma<5>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
-        return launch_blur_tma<7>(x, x_sp, x_sh, y, N, H, W, taps_host, st);
+        WM_EP_CHECK(ep, "wm_gaussblur");
+        if (k == 3) return launch_blur_tma<3>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+        if (k == 5) return launch_blur_tma<5>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+        return launch_blur_tma<7>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
     }
-    if (reject_store_epilogue("wm_gaussblur (generic path)")) return WM_E_ARG;
+    WM_EP_REJECT(ep, "wm_gaussblur (generic path)");
     const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;
     const size_t smem = sizeof(float) * (size_t(IH) * IW + size_t(IH) * BL_TW);
     cudaError_t e = cudaFuncSetAttribute(gaussblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

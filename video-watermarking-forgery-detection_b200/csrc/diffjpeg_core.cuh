@@ -347,6 +347,23 @@ __device__ __forceinline__ void dj_chroma_terms(const float (&cb)[4], const floa
     }
 }
 
+// torch's min/max clamp (utils/JPEG.py:467-468) propagates NaN, .sat returns 0.  A NaN (or an inf, or the 0/0 of
+// quality = 100, factor 0) anywhere in an 8x8 block reaches EVERY output of the inverse transform of that block,
+// so one test per row and plane is enough: rare path, nothing on the common one but two compares.
+__device__ __forceinline__ void dj_propagate_nan(const float (&yv)[8], const float (&tR)[4], const float (&tB)[4],
+                                                 f8& oR, f8& oG, f8& oB) {
+    const float probe = yv[0] + tR[0] + tB[0] + tR[3] + tB[3];
+    if (probe != probe) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float nR = yv[c] + tR[c >> 1], nB = yv[c] + tB[c >> 1], nG = nR + nB;
+            if (nR != nR) oR.v[c] = nR;
+            if (nG != nG) oG.v[c] = nG;
+            if (nB != nB) oB.v[c] = nB;
+        }
+    }
+}
+
 // Final phase of forward / decompress: row IDCT, upsampled chroma, colour transform, clamp.
 template <int NT, bool EP = false>
 __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, const float4* scr) {
@@ -378,6 +395,7 @@ __device__ __forceinline__ void dj_emit_rgb(const DJArgs& a, const DJThread& t, 
                 oG.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tG[c >> 1]));
                 oB.v[c] = __saturatef(fmaf(yv[c], DJ_I255, tB[c >> 1]));
             }
+            dj_propagate_nan(yv, tR, tB, oR, oG, oB);
             if (t.active) {
                 if (EP) { ep_apply_n<8>(oR.v, xR.v, a.ep); ep_apply_n<8>(oG.v, xG.v, a.ep); ep_apply_n<8>(oB.v, xB.v, a.ep); }
                 stg256(p, oR);
@@ -428,6 +446,7 @@ __device__ __forceinline__ void dj_emit_rgb_save(const DJArgs& a, const DJThread
                 float& acc = c < 4 ? accl : acch;
                 acc = fmaf(fmaf(fmaf(acc, 4.f, cB), 4.f, cG), 4.f, cR);
             }
+            dj_propagate_nan(yv, tR, tB, oR, oG, oB);
             const unsigned lo = __float2uint_rn(accl), hi = __float2uint_rn(acch);
             if (t.active) {
                 float* p = yo + int64_t(r) * a.W;

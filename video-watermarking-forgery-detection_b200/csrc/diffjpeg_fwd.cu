@@ -59,14 +59,15 @@ extern "C" int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, 
 
 extern "C" int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                                int B, int H, int W, float factor, const float* factor_ps,
-                               int rounding, void* stream) {
+                               int rounding, const wm_store_epilogue* ep, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd")) return rc;
     WM_REQUIRE(y != nullptr && aligned(y, 32), WM_E_ALIGN, "wm_diffjpeg_fwd: y must be non-null, 32-byte aligned");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
-    a.ep = take_store_epilogue();
+    WM_EP_CHECK(ep, "wm_diffjpeg_fwd");
+    a.ep = make_store_ep(ep);
     if (a.ep.x) {
         switch (rounding) {
             case WM_ROUND_ONLY_AT_0: return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_ONLY_AT_0, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");

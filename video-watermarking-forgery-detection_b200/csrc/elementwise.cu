@@ -4,62 +4,14 @@
 // HOST and copies them over PCIe: noise_layers/salt_pepper_noise.py:14, crop.py:145,
 // gaussian_noise.py:14, dropout.py:21), with an `inject` pointer so that parity tests can feed
 // the very tensor the reference drew.
+#include "philox.cuh"
 #include "wm_common.cuh"
 
 namespace wm {
 
-// ---- Philox4x32-10 (Salmon et al. 2011), counter = (idx_lo, idx_hi, 0, 0), key = seed -------
-struct Philox {
-    uint32_t k0, k1;
-    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
-    __device__ __forceinline__ uint4 operator()(uint64_t ctr) const {
-        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
-        uint32_t a = k0, b = k1;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
-            a += 0x9E3779B9u; b += 0xBB67AE85u;
-        }
-        return make_uint4(c0, c1, c2, c3);
-    }
-};
-
-// Device-resident randomness (CUDA-graph capture): when seed == WM_RNG_FROM_DEVICE the `offset` argument is
-// a device pointer to {seed, offset} — written by wm_rng_reserve in the same stream — so that a captured
-// launch draws fresh numbers at every replay and its backward regenerates exactly the same ones.
-__device__ __forceinline__ void resolve_rng(uint64_t& seed, uint64_t& offset) {
-    if (seed == WM_RNG_FROM_DEVICE) {
-        const uint64_t* p = reinterpret_cast<const uint64_t*>(offset);
-        seed = __ldg(p); offset = __ldg(p + 1);
-    }
-}
 __global__ void rng_reserve_kernel(uint64_t* state, uint64_t* slot, uint64_t count) {
     slot[0] = state[0]; slot[1] = state[1];
     state[1] += count;
-}
-
-// uniform in [0,1) with 24 bits (same support as torch.rand float32)
-__device__ __forceinline__ float u01(uint32_t r) { return (r >> 8) * (1.0f / 16777216.0f); }
-
-__device__ __forceinline__ float4 uniform4(const Philox& ph, uint64_t ctr) {
-    const uint4 r = ph(ctr);
-    return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
-}
-__device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t ctr) {
-    const uint4 r = ph(ctr);
-    // Box-Muller on (0,1] x [0,1)
-    const float u1 = ((r.x >> 8) + 1) * (1.0f / 16777216.0f), u2 = u01(r.y);
-    const float u3 = ((r.z >> 8) + 1) * (1.0f / 16777216.0f), u4 = u01(r.w);
-    // sqrt.approx (MUFU.SQRT, max 1 ulp): the radius of a RANDOM draw needs no IEEE rounding
-    float ra, rb;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-2.f * __logf(u1)));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-2.f * __logf(u3)));
-    float s1, c1, s2, c2;
-    __sincosf(6.283185307179586f * u2, &s1, &c1);
-    __sincosf(6.283185307179586f * u4, &s2, &c2);
-    return make_float4(ra * c1, ra * s1, rb * c2, rb * s2);
 }
 
 __device__ __forceinline__ float4 ld4(const float* p, int64_t i, int64_t n) {
@@ -101,11 +53,10 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
                nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
         float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
         if (!BWD) {
-            if (clamp) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
-                         v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
+            if (clamp) v = clamp01_nan4(v);
             if (EP) {
                 const float4 ex = ep.from_input ? xv : ld4(ep.x, i, n);
-                v = make_float4(ep_apply(v.x, ex.x, ep), ep_apply(v.y, ex.y, ep), ep_apply(v.z, ex.z, ep), ep_apply(v.w, ex.w, ep));
+                v = ep_apply4v(v, ex, ep);
             }
             st4(out, i, n, v);
         } else {
@@ -138,7 +89,7 @@ __global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* _
         else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
                nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
         const float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
-        const float4 c = make_float4(__saturatef(v.x), __saturatef(v.y), __saturatef(v.z), __saturatef(v.w));
+        const float4 c = clamp01_nan4(v);           // NaN propagates (torch.clamp)
         st4(out, i, n, c);
         // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN, like torch.clamp's backward mask)
         const unsigned b0 = __ballot_sync(0xffffffffu, c.x == v.x), b1 = __ballot_sync(0xffffffffu, c.y == v.y);
@@ -241,8 +192,7 @@ __global__ void __launch_bounds__(256) bernoulli_kernel(float* __restrict__ mask
 __global__ void __launch_bounds__(256) quantize8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int clamp01) {
     WM_EW_LOOP(i) {
         float4 v = ld4(x, i, n);
-        if (clamp01) { v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
-                       v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f); }
+        if (clamp01) v = clamp01_nan4(v);
         // correctly rounded quotient: bit-parity with torch's `/ 255.` (quant255_n, wm_common.cuh)
         float q[4] = {v.x, v.y, v.z, v.w};
         quant255_n<4>(q);
@@ -267,7 +217,7 @@ __global__ void __launch_bounds__(256) cropout_kernel(const float* __restrict__ 
 // straight into a slice of the K-way batch.  Same fp32 operation order (no FMA contraction), so the
 // values are bit-identical to the reference's.  Backward is the identity on x (straight-through).
 __device__ __forceinline__ float epilogue1(float x, float s, int clamp01, int quant) {
-    if (clamp01) s = fminf(fmaxf(s, 0.f), 1.f);
+    if (clamp01) s = clamp01_nan(s);
     float v = __fadd_rn(x, __fsub_rn(s, x));
     if (quant) v = __fdiv_rn(rintf(__fmul_rn(v, 255.f)), 255.f);
     return v;
@@ -384,12 +334,14 @@ using namespace wm;
              "%s: pointers must be 16-byte aligned", who); } while (0)
 
 extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
-                                 uint64_t seed, uint64_t offset, const float* inject, void* stream) {
+                                 uint64_t seed, uint64_t offset, const float* inject,
+                                 const wm_store_epilogue* ep_in, void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
+    WM_EP_CHECK(ep_in, "wm_gaussnoise_fwd");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
-    StoreEp ep = take_store_epilogue();
+    StoreEp ep = make_store_ep(ep_in);
     ep.from_input = ep.x == x;
     if (ep.x) gaussnoise_kernel<false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
     else gaussnoise_kernel<false, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
@@ -416,7 +368,6 @@ extern "C" int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbi
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && maskbits, WM_E_NULL, "wm_gaussnoise_fwd_mask: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd_mask", x, y, inject, maskbits);
-    WM_REQUIRE(!reject_store_epilogue("wm_gaussnoise_fwd_mask"), WM_E_ARG, "wm_gaussnoise_fwd_mask: the store epilogue is a no-grad path");
     gaussnoise_mask_fwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, maskbits, n, mean, std, seed, offset, inject);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd_mask");
     return WM_OK;

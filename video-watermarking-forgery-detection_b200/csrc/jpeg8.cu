@@ -576,15 +576,16 @@ static int j8_fwd_any(const J8Args& a, int variant, int submode, bool vec, bool 
 using namespace wm;
 
 extern "C" int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
-                            int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
+                            int B, int H, int W, const wm_jpeg8_params* p, const wm_store_epilogue* ep, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
     if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd")) return rc;
+    WM_EP_CHECK(ep, "wm_jpeg8_fwd");
     WM_REQUIRE(y != nullptr, WM_E_NULL, "wm_jpeg8_fwd: null output");
     a.out = y;
     const bool vec = j8_vec_ok(x, x_sb, x_sc, x_sh, W) && aligned(y, 32);
-    if (vec && p->subsample == 0) a.ep = take_store_epilogue();       // the two-threads-per-block kernel applies it
-    else if (reject_store_epilogue("wm_jpeg8_fwd (ragged / subsampled path)")) return WM_E_ARG;
+    if (vec && p->subsample == 0) a.ep = make_store_ep(ep);           // the two-threads-per-block kernel applies it
+    else WM_EP_REJECT(ep, "wm_jpeg8_fwd (ragged / subsampled path)");
     return j8_fwd_any(a, p->variant, p->subsample, vec, false, (cudaStream_t)stream, "wm_jpeg8_fwd");
 }
 

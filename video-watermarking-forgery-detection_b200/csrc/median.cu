@@ -498,9 +498,10 @@ __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict
 using namespace wm;
 
 extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
-                             int N, int H, int W, int k, void* stream) {
+                             int N, int H, int W, int k, const wm_store_epilogue* ep, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_median_fwd: null pointer");
+    WM_EP_CHECK(ep, "wm_median_fwd");
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_fwd: kernel size must be 3 or 5 (got %d)", k);
     WM_REQUIRE(N >= 0 && N <= 65535 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd: bad shape N=%d H=%d W=%d", N, H, W);
     if (N == 0) return WM_OK;
@@ -513,7 +514,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
         }
         MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
-        ta.ep = take_store_epilogue();
+        ta.ep = make_store_ep(ep);
         ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
         const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
         auto kern = ta.ep.x ? (idx ? median3_tma_kernel<true, true> : median3_tma_kernel<false, true>)
@@ -533,7 +534,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
         }
         MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0, StoreEp{nullptr, 0, 0, 0}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
-        ta.ep = take_store_epilogue();
+        ta.ep = make_store_ep(ep);
         ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
         const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
         auto kern = ta.ep.x ? (idx ? median5_tma_kernel<true, true> : median5_tma_kernel<false, true>)
@@ -545,7 +546,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
         WM_LAUNCH_CHECK("wm_median_fwd(tma5)");
         return WM_OK;
     }
-    if (reject_store_epilogue("wm_median_fwd (generic path)")) return WM_E_ARG;
+    WM_EP_REJECT(ep, "wm_median_fwd (generic path)");
     MedArgs a{x, x_sp, x_sh, y, idx, N, H, W};
     const int tiles = ((W + MD_TW - 1) / MD_TW) * ((H + MD_TH - 1) / MD_TH);
     dim3 grid(tiles, N);

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(RS_THREADS) interp_fwd_tiled_kernel(const Inte
             for (int k = 0; k < NT; ++k) acc = fmaf(rW[r][k], tmp[(rIdx[r][k] - ry_lo) * RS_TW + c], acc);
             const bool ok = oy < a.Hout && ox < a.Wout;
             bool inside = true;
-            if (a.clamp01) { inside = acc >= 0.f && acc <= 1.f; acc = fminf(fmaxf(acc, 0.f), 1.f); }
+            if (a.clamp01) { inside = acc >= 0.f && acc <= 1.f; acc = clamp01_nan(acc); }
             if (ok) dst[int64_t(oy) * a.Wout + ox] = acc;
             if (a.maskbits) {
                 const unsigned bits = __ballot_sync(0xffffffffu, inside && ok);
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(const InterpArgs a) {
 #pragma unroll
         for (int r = 0; r < NT; ++r) acc = fmaf(wy[r], tmpv[r], acc);
         bool inside = true;
-        if (a.clamp01) { inside = acc >= 0.f && acc <= 1.f; acc = fminf(fmaxf(acc, 0.f), 1.f); }
+        if (a.clamp01) { inside = acc >= 0.f && acc <= 1.f; acc = clamp01_nan(acc); }
         a.y[i] = acc;
         if (a.maskbits && !inside)
             atomicAnd(a.maskbits + (int64_t(n) * a.Hout + oy) * a.mask_words_per_row + (ox >> 5), ~(1u << (ox & 31)));
@@ -293,7 +293,7 @@ static inline bool rs_tiled_ok(float sh, float sw, int N) {
 
 using namespace wm;
 
-extern "C" int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0, int w0, int Hin, int Win,
+extern "C" int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int Hsrc, int Wsrc, int h0, int w0, int Hin, int Win,
                              float* y, int N, int Hout, int Wout, int mode, int clamp01,
                              uint32_t* maskbits, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
@@ -301,6 +301,9 @@ extern "C" int wm_interp_fwd(const float* x, int64_t x_sp, int64_t x_sh, int h0,
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_interp_fwd: mode must be 0 (bilinear) or 1 (bicubic)");
     WM_REQUIRE(N >= 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && h0 >= 0 && w0 >= 0, WM_E_SHAPE,
                "wm_interp_fwd: bad shape N=%d in=%dx%d out=%dx%d", N, Hin, Win, Hout, Wout);
+    WM_REQUIRE(int64_t(h0) + Hin <= Hsrc && int64_t(w0) + Win <= Wsrc, WM_E_SHAPE,
+               "wm_interp_fwd: window [%d:%d, %d:%d] is outside the %dx%d source plane (it is read in place)",
+               h0, h0 + Hin, w0, w0 + Win, Hsrc, Wsrc);
     if (N == 0) return WM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     InterpArgs a{};

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     const bool okr = 4 * qd + k < th;              // uniform
                     const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
-                        const float4 c = make_float4(__saturatef(acc.x), __saturatef(acc.y), __saturatef(acc.z), __saturatef(acc.w));
+                        const float4 c = clamp01_nan4(acc);
                         if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4v(c, xe[k], a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
@@ -336,6 +336,63 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         }
         __syncthreads();          // tmp is rewritten by the next plane's H pass
     }
+}
+
+// Proof that a geometry fits: the SAME window arithmetic as rb_banded_kernel's prologue, evaluated from the tables
+// alone for every tile position (one CTA each), for one direction's table set.  Sets *flag when a non-zero band
+// weight would fall outside the lane pair's register window (H pass), the staged columns, the row quad's shared
+// window (V pass) or the staged rows.  Launched by wm_resize_tables for both directions, so the flag in the
+// workspace's last word is final when the tables are: the host reads it ONCE per new geometry.
+template <int BT>
+__global__ void __launch_bounds__(RB_THREADS) rb_prove_kernel(const int* __restrict__ lox, const float* __restrict__ wx,
+                                                              const int* __restrict__ loy, const float* __restrict__ wy,
+                                                              int H, int W, int* __restrict__ flag) {
+    using G = RBGeom<BT>;
+    constexpr int BTW = BT <= 10 ? 10 : 14, BTV = G::BTV;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ox0 = blockIdx.x * RB_TW, oy0 = blockIdx.y * RB_TH;
+    const int tw = min(RB_TW, W - ox0), th = min(RB_TH, H - oy0);
+    const int xs = (lox[ox0] & ~3) - 8, ys = loy[oy0];
+    bool bad = false;
+    if (warp < 2) {                                   // the two 64-column groups of the H pass
+        const int oa = 64 * warp + 2 * lane;
+        const bool hv0 = oa < tw, hv1 = oa + 1 < tw;
+        const int hg0 = min(ox0 + oa, W - 1), hg1 = min(ox0 + oa + 1, W - 1);
+        const int hlo0 = lox[hg0], hlo1 = lox[hg1];
+        int hmin = hv0 ? hlo0 - 2 * lane : (1 << 30);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) hmin = min(hmin, __shfl_xor_sync(0xffffffffu, hmin, d));
+        hmin = min(hmin, W) & ~1;
+        const int hs = hmin + 2 * lane;
+        const int hshift0 = hv0 ? hlo0 - hs : BTW, hshift1 = hv1 ? hlo1 - hs : BTW;
+        for (int j = 0; j < BT; ++j) {
+            bad |= hv0 && (j + hshift0 >= BTW || j + hshift0 < 0) && wx[int64_t(hg0) * BT + j] != 0.f;
+            bad |= hv1 && (j + hshift1 >= BTW || j + hshift1 < 0) && wx[int64_t(hg1) * BT + j] != 0.f;
+        }
+        const int hbase = min(max(hs - xs, 0), G::IW - BTW) & ~1;
+        bad |= hv0 && hbase != hs - xs;
+    }
+    for (int i = tid; i < G::NQ * 4; i += RB_THREADS) {              // V pass: rows 4p .. 4p+3 share one BTV-row window
+        const int p = i >> 2, k = i & 3;
+        if (4 * p >= th) continue;
+        const int r0 = min(oy0 + 4 * p, H - 1), rk = min(oy0 + 4 * p + k, H - 1);
+        const int d = loy[rk] - loy[r0];
+        for (int t = 0; t < BT; ++t) bad |= (t + d >= BTV || t + d < 0) && wy[int64_t(rk) * BT + t] != 0.f;
+        const int y0 = loy[r0] - ys;
+        bad |= y0 < 0 || y0 > G::IH - BTV;                           // the quad's window must lie in the staged rows
+    }
+    if (tid == 0) {
+        const int need = max(loy[oy0 + th - 1] + BT, loy[oy0 + ((th - 1) & ~3)] + BT + 2) - ys;
+        // rows beyond IH are only harmless when they lie past the image bottom (their weights are zero)
+        bad |= need > G::IH && ys + G::IH < H;
+    }
+    if (bad) atomicExch(flag, 1);
+}
+
+template <int BT>
+static void rb_prove(const float* tx, const float* ty, int H, int W, int* flag, cudaStream_t st) {
+    dim3 grid((W + RB_TW - 1) / RB_TW, (H + RB_TH - 1) / RB_TH);
+    rb_prove_kernel<BT><<<grid, RB_THREADS, 0, st>>>(reinterpret_cast<const int*>(tx), tx + W, reinterpret_cast<const int*>(ty), ty + H, H, W, flag);
 }
 
 static inline bool rb_ok(int H, int W, int Hm, int Wm, int N) {
@@ -402,13 +459,21 @@ extern "C" int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int
     }
     rb_adj_tables_kernel<<<(W + 127) / 128, 128, 0, st>>>(W, BT, lo(fx), fx + W, lo(bx), bx + W);
     rb_adj_tables_kernel<<<(H + 127) / 128, 128, 0, st>>>(H, BT, lo(fy), fy + H, lo(by), by + H);
-    cudaMemsetAsync(by + rb_axis_words(H, BT), 0, 4 * sizeof(float), st);
+    int* flag = reinterpret_cast<int*>(by + rb_axis_words(H, BT));
+    cudaMemsetAsync(flag, 0, 4 * sizeof(float), st);
+    // prove both directions' tables against the kernel's windows (flag != 0: use wm_interp_fwd twice instead)
+    switch (BT) {
+        case 8:  rb_prove<8>(fx, fy, H, W, flag, st);  rb_prove<8>(bx, by, H, W, flag, st);  break;
+        case 10: rb_prove<10>(fx, fy, H, W, flag, st); rb_prove<10>(bx, by, H, W, flag, st); break;
+        case 12: rb_prove<12>(fx, fy, H, W, flag, st); rb_prove<12>(bx, by, H, W, flag, st); break;
+        default: rb_prove<14>(fx, fy, H, W, flag, st); rb_prove<14>(bx, by, H, W, flag, st); break;
+    }
     WM_LAUNCH_CHECK("wm_resize_tables");
     return WM_OK;
 }
 
 static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* dst, uint32_t* mask, const float* tables,
-                  int N, int H, int W, int Hm, int Wm, void* stream, const char* who) {
+                  int N, int H, int W, int Hm, int Wm, const wm_store_epilogue* ep, void* stream, const char* who) {
     const int BT = rb_band(H, W, Hm, Wm);
     const float* fx = tables; const float* fy = fx + rb_axis_words(W, BT);
     const float* bx = fy + rb_axis_words(H, BT); const float* by = bx + rb_axis_words(W, BT);
@@ -418,8 +483,8 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
     a.lox = reinterpret_cast<const int*>(tx); a.wx = tx + W;
     a.loy = reinterpret_cast<const int*>(ty); a.wy = ty + H;
     a.N = N; a.H = H; a.W = W; a.tiles_x = (W + RB_TW - 1) / RB_TW; a.tiles_y = (H + RB_TH - 1) / RB_TH;
-    a.overflow = reinterpret_cast<int*>(const_cast<float*>(by + rb_axis_words(H, BT)));
-    a.ep = dir == 0 ? take_store_epilogue() : StoreEp{nullptr, 0, 0};
+    a.overflow = nullptr;          // proven per geometry at table-build time (rb_prove_kernel), not per launch
+    a.ep = dir == 0 ? make_store_ep(ep) : StoreEp{nullptr, 0, 0, 0};
     CUtensorMap tm{}, tmm{};
     int rc = 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -447,9 +512,10 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
 }
 
 extern "C" int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
-                             int mode, uint32_t* maskbits, const float* tables, void* stream) {
+                             int mode, uint32_t* maskbits, const float* tables, const wm_store_epilogue* ep, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && tables, WM_E_NULL, "wm_resize_fwd: null pointer");
+    WM_EP_CHECK(ep, "wm_resize_fwd");
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_fwd: mode must be 0 (bilinear) or 1 (bicubic)");
     if (N == 0) return WM_OK;
     WM_REQUIRE(rb_ok(H, W, Hm, Wm, N), WM_E_SHAPE,
@@ -457,7 +523,7 @@ extern "C" int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
                "use wm_interp_fwd twice", H, W, Hm, Wm, N, RB_RATIO_MIN, RB_RATIO_MAX);
     WM_REQUIRE(tmap_ok(x, x_sp, x_sh, 4) && aligned(y, 16) && (!maskbits || aligned(maskbits, 16)), WM_E_ALIGN,
                "wm_resize_fwd: x, y, maskbits must be 16-byte aligned with strides multiples of 4 elements");
-    return rb_run(0, x, x_sp, x_sh, y, maskbits, tables, N, H, W, Hm, Wm, stream, "wm_resize_fwd");
+    return rb_run(0, x, x_sp, x_sh, y, maskbits, tables, N, H, W, Hm, Wm, ep, stream, "wm_resize_fwd");
 }
 
 extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
@@ -471,5 +537,5 @@ extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* g
                H, W, Hm, Wm, N);
     WM_REQUIRE(aligned(gy, 16) && aligned(gx, 16) && (!maskbits || aligned(maskbits, 16)), WM_E_ALIGN,
                "wm_resize_bwd: gy, gx, maskbits must be 16-byte aligned");
-    return rb_run(1, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, stream, "wm_resize_bwd");
+    return rb_run(1, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, nullptr, stream, "wm_resize_bwd");
 }

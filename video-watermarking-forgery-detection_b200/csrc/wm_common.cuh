@@ -50,6 +50,36 @@ __device__ __forceinline__ float4 ldg128_stream(const float* p) {
     return r;
 }
 
+// ---- clamp to [0,1] with torch.clamp's NaN rule (NaN propagates; fminf/fmaxf and .sat return 0 for NaN):
+// two FMNMX.NAN instead of the compare + select a separate NaN test would need
+__device__ __forceinline__ float clamp01_nan(float v) {
+    float d;
+    asm("max.NaN.f32 %0, %1, 0f00000000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(d) : "f"(v));
+    return d;
+}
+
+// N values at once: the common case (no NaN in the group) costs N saturating moves on the FMA pipe, N-1 adds and
+// ONE compare; only a group that holds a NaN (or +inf and -inf together: their sum is NaN too) takes the exact
+// per-element rule.  +-inf alone saturates to 1 / 0 on the fast path, as torch.clamp does.
+template <int N>
+__device__ __forceinline__ void clamp01_nan_n(float* v) {
+    float s = v[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) s += v[i];
+    if (s != s) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = clamp01_nan(v[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __saturatef(v[i]);
+    }
+}
+__device__ __forceinline__ float4 clamp01_nan4(float4 v) {
+    float a[4] = {v.x, v.y, v.z, v.w};
+    clamp01_nan_n<4>(a);
+    return make_float4(a[0], a[1], a[2], a[3]);
+}
+
 // ---- 3-input min/max (sm_100: FMNMX3) -----------------------------------------------------
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
@@ -80,13 +110,20 @@ __device__ __forceinline__ float fast_rcp(float b) {
 
 // ---- store epilogue: out = Quantization( x + (clamp(v, 0, 1) - x) ) applied by a
 // forward kernel in its own store, x read at the output position (models/IRNp_model.py:674-680).
-// Armed per host thread by wm_set_store_epilogue for the NEXT forward launch (see include/wm_attack.h).
+// Passed explicitly to the forward entry points as a wm_store_epilogue (see include/wm_attack.h).
 struct StoreEp { const float* x; int clamp01; int quant; int from_input; };
 // from_input is set by a launcher when ep.x IS the kernel's own (dense) input: kernels that still hold the
 // input value at the output position (registers / staged tile) then skip the second global read.
-void arm_store_epilogue(const StoreEp& e);
-StoreEp take_store_epilogue();                 // returns this thread's pending descriptor and clears it
-bool reject_store_epilogue(const char* who);   // true (and an error message) if one is pending
+inline StoreEp make_store_ep(const wm_store_epilogue* e) {
+    return (e && e->x) ? StoreEp{e->x, e->clamp01, e->quantize, 0} : StoreEp{nullptr, 0, 0, 0};
+}
+inline bool wants_store_ep(const wm_store_epilogue* e) { return e && e->x; }
+#define WM_EP_CHECK(ep, who)                                                                              \
+    WM_REQUIRE(!::wm::wants_store_ep(ep) || ::wm::aligned((ep)->x, 32), WM_E_ALIGN,                      \
+               "%s: the store epilogue's x must be 32-byte aligned", who)
+#define WM_EP_REJECT(ep, who)                                                                             \
+    WM_REQUIRE(!::wm::wants_store_ep(ep), WM_E_ARG,                                                      \
+               "%s: a store epilogue was passed but this code path does not apply one", who)
 
 // n / 255 for an integer-valued n: reciprocal + one Newton step is the correctly rounded quotient
 // (checked exhaustively for |n| <= 70000 against IEEE division) at 3 FMAs instead of the ~12-instruction
@@ -99,6 +136,9 @@ __device__ __forceinline__ float div255(float n) {
 // round(v * 255) / 255 for N values at once, bit-identical to torch's (v * 255.).round() / 255.: one range
 // check (and branch) for the whole group.  Fast path: the 1.5 * 2^23 trick for round-half-even (exact for
 // |t| < 2^22) + div255; anything out of range takes rintf + the IEEE division.
+// (the out-of-range path is a real call: inlined, its IEEE division sequence would be replicated at every store
+// site of every kernel and push the stencil kernels out of the instruction cache)
+static __device__ __noinline__ float quant255_slow(float t) { return __fdiv_rn(rintf(t), 255.f); }
 template <int N>
 __device__ __forceinline__ void quant255_n(float* v) {
     float m = 0.f;
@@ -109,15 +149,12 @@ __device__ __forceinline__ void quant255_n(float* v) {
         for (int i = 0; i < N; ++i) v[i] = div255(__fsub_rn(__fadd_rn(v[i], 12582912.f), 12582912.f));
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = __fdiv_rn(rintf(v[i]), 255.f);
+        for (int i = 0; i < N; ++i) v[i] = quant255_slow(v[i]);
     }
 }
 template <int N>
 __device__ __forceinline__ void ep_apply_n(float* v, const float* x, const StoreEp& e) {
-    if (e.clamp01) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 1.f);
-    }
+    if (e.clamp01) clamp01_nan_n<N>(v);
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = __fadd_rn(x[i], __fsub_rn(v[i], x[i]));   // same fp32 operation order as the reference
     if (e.quant) quant255_n<N>(v);

@@ -26,24 +26,38 @@ class Jpeg8Params(C.Structure):
                 ("variant", i32), ("subsample", i32)]
 
 
+class StoreEpilogue(C.Structure):
+    """Mirror of wm_store_epilogue (include/wm_attack.h): optional argument of the forward entry points."""
+    _fields_ = [("x", C.c_void_p), ("clamp01", i32), ("quantize", i32)]
+
+
+epp = C.POINTER(StoreEpilogue)
+
+
+class Bank3Desc(C.Structure):
+    """Mirror of wm_bank3_desc (include/wm_attack.h): members of the shared-read bank kernel."""
+    _fields_ = [("y_blur", C.c_void_p), ("blur_taps", f32 * 3), ("y_median", C.c_void_p), ("y_noise", C.c_void_p),
+                ("noise_mean", f32), ("noise_std", f32), ("noise_clamp", i32), ("seed", u64), ("offset", u64),
+                ("y_identity", C.c_void_p), ("clamp01", i32), ("quantize", i32)]
+
 # name -> argtypes; every function returns int.  Kept in one table so that the CPU test-suite
 # can check that the built library exports exactly the header's entry points.
 SIGNATURES = {
-    "wm_diffjpeg_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
+    "wm_diffjpeg_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, epp, vp],
     "wm_diffjpeg_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
     "wm_diffjpeg_fwd_save": [c_f32p, i64, i64, i64, c_f32p, c_f32p, c_f32p, vp, i32, i32, i32, f32, c_f32p, i32, vp],
     "wm_diffjpeg_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, vp, c_f32p, i32, i32, i32, vp],
     "wm_diffjpeg_compress": [c_f32p, i64, i64, i64, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
     "wm_diffjpeg_decompress": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, vp],
-    "wm_jpeg8_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), epp, vp],
     "wm_jpeg8_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_fwd_save": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_quantised": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
-    "wm_gaussblur": [c_f32p, i64, i64, c_f32p, i32, i32, i32, C.POINTER(f32), i32, i32, i32, vp],
-    "wm_median_fwd": [c_f32p, i64, i64, c_f32p, c_u8p, i32, i32, i32, i32, vp],
+    "wm_gaussblur": [c_f32p, i64, i64, c_f32p, i32, i32, i32, C.POINTER(f32), i32, i32, i32, epp, vp],
+    "wm_median_fwd": [c_f32p, i64, i64, c_f32p, c_u8p, i32, i32, i32, i32, epp, vp],
     "wm_median_bwd": [c_f32p, c_u8p, c_f32p, i32, i32, i32, i32, vp],
-    "wm_gaussnoise_fwd": [c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
+    "wm_gaussnoise_fwd": [c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, epp, vp],
     "wm_gaussnoise_bwd": [c_f32p, c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_fwd_mask": [c_f32p, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_bwd_mask": [c_f32p, vp, c_f32p, i64, vp],
@@ -57,17 +71,17 @@ SIGNATURES = {
     "wm_bernoulli_mask": [c_f32p, i64, f32, u64, u64, vp],
     "wm_quantize8_fwd": [c_f32p, c_f32p, i64, i32, vp],
     "wm_cropout_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, i32, i32, vp],
-    "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
+    "wm_interp_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, vp, vp],
     "wm_interp_bwd": [c_f32p, c_f32p, vp, i32, i32, i32, c_f32p, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
     "wm_u8_to_unit_float": [c_u8p, c_f32p, i64, vp],
     "wm_unit_float_to_u8": [c_f32p, c_u8p, i64, vp],
-    "wm_set_store_epilogue": [c_f32p, i32, i32],
+    "wm_bank3_fwd": [c_f32p, i64, i64, i32, i32, i32, C.POINTER(Bank3Desc), vp],
     "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
     "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],
     "wm_splice_fwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
     "wm_splice_bwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],
     "wm_resize_tables": [c_f32p, i32, i32, i32, i32, i32, vp],
-    "wm_resize_fwd": [c_f32p, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, vp],
+    "wm_resize_fwd": [c_f32p, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, epp, vp],
     "wm_resize_bwd": [c_f32p, vp, c_f32p, i32, i32, i32, i32, i32, i32, c_f32p, vp],
     "wm_cropresize_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, vp, vp],
     "wm_cropresize_bwd": [c_f32p, c_f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
@@ -76,13 +90,13 @@ SIGNATURES = {
 
 # kernels launched by one successful call (wm_interp_bwd runs its two gather passes)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
-KERNELS_PER_CALL["wm_resize_tables"] = 4
-KERNELS_PER_CALL["wm_set_store_epilogue"] = 0
+KERNELS_PER_CALL["wm_resize_tables"] = 6
 KERNELS_PER_CALL["wm_jpegcodec"] = 2
 KERNELS_PER_CALL["wm_cropresize_fwd"] = 2
 KERNELS_PER_CALL["wm_cropresize_bwd"] = 2
 # plain (non-status) helpers: name -> (restype, argtypes)
 HELPERS = {"wm_interp_is_tiled": (C.c_int, [i32, i32, i32, i32, i32]),
+           "wm_bank3_ok": (C.c_int, [i32, i32, i32]),
            "wm_resize_is_fused": (C.c_int, [i32, i32, i32, i32, i32]),
            "wm_resize_table_floats": (C.c_int64, [i32, i32, i32, i32]),
            "wm_cropresize_ok": (C.c_int, [i32, i32, i32, i32, i32, i32]),

@@ -118,16 +118,32 @@ def device_rng(enabled: bool = True, seed: Optional[int] = None) -> None:
     _dev_rng["on"] = bool(enabled)
     _dev_rng["state"].clear()
     _dev_rng["seed"] = seed
+    if enabled and torch.cuda.is_available():
+        # create the state of the current device NOW (eagerly, outside any capture): building it lazily inside a
+        # captured region would be an H2D copy during capture
+        _device_rng_state(torch.device("cuda", torch.cuda.current_device()))
 
 
-def _device_rng_slot(device, n_elems: int) -> torch.Tensor:
+def _device_rng_state(device) -> torch.Tensor:
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     key = str(device)
     st = _dev_rng["state"].get(key)
     if st is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"device_rng: no generator state on {key} yet and a CUDA graph is being captured — call "
+                               "functional.device_rng(True) with that device current before capturing")
         seed = _dev_rng.get("seed")
         seed = (torch.initial_seed() if seed is None else int(seed)) & 0x7FFFFFFFFFFFFFFF
         rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
         st = _dev_rng["state"][key] = torch.tensor([seed, rank << 44], dtype=torch.int64, device=device)
+        torch.cuda.current_stream(device).synchronize()        # visible to every stream that uses it later
+    return st
+
+
+def _device_rng_slot(device, n_elems: int) -> torch.Tensor:
+    st = _device_rng_state(device)
     slot = torch.empty(2, dtype=torch.int64, device=device)
     _lib.call("wm_rng_reserve", st.data_ptr(), slot.data_ptr(), (n_elems + 3) // 4 + 1, _stream())
     return slot
@@ -161,7 +177,8 @@ def _off(offset):
 # --------------------------------------------------------------------------------------
 
 def quality_to_factor(quality: float) -> float:
-    """utils/JPEG.py:487-498 (quality == 100 gives 0 and divides by zero downstream, as upstream)."""
+    """utils/JPEG.py:487-498.  quality == 100 gives factor 0: upstream divides by table * 0 and returns NaN images;
+    the kernels do the same (their clamps propagate NaN, tests/test_gpu_parity.py::test_nan_propagates_...)."""
     q = 5000.0 / quality if quality < 50 else 200.0 - quality * 2
     return q / 100.0
 
@@ -204,7 +221,7 @@ class _DiffJPEGFn(torch.autograd.Function):
             ctx.save_for_backward(d_y, d_c, codes)
             ctx.mode = "saved"
         else:
-            _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+            _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, None, _stream())
             if need_grad and rounding != ROUND_HARD:
                 ctx.save_for_backward(x, fps if fps is not None else torch.empty(0, device=x.device))
                 ctx.mode = "recompute"
@@ -304,7 +321,7 @@ class _Jpeg8Fn(torch.autograd.Function):
             ctx.save_for_backward(d)
             ctx.saved_d = True
             return y
-        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), _stream())
+        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), None, _stream())
         if params.variant == JPEG8_SS:
             ctx.save_for_backward(x)
         return y
@@ -376,7 +393,7 @@ class _BlurFn(torch.autograd.Function):
         b, c, h, w = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         arr = _taps_array(taps)
-        _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, y.data_ptr(), b * c, h, w, arr, len(taps), border, 0, _stream())
+        _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, y.data_ptr(), b * c, h, w, arr, len(taps), border, 0, None, _stream())
         ctx.meta = (tuple(taps), border)
         return y
 
@@ -387,7 +404,7 @@ class _BlurFn(torch.autograd.Function):
         b, c, h, w = gy.shape
         gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
         _lib.call("wm_gaussblur", gy.data_ptr(), sp, sh, gx.data_ptr(), b * c, h, w, _taps_array(taps), len(taps),
-                  border, 1, _stream())
+                  border, 1, None, _stream())
         return gx, None, None
 
 
@@ -408,7 +425,7 @@ class _MedianFn(torch.autograd.Function):
         b, c, h, w = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8) if need_idx else None
-        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), b * c, h, w, k, _stream())
+        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), b * c, h, w, k, None, _stream())
         ctx.k, ctx.w0 = k, w0
         if need_idx:
             ctx.save_for_backward(idx)
@@ -436,7 +453,7 @@ def median_blur_with_index(x: torch.Tensor, k: int):
     b, c, h, w = x.shape
     y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
     idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8)
-    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), idx.data_ptr(), b * c, h, w, k, _stream())
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), idx.data_ptr(), b * c, h, w, k, None, _stream())
     return y, idx
 
 
@@ -465,7 +482,7 @@ class _GaussNoiseFn(torch.autograd.Function):
             ctx.mode = "mask"
             return y
         _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, _off(offset),
-                  _ptr(inj), _stream())
+                  _ptr(inj), None, _stream())
         ctx.meta = (mean, std, int(clamp), seed, offset)
         if clamp:
             ctx.save_for_backward(x, inj if inj is not None else torch.empty(0, device=x.device))
@@ -665,8 +682,8 @@ def _interp_fwd(x, sp, sh, n, window, out_hw, mode, clamp, want_mask=False):
     mask = None
     if want_mask:
         mask = torch.empty((n, out_hw[0], (out_hw[1] + 31) // 32), device=x.device, dtype=torch.int32)
-    _lib.call("wm_interp_fwd", x.data_ptr(), sp, sh, h0, w0, hin, win, y.data_ptr(), n, out_hw[0], out_hw[1],
-              mode, int(clamp), _ptr(mask), _stream())
+    _lib.call("wm_interp_fwd", x.data_ptr(), sp, sh, src_hw[0], src_hw[1], h0, w0, hin, win, y.data_ptr(), n, out_hw[0],
+              out_hw[1], mode, int(clamp), _ptr(mask), _stream())
     return y, mask
 
 
@@ -739,16 +756,34 @@ def slice_window(shape, h_start, h_end, w_start, w_end):
 _RESIZE_TABLES: dict = {}      # (device, H, W, Hm, Wm, mode) -> device tensor of band tables (tiny, LRU-capped)
 
 
+_RESIZE_UNFUSED: set = set()   # geometries whose bands were found NOT to fit the fused kernel's windows
+
+
 def _resize_tables(device, h, w, mid_hw, mode):
+    """Band tables of one geometry, built ONCE and proven before first use: wm_resize_tables also runs, for both
+    directions, the fused kernel's window arithmetic over every tile position and sets a flag in the workspace's last
+    word if a band of U*D / its transpose would not fit (a weight outside a window would be dropped silently).  One
+    host sync per NEW geometry (a few small kernels); a geometry that does not fit is remembered and served by the
+    two-call path (returns None).  Completed (synchronised) before it enters the cache, so any stream may use it;
+    never built during CUDA-graph capture."""
     key = (str(device), h, w, mid_hw[0], mid_hw[1], mode)
     t = _RESIZE_TABLES.get(key)
-    if t is None:
-        if len(_RESIZE_TABLES) >= 256:
-            _RESIZE_TABLES.pop(next(iter(_RESIZE_TABLES)))
-        n = int(_lib.load().wm_resize_table_floats(h, w, mid_hw[0], mid_hw[1]))
-        t = torch.empty(n, device=device, dtype=torch.float32)
-        _lib.call("wm_resize_tables", t.data_ptr(), h, w, mid_hw[0], mid_hw[1], mode, _stream())
-        _RESIZE_TABLES[key] = t
+    if t is not None:
+        return t
+    if key in _RESIZE_UNFUSED:
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError(f"resize geometry {h}x{w} -> {mid_hw[0]}x{mid_hw[1]} has no cached band tables and a CUDA graph is "
+                           "being captured: run the layer once eagerly with this ratio before capturing")
+    if len(_RESIZE_TABLES) >= 1024:
+        _RESIZE_TABLES.pop(next(iter(_RESIZE_TABLES)))
+    n = int(_lib.load().wm_resize_table_floats(h, w, mid_hw[0], mid_hw[1]))
+    t = torch.empty(n, device=device, dtype=torch.float32)
+    _lib.call("wm_resize_tables", t.data_ptr(), h, w, mid_hw[0], mid_hw[1], mode, _stream())
+    if int(t[-4:].view(torch.int32)[0].item()) != 0:           # the one sync of this geometry
+        _RESIZE_UNFUSED.add(key)
+        return None
+    _RESIZE_TABLES[key] = t
     return t
 
 
@@ -761,11 +796,11 @@ class _ResizeFusedFn(torch.autograd.Function):
         x, sp, sh = _planes(x, "resize")
         b, c, h, w = x.shape
         n = b * c
-        tables = _resize_tables(x.device, h, w, mid_hw, mode)
+        tables = _resize_tables(x.device, h, w, mid_hw, mode)       # proven by resize_roundtrip before dispatching here
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         mask = torch.empty((n, h, 4 * ((w + 127) // 128)), device=x.device, dtype=torch.int32) if need_grad else None
         _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
-                  _ptr(mask), tables.data_ptr(), _stream())
+                  _ptr(mask), tables.data_ptr(), None, _stream())
         ctx.meta = (tuple(mid_hw), mode, (b, c, h, w))
         if need_grad:
             ctx.save_for_backward(mask, tables)
@@ -789,7 +824,8 @@ def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
     mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
     n = x.shape[0] * x.shape[1]
     if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and x.stride(2) % 4 == 0 and x.stride(1) % 4 == 0 \
-            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 \
+            and _resize_tables(x.device, h, w, mid_hw, _MODES[mode]) is not None:
         return _ResizeFusedFn.apply(x, mid_hw, _MODES[mode])
     mid = interpolate(x, mid_hw, mode)
     return interpolate(mid, (h, w), mode, clamp=True)
@@ -973,28 +1009,14 @@ def jpeg_codec(x: torch.Tensor, quality: int, subsampling: int = 2, value_range:
     return y, (yq[:, :, :wy], cq[0][:, :, :wcb], cq[1][:, :, :wcb])
 
 
-# ---- fused store epilogue: the attack kernel itself writes Quantization(x + (clamp(v) - x)) ---------
+# ---- fused store epilogue: the attack kernel itself writes Quantization(x + (clamp(v) - x)); the descriptor
+# travels as an explicit argument of the forward entry point (wm_store_epilogue), there is no hidden state
 
-def _armed(ep):
-    """ep = (x_dense, clamp, quantize) or None.  Arms the epilogue for the next forward launch."""
-    if ep is not None:
-        _lib.call("wm_set_store_epilogue", ep[0].data_ptr(), int(ep[1]), int(ep[2]))
-
-
-def _disarm():
-    _lib.call("wm_set_store_epilogue", None, 0, 0)
-
-
-def _call_armed(ep, name, *args):
-    """Arm the store epilogue, launch; if the launcher rejects the call before consuming the
-    descriptor, clear it so that it cannot leak into an unrelated later launch of this thread."""
-    _armed(ep)
-    try:
-        _lib.call(name, *args)
-    except BaseException:
-        if ep is not None:
-            _disarm()
-        raise
+def _ep_arg(ep):
+    """ep = (x_dense, clamp, quantize) or None -> the wm_store_epilogue argument of a forward entry point."""
+    if ep is None:
+        return None
+    return C.byref(_lib.StoreEpilogue(ep[0].data_ptr(), int(ep[1]), int(ep[2])))
 
 
 def _out_ok(out, shape):
@@ -1009,7 +1031,7 @@ def diffjpeg_into(x, factor, rounding, out, ep=None) -> bool:
     if c != 3 or h % 16 or w % 16 or not _out_ok(out, x.shape):
         return False
     fs, fps = _factor_args(factor, b, x.device)
-    _call_armed(ep, "wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
+    _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _ep_arg(ep), _stream())
     return True
 
 
@@ -1018,7 +1040,7 @@ def jpeg8_into(x, params, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if c != 3 or w % 8 or params.subsample != 0 or not _out_ok(out, x.shape):
         return False
-    _call_armed(ep, "wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _stream())
+    _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _ep_arg(ep), _stream())
     return True
 
 
@@ -1027,7 +1049,7 @@ def gaussian_blur_into(x, taps, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if len(taps) not in (3, 5, 7) or w % 4 or sp % 4 or sh % 4 or x.data_ptr() % 16 or not _out_ok(out, x.shape):
         return False
-    _call_armed(ep, "wm_gaussblur", x.data_ptr(), sp, sh, out.data_ptr(), b * c, h, w, _taps_array(taps), len(taps), 0, 0, _stream())
+    _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, out.data_ptr(), b * c, h, w, _taps_array(taps), len(taps), 0, 0, _ep_arg(ep), _stream())
     return True
 
 
@@ -1036,7 +1058,7 @@ def median_blur_into(x, k, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if k not in (3, 5) or sp % 4 or sh % 4 or x.data_ptr() % 16 or (k == 3 and w % 4) or not _out_ok(out, x.shape):
         return False
-    _call_armed(ep, "wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _stream())
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _ep_arg(ep), _stream())
     return True
 
 
@@ -1045,8 +1067,8 @@ def gaussian_noise_into(x, mean, std, clamp, out, ep=None) -> bool:
     if not _out_ok(out, x.shape):
         return False
     seed, offset = next_philox_stream(x.numel(), x.device)
-    _call_armed(ep, "wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
-              seed, _off(offset), None, _stream())
+    _lib.call("wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
+              seed, _off(offset), None, _ep_arg(ep), _stream())
     return True
 
 
@@ -1059,8 +1081,10 @@ def resize_roundtrip_into(x, mid_hw, mode, out, ep=None) -> bool:
             and x.data_ptr() % 16 == 0 and _out_ok(out, x.shape)):
         return False
     tables = _resize_tables(x.device, h, w, mid_hw, _MODES[mode])
-    _call_armed(ep, "wm_resize_fwd", x.data_ptr(), sp, sh, out.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], _MODES[mode],
-              None, tables.data_ptr(), _stream())
+    if tables is None:
+        return False
+    _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, out.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], _MODES[mode],
+              None, tables.data_ptr(), _ep_arg(ep), _stream())
     return True
 
 
@@ -1070,7 +1094,7 @@ class _BankFusedFn(torch.autograd.Function):
     finished by the stand-alone epilogue kernel.  Backward: straight-through, gx = sum_k gy_k."""
 
     @staticmethod
-    def forward(ctx, x, clamp, quantize, layers):
+    def forward(ctx, x, clamp, quantize, layers, shared_read=True):
         x = _flat(x.detach(), "attack bank")
         if x.data_ptr() % 32:
             x = x.clone()
@@ -1078,22 +1102,50 @@ class _BankFusedFn(torch.autograd.Function):
         out = torch.empty((k * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
         ep = (x, clamp, quantize)
         names = []
+        # 3x3-neighbourhood members (GaussianBlur(3), MiddleBlur(3), Gaussian, Identity) share ONE read of x:
+        # they are collected here and launched together (wm_bank3_fwd) after the loop; everything with a host-side
+        # random decision or a Philox reservation still happens at the layer's own position, in layer order
+        b_, c_, h_, w_ = x.shape
+        shared_ok = shared_read and x.dim() == 4 and bool(_lib.load().wm_bank3_ok(b_ * c_, h_, w_))
+        kinds = [getattr(layer, "bank3_kind", None) for layer in layers] if shared_ok else [None] * k
+        if len({kd for kd in kinds if kd}) < 2:
+            kinds = [None] * k                                       # a lone member keeps its own kernel
+        desc, taken, keep = _lib.Bank3Desc(), set(), []
         for i, layer in enumerate(layers):
             sl = out[i * x.shape[0]:(i + 1) * x.shape[0]]
+            kind = kinds[i]
+            if kind and kind not in taken:
+                taken.add(kind)
+                spec = layer.bank3_member()                          # (also renames the layer like its forward does)
+                if kind == "blur":
+                    desc.y_blur = sl.data_ptr()
+                    for j in range(3):
+                        desc.blur_taps[j] = float(spec[j])
+                elif kind == "median":
+                    desc.y_median = sl.data_ptr()
+                elif kind == "noise":
+                    seed, offset = next_philox_stream(n, x.device)
+                    keep.append(offset)                              # a reserved device slot must outlive the launch
+                    desc.y_noise = sl.data_ptr()
+                    desc.noise_mean, desc.noise_std, desc.noise_clamp = float(spec[0]), float(spec[1]), int(spec[2])
+                    desc.seed, desc.offset = seed, _off(offset)
+                else:
+                    desc.y_identity = sl.data_ptr()
+                names.append(getattr(layer, "name", type(layer).__name__))
+                continue
             fused = False
             into = getattr(layer, "forward_into", None)
             if into is not None:
-                try:
-                    fused = bool(into(x, sl, ep))
-                finally:
-                    if not fused:
-                        _disarm()
+                fused = bool(into(x, sl, ep))
             if not fused:
                 y = layer(x)
                 y = y[0] if isinstance(y, tuple) else y
                 _lib.call("wm_attack_epilogue_fwd", x.data_ptr(), _flat(y, "attack bank").data_ptr(), sl.data_ptr(), n,
                           int(clamp), int(quantize), _stream())
             names.append(getattr(layer, "name", type(layer).__name__))
+        if taken:
+            desc.clamp01, desc.quantize = int(clamp), int(quantize)
+            _lib.call("wm_bank3_fwd", x.data_ptr(), h_ * w_, w_, b_ * c_, h_, w_, C.byref(desc), _stream())
         ctx.meta = (k, tuple(x.shape))
         ctx.names = names
         return out
@@ -1104,8 +1156,8 @@ class _BankFusedFn(torch.autograd.Function):
         gy = _flat(gy, "attack bank backward")
         gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
         _lib.call("wm_slice_sum", gy.data_ptr(), gx.data_ptr(), gx.numel(), k, _stream())
-        return gx, None, None, None
+        return gx, None, None, None, None
 
 
-def attack_bank_fused(x, layers, clamp: bool = True, quantize: bool = True):
-    return _BankFusedFn.apply(x, clamp, quantize, list(layers))
+def attack_bank_fused(x, layers, clamp: bool = True, quantize: bool = True, shared_read: bool = True):
+    return _BankFusedFn.apply(x, clamp, quantize, list(layers), shared_read)

@@ -9,8 +9,6 @@ run makes the same choices; per-element randomness is generated in-kernel (Philo
 """
 from __future__ import annotations
 
-import math
-import os
 import random
 import string
 from typing import Optional, Sequence
@@ -95,6 +93,8 @@ def _identity_into(self, x, out, ep):
 
 
 Identity.forward_into = _identity_into
+Identity.bank3_kind = "identity"                 # member of the shared-read bank kernel (functional._BankFusedFn)
+Identity.bank3_member = lambda self: ()
 
 
 class Combined(nn.Module):
@@ -281,7 +281,12 @@ class JpegTest(nn.Module):
         self.name = "JpegTest" + str(Q)
 
     def forward(self, image):
-        return F_.jpeg_codec(_first(image), self.Q, self.subsample, "signed")
+        image = _first(image)
+        # upstream draws one temp-file name per frame from python's `random` (get_path, jpeg.py:17-18,32): consume
+        # the same numbers so that a seeded run keeps making the same Combined / get_random_int choices afterwards
+        for _ in range(image.shape[0]):
+            random.sample(string.ascii_letters + string.digits, 16)
+        return F_.jpeg_codec(image, self.Q, self.subsample, "signed")
 
 
 # ---- JpegCompression (noise_layers/jpeg_compression.py) --------------------------------------
@@ -343,6 +348,14 @@ class GaussianBlur(nn.Module):
             _set_name(self, "GaussianBlur")  # gaussian_blur.py:54 renames on first use
         return ok
 
+    @property
+    def bank3_kind(self):
+        return "blur" if self.kernel_size == 3 else None
+
+    def bank3_member(self):
+        _set_name(self, "GaussianBlur")
+        return self._taps
+
     def forward(self, tensor, cover_image=None):
         _set_name(self, "GaussianBlur")
         tensor = _first(tensor)
@@ -378,6 +391,13 @@ class MiddleBlur(nn.Module):
     def forward_into(self, x, out, ep):
         return F_.median_blur_into(x, self.kernel, out, ep)
 
+    @property
+    def bank3_kind(self):
+        return "median" if self.kernel == 3 else None
+
+    def bank3_member(self):
+        return ()
+
     def forward(self, image):
         return F_.median_blur(_first(image), self.kernel)
 
@@ -394,6 +414,14 @@ class Gaussian(nn.Module):
     def forward_into(self, x, out, ep):
         _set_name(self, "Gaussian")
         return F_.gaussian_noise_into(x, 0.0, 0.05, True, out, ep)
+
+    @property
+    def bank3_kind(self):
+        return None if self.host_rng else "noise"
+
+    def bank3_member(self):
+        _set_name(self, "Gaussian")
+        return (0.0, 0.05, True)
 
     def forward(self, tensor, cover_image=None, mean=0, stddev=0.05, noise=None):
         _set_name(self, "Gaussian")
@@ -668,11 +696,12 @@ class AttackBank(nn.Module):
         self.clamp, self.quantize = clamp, quantize
         self.names = []
         self.fused = True                 # False: run every layer plainly + the stand-alone epilogue kernel
+        self.shared_read = True           # 3x3-neighbourhood members read x ONCE (wm_bank3_fwd); False: one kernel each
 
     def forward(self, x):
         if self.fused:
             # the attack kernels write clamp + straight-through + Quantization in their own stores
-            y = F_._BankFusedFn.apply(x, self.clamp, self.quantize, self.list)
+            y = F_._BankFusedFn.apply(x, self.clamp, self.quantize, self.list, self.shared_read)
             self.names = [getattr(layer, "name", type(layer).__name__) for layer in self.list]
             return y
         with torch.no_grad():             # straight-through: the attacks' own graphs are never needed
