@@ -394,10 +394,20 @@ def test_median_forward_bit_exact(k):
     for xn in ("x2028", "xs32"):
         y = wmattack.MiddleBlur(k)(T(xn).to(DEV))
         assert torch.equal(y.cpu(), T(f"middleblur/k{k}/{xn}/y"))       # kornia semantics (unpinned)
-    for shape, seed in (((2, 3, 37, 150), 5), ((1, 3, 64, 256), 6), ((1, 1, 3, 2), 7), ((1, 2, 130, 131), 8)):
+    # 5x5 tiles are 36 rows of a plane PAIR: odd plane counts, heights around the tile size, a shifted bottom tile
+    for shape, seed in (((2, 3, 37, 150), 5), ((1, 3, 64, 256), 6), ((1, 1, 3, 2), 7), ((1, 2, 130, 131), 8),
+                        ((1, 3, 75, 140), 12), ((1, 1, 36, 132), 13), ((1, 5, 35, 8), 14), ((1, 1, 73, 260), 15)):
         x = rnd(shape, seed) - 0.3                      # negative values too
         y = wmattack.MiddleBlur(k)(x.to(DEV)).cpu()
         assert torch.equal(y, O.median_blur(x, k))
+        if shape[2] > 30:                               # arg-median plane too (ties at the zero border)
+            y, idx = WF.median_blur_with_index(x.to(DEV), k)
+            yo, io = O.median_blur(x, k, return_index=True)
+            assert torch.equal(y.cpu(), yo) and torch.equal(idx.cpu(), io)
+    # one frame of a [B, 3, T, H, W] clip, read in place through its strides
+    clip = rnd((2, 3, 3, 40, 64), 16).to(DEV)
+    y = wmattack.MiddleBlur(k)(clip[:, :, 1])
+    assert torch.equal(y.cpu(), O.median_blur(clip[:, :, 1].cpu().contiguous(), k))
     xq = torch.round(rnd((1, 3, 48, 160), 9) * 7) / 7   # heavy ties
     y, idx = WF.median_blur_with_index(xq.to(DEV), k)
     yo, io = O.median_blur(xq, k, return_index=True)

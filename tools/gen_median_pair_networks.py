@@ -132,7 +132,7 @@ class Problem:
         lines = []
         for (a, b), (la, lb) in zip(net, self.liveness(net)):
             if la and lb:
-                lines.append(f"    WM_CE({var}[{a}], {var}[{b}]);")
+                lines.append(f"    ce({var}[{a}], {var}[{b}]);")
             elif la:
                 lines.append(f"    {var}[{a}] = fminf({var}[{a}], {var}[{b}]);")
             elif lb:
@@ -167,21 +167,27 @@ def main():
 // All verified exhaustively with the 0-1 principle over every monotone 0/1 assignment of the sorted groups.
 #pragma once
 namespace wm {{
-#define WM_CE(a, b) {{ const float lo__ = fminf(a, b); b = fmaxf(a, b); a = lo__; }}
-__device__ __forceinline__ void mid6_of_4_sorted_rows(float (&v)[20]) {{
+// A compare-exchange is a functor (a, b) -> (min, max): CeMinMax is the plain FMNMX pair (2 ALU-pipe ops);
+// the kernels may pass one that computes the max on the FMA pipe instead (median.cu, CeIntSum).
+struct CeMinMax {{
+    __device__ __forceinline__ void operator()(float& a, float& b) const {{ const float lo = fminf(a, b); b = fmaxf(a, b); a = lo; }}
+}};
+template <class CE = CeMinMax>
+__device__ __forceinline__ void mid6_of_4_sorted_rows(float (&v)[20], const CE ce = CE()) {{
 {pa.body(na)}
 }}
 __device__ __forceinline__ float median11_sorted_6_5(float (&v)[11]) {{
 {pb.body(nb)}
     return v[5];
 }}
-__device__ __forceinline__ void merge10_sorted_5_5(float (&v)[10]) {{
+template <class CE = CeMinMax>
+__device__ __forceinline__ void merge10_sorted_5_5(float (&v)[10], const CE ce = CE()) {{
 {pm.body(nm)}
 }}
-__device__ __forceinline__ void mid6_of_2_sorted_10(float (&v)[20]) {{
+template <class CE = CeMinMax>
+__device__ __forceinline__ void mid6_of_2_sorted_10(float (&v)[20], const CE ce = CE()) {{
 {pc.body(nc)}
 }}
-#undef WM_CE
 }}  // namespace wm
 """
     here = os.path.dirname(os.path.abspath(__file__))

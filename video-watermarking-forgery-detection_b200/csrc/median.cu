@@ -43,13 +43,26 @@ __device__ __forceinline__ float feq(float a, float b) {
 __device__ __forceinline__ int first_match(float code, int n) {
     return n - 1 - ((__float_as_int(code) >> 23) - 127);
 }
-#define MD_CE(a, b) { const float lo__ = fminf(a, b); b = fmaxf(a, b); a = lo__; }
-__device__ __forceinline__ void sort5(float (&v)[5]) {
+
+// max(a, b) as a + b - min(a, b) on the bit patterns: two IMADs (FMA pipe) instead of one FMNMX (ALU pipe); see the
+// 5x5 kernel below.  one = +1 and neg1 = -1 must reach the kernel as launch parameters.
+struct CeIntSum {
+    int one, neg1;
+    __device__ __forceinline__ void operator()(float& a, float& b) const {
+        const float lo = fminf(a, b);
+        int s, h;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(s) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(b)));
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(h) : "r"(__float_as_int(lo)), "r"(neg1), "r"(s));
+        b = __int_as_float(h); a = lo;
+    }
+};
+template <class CE> __device__ __forceinline__ void sort5(float (&v)[5], const CE ce) {
     // optimal 9-comparator network
-    MD_CE(v[0], v[1]); MD_CE(v[3], v[4]); MD_CE(v[2], v[4]); MD_CE(v[2], v[3]); MD_CE(v[0], v[3]);
-    MD_CE(v[0], v[2]); MD_CE(v[1], v[4]); MD_CE(v[1], v[3]); MD_CE(v[1], v[2]);
+    ce(v[0], v[1]); ce(v[3], v[4]); ce(v[2], v[4]); ce(v[2], v[3]); ce(v[0], v[3]);
+    ce(v[0], v[2]); ce(v[1], v[4]); ce(v[1], v[3]); ce(v[1], v[2]);
 }
-#undef MD_CE
+template <bool INT> struct ce_pick { using type = CeMinMax; static __device__ __forceinline__ type make(int, int) { return type(); } };
+template <> struct ce_pick<true> { using type = CeIntSum; static __device__ __forceinline__ type make(int one, int neg1) { return type{one, neg1}; } };
 
 template <int K, bool WANT_IDX>
 __global__ void __launch_bounds__(MD_THREADS) median_fwd_kernel(const MedArgs a) {
@@ -78,7 +91,7 @@ __global__ void __launch_bounds__(MD_THREADS) median_fwd_kernel(const MedArgs a)
 #pragma unroll
         for (int c = 0; c < K; ++c) rows[j][c] = tile[(ly0 + j) * IW + lx + c];
         if constexpr (K == 3) sort3(rows[j][0], rows[j][1], rows[j][2]);
-        else sort5(rows[j]);
+        else sort5(rows[j], CeMinMax());
     }
 #pragma unroll
     for (int s = 0; s < MD_STRIP; ++s) {
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(MD_THREADS) median_fwd_kernel(const MedArgs a)
                        med3(rows[0][1], rows[1][1], rows[2][1]),
                        fmin3(rows[0][2], rows[1][2], rows[2][2]));
         } else {
-            sort5(rows[slot]);
+            sort5(rows[slot], CeMinMax());
             float v[25];
 #pragma unroll
             for (int j = 0; j < 5; ++j)
@@ -224,8 +237,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
     }
 }
 
-// 5x5 fast path: same TMA ring; one lane per column, two 36-row strips per tile.  A lane keeps the
-// last 6 window rows sorted (9-comparator network per row, shared by the 5 vertically adjacent
+// 5x5 fast path: same TMA ring, but a tile is 128 columns x 36 rows of TWO planes (one 3-D box): thread
+// (c, half) owns column c of plane 2m + half (the older layout, two 36-row strips of one 72-row tile, computed
+// ceil(H / 72) * 72 rows: 12.5 % more than the image at H = 512; this one at most 35 rows more, see m5_row0).
+// A lane keeps the last 6 window rows sorted (9-comparator network per row, shared by the 5 vertically adjacent
 // outputs) and produces TWO outputs per step: rows r and r+1 share four of their five window rows,
 // whose 20 values are reduced once to the six of rank 7..12 — the only ones that can be the median of
 // either window — and each output is then the median of those six and its own sorted row
@@ -233,11 +248,104 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
 // (r+1, r+2) of the next: 30 + 36 + 2 x 10 min/max per pair of outputs against 2 x 110 for the
 // single-output network of median_net.cuh).  The raw rows stay in registers for the arg-median search.  The row loop
 // is unrolled by 3 pairs so that ring slots are compile-time indices.
-constexpr int M5_TW = 128, M5_TH = 72, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_TH + 4,
-              M5_THREADS = 256, M5_ROWS = 36, M5_STAGES = 2, M5_STRIDE = ((M5_BW * M5_BH + 31) / 32) * 32;
+//
+// The kernel is bound by the ALU pipe (FMNMX, FSET) and then by instruction issue, not by HBM (ncu: ALU 89 %, FMA
+// 16 %, DRAM 14 %).  A compare-exchange therefore computes only its MIN with FMNMX; the max is a + b - min on the bit
+// patterns, two IMADs on the otherwise idle FMA pipe (CeIntSum; the +1 / -1 multipliers are kernel parameters so
+// that ptxas cannot fold them back into an ALU-pipe IADD3, and sit in uniform registers: two vector operands per
+// IMAD, no register-bank stalls).  Bit-exact: the result is the other operand's bit pattern by construction.
+constexpr int M5_TW = 128, M5_ROWS = 36, M5_HALO = 4, M5_BW = M5_TW + 2 * M5_HALO, M5_BH = M5_ROWS + 4,
+              M5_THREADS = 256, M5_STAGES = 2, M5_STRIDE = 2 * M5_BW * M5_BH;
+static_assert(M5_ROWS % 6 == 0 && (M5_STRIDE * sizeof(float)) % 128 == 0, "ring slots / stage alignment");
+
+// First image row of tile row ty.  The row loop has a COMPILE-TIME trip count (with a data-dependent one ptxas moves the
+// comparator multipliers out of the uniform registers and the kernel stalls on register banks: 294 -> 320 us), so the
+// bottom tile is not cut short but shifted up to end at the image's last row; the rows it shares with the tile above
+// are computed twice and written twice with identical bits.
+__host__ __device__ __forceinline__ int m5_row0(int ty, int H) {
+    const int r = ty * M5_ROWS, last = H > M5_ROWS ? H - M5_ROWS : 0;
+    return r < last ? r : last;
+}
+
+struct Med5Args {
+    float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
+    int one, neg1;
+    StoreEp ep;
+};
+
+// One 128 x 36 tile of one plane: `col` = the lane's window column in the staged box (row 0 = image row gy0 - 2).
+template <bool WANT_IDX, bool EP>
+__device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col, int64_t obase, int rows_ok) {
+    // with the arg-median search on the ALU pipe too, every comparator moves its max to the FMA pipe; without it the
+    // last network keeps plain FMNMX pairs (measured: 338 -> 261 us with, 231 -> 172 us without the plane at 64x3x504x512)
+    const auto ce_s = ce_pick<true>::make(a.one, a.neg1);
+    const auto ce_c = ce_pick<WANT_IDX>::make(a.one, a.neg1);
+    float srt[6][5], raw[WANT_IDX ? 6 : 1][5];
+    auto load_row = [&](int row, int slot) {
+        const float* p = col + row * M5_BW;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            srt[slot][k] = p[k];
+            if (WANT_IDX) raw[slot][k] = srt[slot][k];
+        }
+        sort5(srt[slot], ce_s);
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) load_row(j, j);
+    float* const yb = a.y + obase;
+    uint8_t* const ib = WANT_IDX ? a.idx + obase : nullptr;
+    int off = 0;
+    float mp[10];                                      // rows r+1, r+2 merged (kept from the previous step)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { mp[k] = srt[1][k]; mp[5 + k] = srt[2][k]; }
+    merge10_sorted_5_5(mp, ce_s);
+#pragma unroll 1
+    for (int r0 = 0; r0 < M5_ROWS; r0 += 6) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            // outputs r and r + 1 share the window rows r+1 .. r+4 (ring slots are compile-time: r0 % 6 == 0)
+            const int r = r0 + 2 * u;
+            load_row(r + 4, (2 * u + 4) % 6);
+            load_row(r + 5, (2 * u + 5) % 6);
+            float mq[10], v[20];                       // rows r+3, r+4 merged: the next step's (r+1, r+2)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { mq[k] = srt[(2 * u + 3) % 6][k]; mq[5 + k] = srt[(2 * u + 4) % 6][k]; }
+            merge10_sorted_5_5(mq, ce_s);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { v[k] = mp[k]; v[10 + k] = mq[k]; mp[k] = mq[k]; }
+            mid6_of_2_sorted_10(v, ce_c);              // v[7..12]: the only shared values that can be a median
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int own = (2 * u + (o ? 5 : 0)) % 6;
+                float w[11];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[k] = v[7 + k];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) w[6 + k] = srt[own][k];
+                const float med = median11_sorted_6_5(w);
+                int pos = 0;
+                if (WANT_IDX) {
+                    float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
+#pragma unroll
+                    for (int j = 0; j < 15; ++j)       // window row j/5 of output r + o is ring slot (2u + o + j/5) % 6
+                        hi = fmaf(hi, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
+#pragma unroll
+                    for (int j = 15; j < 25; ++j)
+                        lo = fmaf(lo, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
+                    pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
+                }
+                if (r + o < rows_ok) {
+                    yb[off] = EP ? ep_apply(med, a.ep.from_input ? col[(r + o + 2) * M5_BW + 2] : a.ep.x[obase + off], a.ep) : med;
+                    if (WANT_IDX) ib[off] = (uint8_t)pos;
+                }
+                off += a.W;
+            }
+        }
+    }
+}
 
 template <bool WANT_IDX, bool EP>
-__global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
+__global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Med5Args a) {
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[M5_STAGES];
     const int tid = threadIdx.x;
@@ -250,10 +358,10 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
     __syncthreads();
     const int per_plane = a.tiles_x * a.tiles_y;
     auto issue = [&](int64_t t, int s) {
-        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int m = int(t / per_plane), rem = int(t - int64_t(m) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], M5_BW * M5_BH * sizeof(float));
-        tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, ty * M5_TH - 2, n, &full[s]);
+        mbar_expect_tx(&full[s], M5_STRIDE * sizeof(float));
+        tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, m5_row0(ty, a.H) - 2, 2 * m, &full[s]);
     };
     if (tid == 0) {
 #pragma unroll
@@ -262,75 +370,19 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
             if (t < a.total) issue(t, s);
         }
     }
-    const int c = tid & 127, strip = tid >> 7;
+    const int c = tid & 127, half = tid >> 7;
     int it = 0;
     for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
         const int s = it % M5_STAGES;
         mbar_wait(&full[s], (it / M5_STAGES) & 1);
-        const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
+        const int m = int(t / per_plane), rem = int(t - int64_t(m) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        const int gx = tx * M5_TW + c, gy0 = ty * M5_TH + strip * M5_ROWS;
-        const float* col = bufs + s * M5_STRIDE + (strip * M5_ROWS) * M5_BW + M5_HALO - 2 + c;
-        float srt[6][5], raw[WANT_IDX ? 6 : 1][5];
-        auto load_row = [&](int row, int slot) {
-            const float* p = col + row * M5_BW;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                srt[slot][k] = p[k];
-                if (WANT_IDX) raw[slot][k] = srt[slot][k];
-            }
-            sort5(srt[slot]);
-        };
-#pragma unroll
-        for (int j = 0; j < 4; ++j) load_row(j, j);
-        const bool col_ok = gx < a.W;
+        const int n = 2 * m + half, gx = tx * M5_TW + c, gy0 = m5_row0(ty, a.H);
+        const int rows_tile = min(M5_ROWS, a.H - gy0);
+        const float* col = bufs + s * M5_STRIDE + half * (M5_BW * M5_BH) + M5_HALO - 2 + c;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
-        float mp[10];                                      // rows r+1, r+2 merged (kept from the previous step)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { mp[k] = srt[1][k]; mp[5 + k] = srt[2][k]; }
-        merge10_sorted_5_5(mp);
-#pragma unroll 1
-        for (int r0 = 0; r0 < M5_ROWS; r0 += 6) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                // outputs r and r + 1 share the window rows r+1 .. r+4 (ring slots are compile-time: r0 % 6 == 0)
-                const int r = r0 + 2 * u;
-                load_row(r + 4, (2 * u + 4) % 6);
-                load_row(r + 5, (2 * u + 5) % 6);
-                float mq[10], v[20];                       // rows r+3, r+4 merged: the next step's (r+1, r+2)
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { mq[k] = srt[(2 * u + 3) % 6][k]; mq[5 + k] = srt[(2 * u + 4) % 6][k]; }
-                merge10_sorted_5_5(mq);
-#pragma unroll
-                for (int k = 0; k < 10; ++k) { v[k] = mp[k]; v[10 + k] = mq[k]; mp[k] = mq[k]; }
-                mid6_of_2_sorted_10(v);                    // v[7..12]: the only shared values that can be a median
-#pragma unroll
-                for (int o = 0; o < 2; ++o) {
-                    const int rr = r + o, own = (2 * u + (o ? 5 : 0)) % 6;
-                    float w[11];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) w[k] = v[7 + k];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) w[6 + k] = srt[own][k];
-                    const float med = median11_sorted_6_5(w);
-                    if (col_ok && gy0 + rr < a.H) {
-                        a.y[obase + int64_t(rr) * a.W] =
-                            EP ? ep_apply(med, a.ep.from_input ? col[(rr + 2) * M5_BW + 2] : a.ep.x[obase + int64_t(rr) * a.W], a.ep) : med;
-                        if (WANT_IDX) {
-                            float hi = 0.f, lo = 0.f;          // rows 0-2 (15 bits) and rows 3-4 (10 bits)
-#pragma unroll
-                            for (int j = 0; j < 15; ++j)       // window row j/5 of output rr is ring slot (2u + o + j/5) % 6
-                                hi = fmaf(hi, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
-#pragma unroll
-                            for (int j = 15; j < 25; ++j)
-                                lo = fmaf(lo, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
-                            const int pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
-                            a.idx[obase + int64_t(rr) * a.W] = (uint8_t)pos;
-                        }
-                    }
-                }
-            }
-        }
+        const int rows_ok = (gx < a.W && n < a.N) ? rows_tile : 0;          // this lane stores output rows r < rows_ok
+        median5_tile<WANT_IDX, EP>(a, col, obase, rows_ok);
         __syncthreads();
         if (tid == 0) {
             const int64_t t2 = t + int64_t(M5_STAGES) * gridDim.x;
@@ -528,12 +580,12 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
     }
     if (k == 5 && tmap_ok(x, x_sp, x_sh, 4)) {
         CUtensorMap tm;
-        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, M5_BW, M5_BH)) {
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, M5_BW, M5_BH, 2)) {
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_TH - 1) / M5_TH, 0, StoreEp{nullptr, 0, 0, 0}};
-        ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        Med5Args ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_ROWS - 1) / M5_ROWS, 0, 1, -1, StoreEp{nullptr, 0, 0, 0}};
+        ta.total = int64_t((N + 1) / 2) * ta.tiles_x * ta.tiles_y;
         ta.ep = make_store_ep(ep);
         ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
         const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;

@@ -39,13 +39,13 @@ inline bool tmap_ok(const void* base, int64_t sp, int64_t sh, size_t elem) {
     return aligned(base, 16) && (sh * (int64_t)elem) % 16 == 0 && (sp * (int64_t)elem) % 16 == 0 && tmap_encoder() != nullptr;
 }
 
-// 3-D map over planes: dim0 = W (innermost), dim1 = H, dim2 = N; box = (box_w, box_h, 1).
+// 3-D map over planes: dim0 = W (innermost), dim1 = H, dim2 = N; box = (box_w, box_h, box_n).
 // Returns 0 on success (CUresult otherwise).
 inline int tmap_planes(CUtensorMap* m, CUtensorMapDataType dt, size_t elem, const void* base, int N, int H, int W,
-                       int64_t sp, int64_t sh, int box_w, int box_h) {
+                       int64_t sp, int64_t sh, int box_w, int box_h, int box_n = 1) {
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[2] = {(cuuint64_t)(sh * (int64_t)elem), (cuuint64_t)(sp * (int64_t)elem)};
-    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     auto enc = [&]() {
         return (int)tmap_encoder()(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
