@@ -298,7 +298,7 @@ def _run_network(path, func, values):
     v = list(values)
     for ln in body.split("\n"):
         ln = ln.strip()
-        m = re.match(r"WM_CE\(v\[(\d+)\], v\[(\d+)\]\);", ln)
+        m = re.match(r"(?:WM_CE|ce)\(v\[(\d+)\], v\[(\d+)\]\);", ln)
         if m:
             a, b = int(m[1]), int(m[2])
             v[a], v[b] = min(v[a], v[b]), max(v[a], v[b])
