@@ -80,21 +80,28 @@ __global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* _
     resolve_rng(seed, offset);
     const Philox ph(seed);
     const int lane = threadIdx.x & 31;
-    for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 4; base < n;
-         base += int64_t(gridDim.x) * blockDim.x * 4) {               // warp-uniform trip count (ballots below)
-        const int64_t i = base + 4 * lane;
-        const float4 xv = ld4(x, i, n);             // requested first: the latency hides under Philox + Box-Muller
-        float4 nz;
-        if (inject) nz = ld4(inject, i, n);
-        else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
-               nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
-        const float4 v = make_float4(xv.x + nz.x, xv.y + nz.y, xv.z + nz.z, xv.w + nz.w);
-        const float4 c = clamp01_nan4(v);           // NaN propagates (torch.clamp)
-        st4(out, i, n, c);
-        // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN, like torch.clamp's backward mask)
-        const unsigned b0 = __ballot_sync(0xffffffffu, c.x == v.x), b1 = __ballot_sync(0xffffffffu, c.y == v.y);
-        const unsigned b2 = __ballot_sync(0xffffffffu, c.z == v.z), b3 = __ballot_sync(0xffffffffu, c.w == v.w);
-        if (lane == 0) *reinterpret_cast<uint4*>(maskbits + (base >> 7) * 4) = make_uint4(b0, b1, b2, b3);
+    // a warp takes 256 consecutive values per step as two independent 128-value halves: the kernel is bound by
+    // instruction issue (Philox + Box-Muller), and the second half shares the loop and index arithmetic of the first
+    for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 8; base < n;
+         base += int64_t(gridDim.x) * blockDim.x * 8) {               // warp-uniform trip count (ballots below)
+        float4 xv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) xv[h] = ld4(x, base + 128 * h + 4 * lane, n);    // requested first: the latency hides under Philox
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = base + 128 * h + 4 * lane;
+            float4 nz;
+            if (inject) nz = ld4(inject, i, n);
+            else { nz = normal4(ph, (uint64_t)(i >> 2) + offset);
+                   nz.x = fmaf(nz.x, std, mean); nz.y = fmaf(nz.y, std, mean); nz.z = fmaf(nz.z, std, mean); nz.w = fmaf(nz.w, std, mean); }
+            const float4 v = make_float4(xv[h].x + nz.x, xv[h].y + nz.y, xv[h].z + nz.z, xv[h].w + nz.w);
+            const float4 c = clamp01_nan4(v);           // NaN propagates (torch.clamp)
+            st4(out, i, n, c);
+            // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN, like torch.clamp's backward mask)
+            const unsigned b0 = __ballot_sync(0xffffffffu, c.x == v.x), b1 = __ballot_sync(0xffffffffu, c.y == v.y);
+            const unsigned b2 = __ballot_sync(0xffffffffu, c.z == v.z), b3 = __ballot_sync(0xffffffffu, c.w == v.w);
+            if (lane == 0 && base + 128 * h < n) *reinterpret_cast<uint4*>(maskbits + ((base >> 7) + h) * 4) = make_uint4(b0, b1, b2, b3);
+        }
     }
 }
 __global__ void __launch_bounds__(256) gaussnoise_mask_bwd_kernel(const float* __restrict__ gy, const uint32_t* __restrict__ maskbits,
@@ -368,7 +375,7 @@ extern "C" int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbi
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && maskbits, WM_E_NULL, "wm_gaussnoise_fwd_mask: null pointer");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd_mask", x, y, inject, maskbits);
-    gaussnoise_mask_fwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, maskbits, n, mean, std, seed, offset, inject);
+    gaussnoise_mask_fwd_kernel<<<ew_grid((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, maskbits, n, mean, std, seed, offset, inject);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd_mask");
     return WM_OK;
 }

@@ -145,7 +145,19 @@ constexpr int MT_TW = 128, MT_TH = 64, MT_HALO = 4, MT_BW = MT_TW + 2 * MT_HALO,
 struct MedTArgs {
     float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
     StoreEp ep;
+    int one, neg1;      // +1 / -1 as launch parameters (FMA-pipe integer sums, see CeIntSum)
 };
+// middle of three as a + b + c - min - max on the bit patterns: four IMADs on the FMA pipe instead of two LOP3 on the
+// ALU pipe, which the arg-median search saturates (102 -> 96 us at 64x3x512x512 with the plane; without it the
+// kernel is HBM-bound and keeps the XOR form)
+__device__ __forceinline__ float mid3_sum(float a, float b, float c, float lo, float hi, int one, int neg1) {
+    int s;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(s) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(b)));
+    asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(__float_as_int(c)), "r"(one));
+    asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(__float_as_int(lo)), "r"(neg1));
+    asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(__float_as_int(hi)), "r"(neg1));
+    return __int_as_float(s);
+}
 
 template <bool WANT_IDX, bool EP>
 __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
@@ -207,9 +219,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
             uint32_t packed = 0;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-                const float med = med3(fmax3(lo[0][c4], lo[1][c4], lo[2][c4]),
-                                       med3(mi[0][c4], mi[1][c4], mi[2][c4]),
-                                       fmin3(hi[0][c4], hi[1][c4], hi[2][c4]));
+                const float m0 = mi[0][c4], m1 = mi[1][c4], m2 = mi[2][c4];
+                const float A = fmax3(lo[0][c4], lo[1][c4], lo[2][c4]), C = fmin3(hi[0][c4], hi[1][c4], hi[2][c4]);
+                float med;
+                if (WANT_IDX) {
+                    const float B = mid3_sum(m0, m1, m2, fmin3(m0, m1, m2), fmax3(m0, m1, m2), a.one, a.neg1);
+                    med = mid3_sum(A, B, C, fmin3(A, B, C), fmax3(A, B, C), a.one, a.neg1);
+                } else {
+                    med = med3(A, med3(m0, m1, m2), C);
+                }
                 op[c4] = med;
                 if (WANT_IDX) {
                     float code = 0.f;
@@ -564,7 +582,7 @@ extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0, 0}};
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0, 0}, 1, -1};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
         ta.ep = make_store_ep(ep);
         ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;

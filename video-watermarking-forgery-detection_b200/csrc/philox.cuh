@@ -42,13 +42,15 @@ __device__ __forceinline__ float4 uniform4(const Philox& ph, uint64_t ctr) {
 }
 __device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t ctr) {
     const uint4 r = ph(ctr);
-    // Box-Muller on (0,1] x [0,1)
-    const float u1 = ((r.x >> 8) + 1) * (1.0f / 16777216.0f), u2 = u01(r.y);
-    const float u3 = ((r.z >> 8) + 1) * (1.0f / 16777216.0f), u4 = u01(r.w);
-    // sqrt.approx (MUFU.SQRT, max 1 ulp): the radius of a RANDOM draw needs no IEEE rounding
+    // Box-Muller on (0,1] x [0,1].  Radius uniforms (r + 0.5) * 2^-32: one unsigned conversion + one FFMA (the conversion
+    // rounds, 2^32 - 1 lands on 1.0, 0 on 2^-33: radius <= 6.8 sigma); angle uniforms r * 2^-32.
+    const float u1 = fmaf(__uint2float_rn(r.x), 0x1p-32f, 0x1p-33f), u2 = __uint2float_rn(r.y) * 0x1p-32f;
+    const float u3 = fmaf(__uint2float_rn(r.z), 0x1p-32f, 0x1p-33f), u4 = __uint2float_rn(r.w) * 0x1p-32f;
+    // -2 ln u = (-2 ln 2) log2 u: MUFU.LG2 + one FMUL; sqrt.approx (MUFU.SQRT, max 1 ulp): the radius of a RANDOM draw
+    // needs no IEEE rounding
     float ra, rb;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-2.f * __logf(u1)));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-2.f * __logf(u3)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-1.3862943611198906f * __log2f(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-1.3862943611198906f * __log2f(u3)));
     float s1, c1, s2, c2;
     __sincosf(6.283185307179586f * u2, &s1, &c1);
     __sincosf(6.283185307179586f * u4, &s2, &c2);
