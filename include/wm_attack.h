@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WM_ABI_VERSION 2
+#define WM_ABI_VERSION 3
 
 #define WM_OK 0
 #define WM_E_NULL (-1)      /* required pointer is NULL */
@@ -40,6 +40,13 @@ extern "C" {
 #define WM_ROUND_CUBIC 1     /* utils/JPEG.py:472 diff_round */
 #define WM_ROUND_HARD 2      /* torch.round (half to even) */
 #define WM_ROUND_FOURIER 3   /* utils/JPEG_utils.py:36 diff_round (9-term Fourier series) */
+
+/* element types of the tensors that cross the boundary in reduced precision (autocast, models/IRNcrop_model.py:340):
+ * the entry points that take a `*_dtype` argument read that type directly / store the input gradient in it (cast fused
+ * into the kernel's load / store, round-to-nearest-even as torch's .to()); all arithmetic stays float32 */
+#define WM_DT_F32 0
+#define WM_DT_F16 1
+#define WM_DT_BF16 2
 
 int wm_version(void);
 const char* wm_last_error(void);
@@ -60,21 +67,22 @@ typedef struct wm_store_epilogue {
 
 /* ------------------------------------------------------------------------------------------
  * DiffJPEG  —  utils/JPEG.py:501-540 (compress_jpeg :256-291, decompress_jpeg :431-469)
- *   x: [B,3,H,W] in [0,1], strides (x_sb, x_sc, x_sh) in elements, multiples of 8, base
- *      pointer 32-byte aligned; H, W multiples of 16.
+ *   x: [B,3,H,W] in [0,1] of x_dtype elements (WM_DT_*), strides (x_sb, x_sc, x_sh) in elements, multiples of
+ *      8, base pointer aligned to 8 elements (32 bytes for float32); H, W multiples of 16.  y is float32; the
+ *      backward entry points store gx as gx_dtype elements (dense NCHW).
  *   factor: quality_to_factor(quality) (utils/JPEG.py:487); if factor_per_sample != NULL it
  *      is a device array [B] that overrides `factor` per image (quality sweep extension).
  * ------------------------------------------------------------------------------------------ */
-int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+int wm_diffjpeg_fwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                     float* y, int B, int H, int W,
                     float factor, const float* factor_per_sample, int rounding,
                     const wm_store_epilogue* ep, void* stream);
 
 /* gx = d<gy, DiffJPEG(x)>/dx, recomputed from x (nothing saved by the forward).
  * Replaces autograd over the ~30 saved activations of the reference graph. */
-int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+int wm_diffjpeg_bwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                     const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
-                    float* gx, int B, int H, int W,
+                    void* gx, int gx_dtype, int B, int H, int W,
                     float factor, const float* factor_per_sample, int rounding, void* stream);
 
 /* Training pair: the forward additionally saves 7 B/px of state — round'(q) of every luminance
@@ -82,11 +90,11 @@ int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
  * 2 on a bound) of every output value (clamp_codes [B,H,W/8], 48 bits per 8-pixel row) — and the
  * backward runs from gy + that state alone (no x, no forward recomputation; 31 B/px each way,
  * every rounding mode).  The layouts are private to this pair. */
-int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
+int wm_diffjpeg_fwd_save(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                          float* dY, float* dC, uint64_t* clamp_codes, int B, int H, int W,
                          float factor, const float* factor_per_sample, int rounding, void* stream);
 int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
-                          const float* dY, const float* dC, const uint64_t* clamp_codes, float* gx,
+                          const float* dY, const float* dC, const uint64_t* clamp_codes, void* gx, int gx_dtype,
                           int B, int H, int W, void* stream);
 
 /* compress_jpeg.forward (utils/JPEG.py:279-291): rounded quantised coefficients,

@@ -231,7 +231,7 @@ def test_diffjpeg_errors():
         wmattack.DiffJPEG(True, 32, 32, 50)(torch.rand(1, 1, 32, 32, device=DEV))
     from wmattack import _lib
     with pytest.raises(_lib.WMAttackError):
-        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
+        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
 
 
 def test_diffjpeg_full_size_properties():
@@ -387,6 +387,29 @@ def test_gaussian_blur_and_gf_vs_oracle(shape):
         yo, go = oracle_fwd_bwd(lambda t: O.gaussian_filter_reflect(t, k, 1.5), x, g)
         assert md(y, yo) <= 1e-6 and md(gx, go) <= 1e-6
     assert md(wmattack.GF(1.5, 7)((T("x2028").to(DEV), None)), T("gf/s1.5k7/x2028/y")) <= 1e-6
+
+
+@pytest.mark.parametrize("dt", (torch.bfloat16, torch.float16))
+def test_diffjpeg_reads_half_inputs_and_stores_half_gradients(dt):
+    """Autocast boundary (models/IRNcrop_model.py:340): a float16 / bfloat16 image is read as it is and the input
+    gradient leaves in that type — bit-identical to casting outside the kernels (x.float() in, gx.to(dt) out)."""
+    x = rnd((2, 3, 64, 96), 21).to(DEV).to(dt)
+    g = rnd((2, 3, 64, 96), 22).to(DEV)
+    for recompute in (False, True):
+        m = wmattack.DiffJPEG(True, 64, 96, quality=50)
+        m.recompute_backward = recompute
+        xa = x.clone().requires_grad_(True)
+        ya = m(xa)
+        ya.backward(g)
+        xb = x.float().requires_grad_(True)
+        yb = m(xb)
+        yb.backward(g)
+        assert ya.dtype == torch.float32 and torch.equal(ya, yb)
+        assert xa.grad.dtype == dt and torch.equal(xa.grad, xb.grad.to(dt))
+    with torch.no_grad():                                   # forward-only kernel, strided clip slice
+        clip = rnd((2, 3, 2, 32, 64), 23).to(DEV).to(dt)
+        m = wmattack.DiffJPEG(True, 32, 64, quality=75)
+        assert torch.equal(m(clip[:, :, 1]), m(clip[:, :, 1].float()))
 
 
 @pytest.mark.parametrize("k", (3, 5))

@@ -38,18 +38,18 @@ def test_library_exports_every_header_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"libwmattack.so does not export {n}"
     assert set(_lib.SIGNATURES) | set(_lib.HELPERS) == names - {"wm_version", "wm_last_error"}
-    assert lib.wm_version() == 2
+    assert lib.wm_version() == 3
     assert isinstance(lib.wm_last_error(), bytes)
 
 
 def test_invalid_arguments_fail_loudly_without_a_gpu(lib):
     # argument validation happens before any CUDA call, so it is testable on a CPU box
     with pytest.raises(_lib.WMAttackError, match="null"):
-        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
+        _lib.call("wm_diffjpeg_fwd", None, 0, 0, 0, 0, None, 1, 32, 32, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="multiples of 16"):
-        _lib.call("wm_diffjpeg_fwd", 256, 8, 8, 8, 256, 1, 24, 24, 1.0, None, 0, None, None)
+        _lib.call("wm_diffjpeg_fwd", 256, 0, 8, 8, 8, 256, 1, 24, 24, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="aligned"):
-        _lib.call("wm_diffjpeg_fwd", 260, 8, 8, 8, 256, 1, 32, 32, 1.0, None, 0, None, None)
+        _lib.call("wm_diffjpeg_fwd", 260, 0, 8, 8, 8, 256, 1, 32, 32, 1.0, None, 0, None, None)
     with pytest.raises(_lib.WMAttackError, match="kernel size"):
         _lib.call("wm_median_fwd", 256, 0, 0, 256, None, 1, 8, 8, 4, None, None)
     with pytest.raises(_lib.WMAttackError, match="odd"):
@@ -63,7 +63,7 @@ def test_invalid_arguments_fail_loudly_without_a_gpu(lib):
     ep = _lib.StoreEpilogue(260, 1, 1)
     import ctypes
     with pytest.raises(_lib.WMAttackError, match="epilogue"):
-        _lib.call("wm_diffjpeg_fwd", 256, 3072, 1024, 32, 256, 1, 32, 32, 1.0, None, 0, ctypes.byref(ep), None)
+        _lib.call("wm_diffjpeg_fwd", 256, 0, 3072, 1024, 32, 256, 1, 32, 32, 1.0, None, 0, ctypes.byref(ep), None)
     ep = _lib.StoreEpilogue(256, 1, 1)
     with pytest.raises(_lib.WMAttackError, match="does not apply"):
         taps = (_lib.f32 * 9)(*([1 / 9] * 9))                      # k = 9: generic blur path

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
 #pragma unroll 1
     for (int rp = 0; rp < 4; ++rp) {
         RowPair g;
-        dj_load_pair(g, gr + int64_t(2 * rp) * a.g_sh, a.g_sh, a.g_sc, t.active);
+        dj_load_pair(g, gr, int64_t(2 * rp) * a.g_sh, a.g_sh, a.g_sc, t.active);
         float cb[4], cr[4], tR[4], tG[4], tB[4], gcb[4], gcr[4];
         f4_to(cb, scr[(SC_CB + rp) * NT]);
         f4_to(cr, scr[(SC_CR + rp) * NT]);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
     }
 
     // ---- back through the colour transform ----------------------------------------------------
-    float* go = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
+    const int64_t go = (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;       // element offset into gx (a.out_dt elements)
     const int64_t plane = int64_t(a.H) * a.W;
 #pragma unroll 1
     for (int rp = 0; rp < 4; ++rp) {
@@ -145,10 +145,10 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
                 oB.v[c] = fmaf(0.114f, gv[c], tB[c >> 1]);
             }
             if (t.active) {
-                float* p = go + int64_t(r) * a.W;
-                stg256(p, oR);
-                stg256(p + plane, oG);
-                stg256(p + 2 * plane, oB);
+                const int64_t p = go + int64_t(r) * a.W;
+                st8_typed(a.out, p, oR, a.out_dt);
+                st8_typed(a.out, p + plane, oG, a.out_dt);
+                st8_typed(a.out, p + 2 * plane, oB, a.out_dt);
             }
         }
     }
@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const
     };
     {
         RowPair A, Bp;          // one pair of loads in flight ahead of the arithmetic
-        dj_load_pair(A, gr, a.g_sh, a.g_sc, t.active);
+        dj_load_pair(A, gr, 0, a.g_sh, a.g_sc, t.active);
 #pragma unroll 1
         for (int rp = 0; rp < 4; ++rp) {
-            if (rp < 3) dj_load_pair(Bp, gr + int64_t(2 * rp + 2) * a.g_sh, a.g_sh, a.g_sc, t.active);
+            if (rp < 3) dj_load_pair(Bp, gr, int64_t(2 * rp + 2) * a.g_sh, a.g_sh, a.g_sc, t.active);
             consume(A, rp);
             A = Bp;
         }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const
     }
 
     // ---- back through the colour transform ----------------------------------------------------
-    float* go = a.out + (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;
+    const int64_t go = (int64_t(t.b) * 3 * a.H + t.row0) * a.W + t.col0;       // element offset into gx (a.out_dt elements)
     const int64_t plane = int64_t(a.H) * a.W;
 #pragma unroll 1
     for (int rp = 0; rp < 4; ++rp) {
@@ -284,10 +284,10 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const
                 oB.v[c] = fmaf(0.114f, gv[c], tB[c >> 1]);
             }
             if (t.active) {
-                float* p = go + int64_t(r) * a.W;
-                stg256(p, oR);
-                stg256(p + plane, oG);
-                stg256(p + 2 * plane, oB);
+                const int64_t p = go + int64_t(r) * a.W;
+                st8_typed(a.out, p, oR, a.out_dt);
+                st8_typed(a.out, p + plane, oG, a.out_dt);
+                st8_typed(a.out, p + 2 * plane, oB, a.out_dt);
             }
         }
     }
@@ -298,15 +298,16 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const
 using namespace wm;
 
 extern "C" int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
-                                     const float* dY, const float* dC, const uint64_t* clamp_codes, float* gx,
+                                     const float* dY, const float* dC, const uint64_t* clamp_codes, void* gx, int gx_dtype,
                                      int B, int H, int W, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     if (int rc = dj_check(gy, g_sb, g_sc, g_sh, B, H, W, "wm_diffjpeg_bwd_saved(gy)")) return rc;
     WM_REQUIRE(dY && dC && clamp_codes && gx, WM_E_NULL, "wm_diffjpeg_bwd_saved: null pointer");
-    WM_REQUIRE(aligned(gx, 32) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
-               "wm_diffjpeg_bwd_saved: gx must be 32-byte, dY/dC 16-byte, clamp_codes 8-byte aligned");
+    WM_REQUIRE(dtype_ok(gx_dtype), WM_E_ARG, "wm_diffjpeg_bwd_saved: unknown gx element type %d", gx_dtype);
+    WM_REQUIRE(aligned(gx, 8 * dtype_size(gx_dtype)) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
+               "wm_diffjpeg_bwd_saved: gx must be aligned to 8 elements, dY/dC 16-byte, clamp_codes 8-byte aligned");
     DJArgs a = dj_args(B, H, W, 1.f, nullptr);
-    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = gx;
+    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = reinterpret_cast<float*>(gx); a.out_dt = gx_dtype;
     a.dY = const_cast<float*>(dY); a.dC = const_cast<float*>(dC);
     a.cm = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(clamp_codes));
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
@@ -314,17 +315,18 @@ extern "C" int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc
 }
 
 
-extern "C" int wm_diffjpeg_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
-                               const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, float* gx,
+extern "C" int wm_diffjpeg_bwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+                               const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, void* gx, int gx_dtype,
                                int B, int H, int W, float factor, const float* factor_ps,
                                int rounding, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
-    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_bwd(x)")) return rc;
+    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_bwd(x)", x_dtype)) return rc;
     if (int rc = dj_check(gy, g_sb, g_sc, g_sh, B, H, W, "wm_diffjpeg_bwd(gy)")) return rc;
-    WM_REQUIRE(gx != nullptr && aligned(gx, 32), WM_E_ALIGN, "wm_diffjpeg_bwd: gx must be non-null, 32-byte aligned");
+    WM_REQUIRE(dtype_ok(gx_dtype), WM_E_ARG, "wm_diffjpeg_bwd: unknown gx element type %d", gx_dtype);
+    WM_REQUIRE(gx != nullptr && aligned(gx, 8 * dtype_size(gx_dtype)), WM_E_ALIGN, "wm_diffjpeg_bwd: gx must be non-null, aligned to 8 elements");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
-    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = gx;
+    a.x = x; a.x_dt = x_dtype; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
+    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = reinterpret_cast<float*>(gx); a.out_dt = gx_dtype;
     const size_t smem = SC_BWD_CHUNKS * DJB_THREADS * sizeof(float4);
     DJ_DISPATCH_ROUND(diffjpeg_bwd_kernel, a, DJB_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd")
 }

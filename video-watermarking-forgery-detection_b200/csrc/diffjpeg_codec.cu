@@ -115,7 +115,7 @@ extern "C" int wm_diffjpeg_compress(const float* x, int64_t x_sb, int64_t x_sc, 
     WM_REQUIRE(coef_y && coef_cb && coef_cr && aligned(coef_y, 32), WM_E_NULL,
                "wm_diffjpeg_compress: coefficient outputs must be non-null (coef_y 32-byte aligned)");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
+    a.x = x; a.x_dt = WM_DT_F32; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
     a.coef_y = coef_y; a.coef_cb = coef_cb; a.coef_cr = coef_cr;
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
     DJ_DISPATCH_ROUND(diffjpeg_compress_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_compress")

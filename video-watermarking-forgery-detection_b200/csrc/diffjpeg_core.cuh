@@ -97,9 +97,10 @@ __device__ __forceinline__ float round_grad(float q) {
 #define DJ_I255 (1.f / 255.f)
 
 struct DJArgs {
-    const float* x; int64_t x_sb, x_sc, x_sh;
+    const void* x; int x_dt; int64_t x_sb, x_sc, x_sh;   // image in WM_DT_* elements (cast fused into the load)
     const float* gy; int64_t g_sb, g_sc, g_sh;
-    float* out;                 // y (fwd) or gx (bwd), dense NCHW
+    float* out;                 // y (fwd) or gx (bwd), dense NCHW; the backward kernels store gx as out_dt elements
+    int out_dt;
     float* coef_y; float* coef_cb; float* coef_cr;  // compress / decompress
     // state saved by the forward for the backward (wm_diffjpeg_fwd_save / wm_diffjpeg_bwd_saved):
     float* dY;                  // [B, H, W]        round'(q) of the luminance coefficient at [8i+u, 8j+v]
@@ -149,14 +150,15 @@ __device__ __forceinline__ float4 to_f4(const float (&v)[4]) { return make_float
 
 struct RowPair { f8 R[2], G[2], B[2]; };
 
-__device__ __forceinline__ void dj_load_pair(RowPair& p, const float* xr, int64_t sh, int64_t sc, bool active) {
+__device__ __forceinline__ void dj_load_pair(RowPair& p, const void* base, int64_t off, int64_t sh, int64_t sc, bool active,
+                                             int dt = WM_DT_F32) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-        const float* q = xr + int64_t(rr) * sh;
+        const int64_t q = off + int64_t(rr) * sh;
         if (active) {
-            p.R[rr] = ldg256_stream(q);
-            p.G[rr] = ldg256_stream(q + sc);
-            p.B[rr] = ldg256_stream(q + 2 * sc);
+            p.R[rr] = ld8_typed(base, q, dt);
+            p.G[rr] = ld8_typed(base, q + sc, dt);
+            p.B[rr] = ld8_typed(base, q + 2 * sc, dt);
         } else {
 #pragma unroll
             for (int c = 0; c < 8; ++c) p.R[rr].v[c] = p.G[rr].v[c] = p.B[rr].v[c] = 0.f;
@@ -194,14 +196,14 @@ __device__ __forceinline__ void dj_consume_pair(const RowPair& p, int rp, float4
 // the kernel inside the instruction cache.
 template <int NT>
 __device__ __forceinline__ void dj_load_block(const DJArgs& a, const DJThread& t, float4* scr) {
-    const float* xr = a.x + int64_t(t.b) * a.x_sb + int64_t(t.row0) * a.x_sh + t.col0;
+    const int64_t xr = int64_t(t.b) * a.x_sb + int64_t(t.row0) * a.x_sh + t.col0;
     RowPair A, B;
-    dj_load_pair(A, xr, a.x_sh, a.x_sc, t.active);
+    dj_load_pair(A, a.x, xr, a.x_sh, a.x_sc, t.active, a.x_dt);
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        dj_load_pair(B, xr + int64_t(4 * it + 2) * a.x_sh, a.x_sh, a.x_sc, t.active);
+        dj_load_pair(B, a.x, xr + int64_t(4 * it + 2) * a.x_sh, a.x_sh, a.x_sc, t.active, a.x_dt);
         dj_consume_pair<NT>(A, 2 * it, scr);
-        if (it == 0) dj_load_pair(A, xr + int64_t(4) * a.x_sh, a.x_sh, a.x_sc, t.active);
+        if (it == 0) dj_load_pair(A, a.x, xr + int64_t(4) * a.x_sh, a.x_sh, a.x_sc, t.active, a.x_dt);
         dj_consume_pair<NT>(B, 2 * it + 1, scr);
     }
 }
@@ -460,13 +462,15 @@ __device__ __forceinline__ void dj_emit_rgb_save(const DJArgs& a, const DJThread
 }
 
 // ---------------------------------------------------------------------------------------------
-static inline int dj_check(const float* x, int64_t sb, int64_t sc, int64_t sh, int B, int H, int W, const char* who) {
+static inline int dj_check(const void* x, int64_t sb, int64_t sc, int64_t sh, int B, int H, int W, const char* who,
+                           int dt = WM_DT_F32) {
     WM_REQUIRE(x != nullptr, WM_E_NULL, "%s: null image pointer", who);
+    WM_REQUIRE(dtype_ok(dt), WM_E_ARG, "%s: unknown element type %d (WM_DT_F32 / WM_DT_F16 / WM_DT_BF16)", who, dt);
     WM_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, WM_E_SHAPE,
                "%s: H and W must be positive multiples of 16 (got B=%d H=%d W=%d); the reference's "
                "block_merging views require it (utils/JPEG.py:371-376)", who, B, H, W);
-    WM_REQUIRE(aligned(x, 32) && sb % 8 == 0 && sc % 8 == 0 && sh % 8 == 0, WM_E_ALIGN,
-               "%s: base pointer must be 32-byte aligned and strides multiples of 8 elements "
+    WM_REQUIRE(aligned(x, 8 * dtype_size(dt)) && sb % 8 == 0 && sc % 8 == 0 && sh % 8 == 0, WM_E_ALIGN,
+               "%s: base pointer must be aligned to 8 elements (32 bytes for float32) and strides multiples of 8 elements "
                "(sb=%lld sc=%lld sh=%lld)", who, (long long)sb, (long long)sc, (long long)sh);
     return WM_OK;
 }

@@ -41,30 +41,30 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_save_kernel(const 
 
 using namespace wm;
 
-extern "C" int wm_diffjpeg_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
+extern "C" int wm_diffjpeg_fwd_save(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                                     float* dY, float* dC, uint64_t* clamp_codes, int B, int H, int W,
                                     float factor, const float* factor_ps, int rounding, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
-    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd_save")) return rc;
+    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd_save", x_dtype)) return rc;
     WM_REQUIRE(y && dY && dC && clamp_codes, WM_E_NULL, "wm_diffjpeg_fwd_save: null output pointer");
     WM_REQUIRE(aligned(y, 32) && aligned(dY, 16) && aligned(dC, 16) && aligned(clamp_codes, 8), WM_E_ALIGN,
                "wm_diffjpeg_fwd_save: y must be 32-byte, dY/dC 16-byte, clamp_codes 8-byte aligned");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
+    a.x = x; a.x_dt = x_dtype; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
     a.dY = dY; a.dC = dC; a.cm = reinterpret_cast<unsigned long long*>(clamp_codes);
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
     DJ_DISPATCH_ROUND(diffjpeg_fwd_save_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd_save")
 }
 
 
-extern "C" int wm_diffjpeg_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
+extern "C" int wm_diffjpeg_fwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                                int B, int H, int W, float factor, const float* factor_ps,
                                int rounding, const wm_store_epilogue* ep, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
-    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd")) return rc;
+    if (int rc = dj_check(x, x_sb, x_sc, x_sh, B, H, W, "wm_diffjpeg_fwd", x_dtype)) return rc;
     WM_REQUIRE(y != nullptr && aligned(y, 32), WM_E_ALIGN, "wm_diffjpeg_fwd: y must be non-null, 32-byte aligned");
     DJArgs a = dj_args(B, H, W, factor, factor_ps);
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
+    a.x = x; a.x_dt = x_dtype; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
     WM_EP_CHECK(ep, "wm_diffjpeg_fwd");
     a.ep = make_store_ep(ep);

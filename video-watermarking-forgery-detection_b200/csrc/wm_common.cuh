@@ -50,6 +50,43 @@ __device__ __forceinline__ float4 ldg128_stream(const float* p) {
     return r;
 }
 
+// ---- typed rows (boundary cast fused into the load / store: SURVEY 8b, autocast at models/IRNcrop_model.py:340) ------
+// 8 consecutive elements at element offset `off` of a float32 / float16 / bfloat16 array, as floats (f16 / bf16 -> f32
+// is exact), and the reverse with round-to-nearest-even (what torch's .to(dtype) does).  dt is warp-uniform.
+__device__ __forceinline__ f8 ld8_typed(const void* base, int64_t off, int dt) {
+    if (dt == WM_DT_F32) return ldg256_stream(reinterpret_cast<const float*>(base) + off);
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(reinterpret_cast<const uint16_t*>(base) + off));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    f8 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (dt == WM_DT_BF16) {
+            o.v[2 * i] = __uint_as_float(w[i] << 16);
+            o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        } else {
+            float lo, hi;
+            asm("{\n .reg .b16 l, h;\n mov.b32 {l, h}, %2;\n cvt.f32.f16 %0, l;\n cvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(w[i]));
+            o.v[2 * i] = lo; o.v[2 * i + 1] = hi;
+        }
+    }
+    return o;
+}
+__device__ __forceinline__ void st8_typed(void* base, int64_t off, const f8& v, int dt) {
+    if (dt == WM_DT_F32) { stg256(reinterpret_cast<float*>(base) + off, v); return; }
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (dt == WM_DT_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v.v[2 * i + 1]), "f"(v.v[2 * i]));
+        else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v.v[2 * i + 1]), "f"(v.v[2 * i]));
+    }
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<uint16_t*>(base) + off),
+                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+inline bool dtype_ok(int dt) { return dt == WM_DT_F32 || dt == WM_DT_F16 || dt == WM_DT_BF16; }
+inline size_t dtype_size(int dt) { return dt == WM_DT_F32 ? 4 : 2; }
+
 // ---- clamp to [0,1] with torch.clamp's NaN rule (NaN propagates; fminf/fmaxf and .sat return 0 for NaN):
 // two FMNMX.NAN instead of the compare + select a separate NaN test would need
 __device__ __forceinline__ float clamp01_nan(float v) {

@@ -43,10 +43,10 @@ class Bank3Desc(C.Structure):
 # name -> argtypes; every function returns int.  Kept in one table so that the CPU test-suite
 # can check that the built library exports exactly the header's entry points.
 SIGNATURES = {
-    "wm_diffjpeg_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, epp, vp],
-    "wm_diffjpeg_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
-    "wm_diffjpeg_fwd_save": [c_f32p, i64, i64, i64, c_f32p, c_f32p, c_f32p, vp, i32, i32, i32, f32, c_f32p, i32, vp],
-    "wm_diffjpeg_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, vp, c_f32p, i32, i32, i32, vp],
+    "wm_diffjpeg_fwd": [vp, i32, i64, i64, i64, c_f32p, i32, i32, i32, f32, c_f32p, i32, epp, vp],
+    "wm_diffjpeg_bwd": [vp, i32, i64, i64, i64, c_f32p, i64, i64, i64, vp, i32, i32, i32, i32, f32, c_f32p, i32, vp],
+    "wm_diffjpeg_fwd_save": [vp, i32, i64, i64, i64, c_f32p, c_f32p, c_f32p, vp, i32, i32, i32, f32, c_f32p, i32, vp],
+    "wm_diffjpeg_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, vp, vp, i32, i32, i32, i32, vp],
     "wm_diffjpeg_compress": [c_f32p, i64, i64, i64, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
     "wm_diffjpeg_decompress": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, vp],
     "wm_jpeg8_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), epp, vp],

@@ -53,16 +53,24 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.float32 else t.float()
 
 
-def _image(t: torch.Tensor, who: str, align_elems: int = 8) -> Tuple[torch.Tensor, int, int, int]:
+# element types the typed entry points read / store directly (include/wm_attack.h WM_DT_*): the autocast boundary's
+# cast is fused into the kernel instead of a separate .float() / .to(bfloat16) pass
+DT_F32, DT_F16, DT_BF16 = 0, 1, 2
+_DT_CODE = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
+
+
+def _image(t: torch.Tensor, who: str, align_elems: int = 8, typed: bool = False) -> Tuple[torch.Tensor, int, int, int]:
     """Return (tensor, sb, sc, sh) of a [B,C,H,W] float32 CUDA tensor readable in place by the
-    vector kernels (unit W stride, aligned strides/base); otherwise a contiguous copy."""
+    vector kernels (unit W stride, aligned strides/base); otherwise a contiguous copy.
+    typed=True keeps float16 / bfloat16 tensors as they are (for entry points with a *_dtype argument)."""
     _check_cuda(t, who)
     if t.dim() != 4:
         raise ValueError(f"{who}: expected a 4-D [B,C,H,W] tensor, got shape {tuple(t.shape)}")
-    t = _f32(t)
+    if not (typed and t.dtype in _DT_CODE):
+        t = _f32(t)
     sb, sc, sh, sw = t.stride()
     ok = (sw == 1 and sb % align_elems == 0 and sc % align_elems == 0 and sh % align_elems == 0
-          and t.data_ptr() % (4 * align_elems) == 0 and min(sb, sc, sh) >= 0)
+          and t.data_ptr() % (t.element_size() * align_elems) == 0 and min(sb, sc, sh) >= 0)
     if not ok:
         t = t.contiguous()
         sb, sc, sh, sw = t.stride()
@@ -201,7 +209,8 @@ class _DiffJPEGFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, factor, rounding, recompute):
-        x, sb, sc, sh = _image(x, "DiffJPEG")
+        x, sb, sc, sh = _image(x, "DiffJPEG", typed=True)      # float16 / bfloat16 inputs are read as they are
+        xdt = _DT_CODE[x.dtype]
         b, c, h, w = x.shape
         if c != 3:
             raise ValueError(f"DiffJPEG expects 3 channels, got {c}")
@@ -216,33 +225,34 @@ class _DiffJPEGFn(torch.autograd.Function):
             d_y = torch.empty((b, h, w), device=x.device, dtype=torch.float32)
             d_c = torch.empty((b, 2, h // 2, w // 2), device=x.device, dtype=torch.float32)
             codes = torch.empty((b, h, w // 8), device=x.device, dtype=torch.int64)
-            _lib.call("wm_diffjpeg_fwd_save", x.data_ptr(), sb, sc, sh, y.data_ptr(), d_y.data_ptr(), d_c.data_ptr(),
+            _lib.call("wm_diffjpeg_fwd_save", x.data_ptr(), xdt, sb, sc, sh, y.data_ptr(), d_y.data_ptr(), d_c.data_ptr(),
                       codes.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _stream())
             ctx.save_for_backward(d_y, d_c, codes)
             ctx.mode = "saved"
         else:
-            _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, None, _stream())
+            _lib.call("wm_diffjpeg_fwd", x.data_ptr(), xdt, sb, sc, sh, y.data_ptr(), b, h, w, fs, _ptr(fps), rounding, None, _stream())
             if need_grad and rounding != ROUND_HARD:
                 ctx.save_for_backward(x, fps if fps is not None else torch.empty(0, device=x.device))
                 ctx.mode = "recompute"
-        ctx.meta = (fs, fps is not None, rounding, (b, 3, h, w))
+        ctx.meta = (fs, fps is not None, rounding, (b, 3, h, w), x.dtype)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        fs, has_fps, rounding, (b, _, h, w) = ctx.meta
+        fs, has_fps, rounding, (b, _, h, w), xdtype = ctx.meta
         if ctx.mode == "none":                        # torch.round: zero gradient everywhere
-            return torch.zeros((b, 3, h, w), device=gy.device, dtype=torch.float32), None, None, None
+            return torch.zeros((b, 3, h, w), device=gy.device, dtype=xdtype), None, None, None
         gy, gsb, gsc, gsh = _image(gy, "DiffJPEG.backward")
-        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
+        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=xdtype)     # stored in the input's element type by the kernel
+        gdt = _DT_CODE[xdtype]
         if ctx.mode == "saved":
             d_y, d_c, codes = ctx.saved_tensors
             _lib.call("wm_diffjpeg_bwd_saved", gy.data_ptr(), gsb, gsc, gsh, d_y.data_ptr(), d_c.data_ptr(),
-                      codes.data_ptr(), gx.data_ptr(), b, h, w, _stream())
+                      codes.data_ptr(), gx.data_ptr(), gdt, b, h, w, _stream())
         else:
             x, fps_t = ctx.saved_tensors
             sb, sc, sh, _ = x.stride()
-            _lib.call("wm_diffjpeg_bwd", x.data_ptr(), sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(),
+            _lib.call("wm_diffjpeg_bwd", x.data_ptr(), gdt, sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(), gdt,
                       b, h, w, fs, _ptr(fps_t) if has_fps else None, rounding, _stream())
         return gx, None, None, None
 
@@ -1031,7 +1041,7 @@ def diffjpeg_into(x, factor, rounding, out, ep=None) -> bool:
     if c != 3 or h % 16 or w % 16 or not _out_ok(out, x.shape):
         return False
     fs, fps = _factor_args(factor, b, x.device)
-    _lib.call("wm_diffjpeg_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _ep_arg(ep), _stream())
+    _lib.call("wm_diffjpeg_fwd", x.data_ptr(), DT_F32, sb, sc, sh, out.data_ptr(), b, h, w, fs, _ptr(fps), rounding, _ep_arg(ep), _stream())
     return True
 
 
