@@ -58,7 +58,7 @@ const char* wm_last_error(void);
  * position - no separate pass over the attacked batch, and `y` may be a slice of a K-way batch.  The struct lives in
  * HOST memory and is copied into the launch.  A code path that cannot apply it fails with WM_E_ARG instead of
  * silently ignoring it: wm_jpeg8_fwd (needs W % 8 == 0, aligned, subsample 0), wm_gaussblur (zero border,
- * k in {3,5,7}, W % 4 == 0), wm_median_fwd (TMA paths), wm_resize_fwd, wm_diffjpeg_fwd, wm_gaussnoise_fwd. */
+ * k in {3,5,7}, W % 4 == 0), wm_median_fwd (W % 4 == 0), wm_resize_fwd, wm_diffjpeg_fwd, wm_gaussnoise_fwd. */
 typedef struct wm_store_epilogue {
     const float* x;
     int clamp01;
@@ -153,7 +153,8 @@ int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
  *   border 1 = reflect       (GF -> kornia GaussianBlur2d, noise_layers/gaussian_filter.py:9)
  * taps_host: k normalised 1-D taps (k odd, k <= 31).  x plane stride = x_sp elements, row
  * stride x_sh.  `adjoint` != 0 applies the transpose operator (== backward); for border 0
- * it is the same filter.
+ * it is the same filter.  Zero border, k in {3,5,7}: rows on 16-byte boundaries are staged by TMA, any other
+ * geometry (W % 4 != 0) by the same kernel fed with cp.async.
  * ------------------------------------------------------------------------------------------ */
 int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
                  const float* taps_host, int k, int border, int adjoint,
@@ -161,12 +162,15 @@ int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, in
 
 /* ------------------------------------------------------------------------------------------
  * k x k median, zero padding, k in {3,5}  (MiddleBlur, noise_layers/middle_filter.py:5-13 ->
- * kornia MedianBlur).  idx (optional, uint8 [N,H,W]) receives the raster position inside
- * the window of the FIRST element equal to the median; wm_median_bwd routes gy through it.
+ * kornia MedianBlur).  idx (optional, uint8 [N,H] rows of idx_sh >= W bytes) receives the raster position
+ * inside the window of the FIRST element equal to the median; wm_median_bwd routes gy through it.
+ * Rows on 16-byte boundaries (W % 4 == 0, aligned strides) are staged by TMA, any other geometry by the same
+ * kernels fed with cp.async; give idx a 16-byte aligned base and an idx_sh that is a multiple of 16 (the bytes past W
+ * are padding) and the backward keeps its idx ring on TMA for every W.
  * ------------------------------------------------------------------------------------------ */
-int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
+int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh,
                   int N, int H, int W, int k, const wm_store_epilogue* ep, void* stream);
-int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int k, void* stream);
+int wm_median_bwd(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise attacks over n contiguous floats.  Randomness: Philox4x32-10 keyed by `seed`,

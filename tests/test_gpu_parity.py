@@ -437,6 +437,30 @@ def test_median_forward_bit_exact(k):
     assert torch.equal(y.cpu(), yo) and torch.equal(idx.cpu(), io)
 
 
+def test_ragged_width_ring_kernels():
+    """W % 4 != 0: rows are not 16-byte aligned, no tensor map exists; the SAME ring kernels run fed by cp.async
+    (blur, median forward with / without the arg-median plane, median backward through the padded idx plane)."""
+    for shape, seed in (((2, 3, 70, 131), 31), ((1, 3, 37, 510), 32), ((1, 3, 5, 3), 33), ((3, 3, 90, 258), 34)):
+        x, g = rnd(shape, seed), rnd(shape, seed + 100)
+        for k in (3, 5, 7):
+            y, gx = fwd_bwd(wmattack.GaussianBlur(k), x, g)
+            yo, go = oracle_fwd_bwd(lambda t: O.gaussian_blur(t, k), x, g)
+            assert md(y, yo) <= 1e-6 and md(gx, go) <= 1e-6
+        for k in (3, 5):
+            xq = torch.round(x * 9) / 9                      # ties
+            for xx in (x, xq):
+                assert torch.equal(wmattack.MiddleBlur(k)(xx.to(DEV)).cpu(), O.median_blur(xx, k))     # no-grad kernel
+                y, gx = fwd_bwd(wmattack.MiddleBlur(k), xx, g)
+                yo, idx = O.median_blur(xx, k, return_index=True)
+                assert torch.equal(y, yo) and torch.equal(gx, O.median_blur_backward(g, idx, k))
+    # odd row stride: a column slice of a wider tensor
+    wide = rnd((1, 3, 40, 203), 35).to(DEV)
+    view = wide[..., 3:201]
+    for k in (3, 5):
+        assert torch.equal(wmattack.MiddleBlur(k)(view).cpu(), O.median_blur(view.cpu().contiguous(), k))
+    assert md(wmattack.GaussianBlur(5)(view), O.gaussian_blur(view.cpu().contiguous(), 5)) <= 1e-6
+
+
 @pytest.mark.parametrize("k", (3, 5))
 def test_median_backward(k):
     x, g = rnd((2, 3, 41, 133), 10), rnd((2, 3, 41, 133), 11)

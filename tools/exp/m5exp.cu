@@ -6,7 +6,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "median_net.cuh"
 #include "median_pair_net.cuh"
 #include "tma.cuh"
 #include "wm_common.cuh"

@@ -9,7 +9,7 @@ those six and its own sorted row (network B, 11 inputs).  Networks M and C split
 merged row pair (r+3, r+4) of one step is the pair (r+1, r+2) of the next, so each step merges ONE new
 pair (M) and takes the middle six of two merged pairs (C).
 
-Method as in gen_median_network.py: Batcher's odd-even merge sort restricted to the real wires,
+Method: Batcher's odd-even merge sort restricted to the real wires,
 comparators that never fire under the sortedness precondition dropped, greedy deletion with random
 restarts while the required outputs stay correct, correctness checked EXHAUSTIVELY with the 0-1
 principle over all monotone 0/1 assignments (6^4 = 1296 for A, 7*6 = 42 for B); comparators with one

@@ -89,18 +89,21 @@ struct BlurTArgs {
     float* y; int N, H, W, tiles_x, tiles_y; int64_t total;
     float taps[8];
     StoreEp ep;
+    RaggedSrc rag;      // RAGGED instantiation only: the source planes (no tensor map for rows that are not 16-byte aligned)
 };
 
 template <int K> constexpr int bt_stages() { return K <= 5 ? 3 : 2; }
 template <int K> constexpr int bt_stage_floats() { return ((BT_BW * (BT_TH + K - 1) + 31) / 32) * 32; }
 
-template <int K>
+// RAGGED = rows not 16-byte aligned (W % 4 != 0): the ring is filled by cp.async instead of TMA (stage_box_cpasync) and
+// the output leaves by scalar stores; everything between is the same code.
+template <int K, bool RAGGED>
 __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BlurTArgs a) {
     constexpr int R = K / 2, BH = BT_TH + 2 * R, S = bt_stages<K>(), STRIDE = bt_stage_floats<K>();
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[S];
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    if (!RAGGED && tid == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -111,14 +114,19 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
     auto issue = [&](int64_t t, int s) {
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], BT_BW * BH * sizeof(float));
-        tma_load_3d(bufs + s * STRIDE, &tmap, tx * BT_TW - BT_HALO, ty * BT_TH - R, n, &full[s]);
+        if (RAGGED) {       // every thread; an empty group keeps the per-thread group count in step with the ring
+            if (t < a.total) stage_box_cpasync<BT_THREADS>(bufs + s * STRIDE, a.rag, n, a.H, a.W, tx * BT_TW - BT_HALO, ty * BT_TH - R, BT_BW, BH);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            mbar_expect_tx(&full[s], BT_BW * BH * sizeof(float));
+            tma_load_3d(bufs + s * STRIDE, &tmap, tx * BT_TW - BT_HALO, ty * BT_TH - R, n, &full[s]);
+        }
     };
-    if (tid == 0) {
+    if (RAGGED || tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
-            if (t < a.total) issue(t, s);
+            if (RAGGED || t < a.total) issue(t, s);
         }
     }
     float w[K];
@@ -128,7 +136,8 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
     int it = 0;
     for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
         const int s = it % S;
-        mbar_wait(&full[s], (it / S) & 1);
+        if (RAGGED) { cpasync_wait<S - 1>(); __syncthreads(); }      // this thread's copies of tile `it` landed; then everyone's
+        else mbar_wait(&full[s], (it / S) & 1);
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * BT_TW + 4 * cg, gy0 = ty * BT_TH + strip * BT_ROWS;
@@ -169,27 +178,30 @@ __global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __gr
                 if (a.ep.x)      // x at the output position is the centre of the staged tile row
                     o = a.ep.from_input ? ep_apply4v(o, *reinterpret_cast<const float4*>(col + (r + R) * BT_BW), a.ep)
                                         : ep_apply4(o, a.ep.x + (dst - a.y) + int64_t(r) * a.W, a.ep);
-                stg128(dst + int64_t(r) * a.W, o);
+                if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
+                else stg128(dst + int64_t(r) * a.W, o);
             }
         }
         __syncthreads();                      // every lane is done with stage s
-        if (tid == 0) {
+        if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(S) * gridDim.x;
-            if (t2 < a.total) issue(t2, s);
+            if (RAGGED || t2 < a.total) issue(t2, s);
         }
     }
 }
 
-template <int K>
+template <int K, bool RAGGED>
 static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
                            const float* taps_host, const wm_store_epilogue* ep, cudaStream_t st) {
     constexpr int R = K / 2, S = bt_stages<K>();
-    CUtensorMap tm;
-    if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, BT_BW, BT_TH + 2 * R)) {
-        set_error("wm_gaussblur: cuTensorMapEncodeTiled failed (%d)", rc);
-        return WM_E_ARG;
-    }
+    CUtensorMap tm{};
+    if (!RAGGED)
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, BT_BW, BT_TH + 2 * R)) {
+            set_error("wm_gaussblur: cuTensorMapEncodeTiled failed (%d)", rc);
+            return WM_E_ARG;
+        }
     BlurTArgs a{};
+    a.rag = RaggedSrc{x, x_sp, x_sh};
     a.y = y; a.N = N; a.H = H; a.W = W;
     a.tiles_x = (W + BT_TW - 1) / BT_TW; a.tiles_y = (H + BT_TH - 1) / BT_TH;
     a.total = int64_t(N) * a.tiles_x * a.tiles_y;
@@ -197,11 +209,11 @@ static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y,
     a.ep = make_store_ep(ep);
     a.ep.from_input = a.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
     const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
-    cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
     const int64_t cap = int64_t(sm_count()) * 2;
     const unsigned grid = (unsigned)(a.total < cap ? a.total : cap);
-    gaussblur_tma_kernel<K><<<grid, BT_THREADS, smem, st>>>(tm, a);
+    gaussblur_tma_kernel<K, RAGGED><<<grid, BT_THREADS, smem, st>>>(tm, a);
     WM_LAUNCH_CHECK("wm_gaussblur(tma)");
     return WM_OK;
 }
@@ -264,9 +276,15 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
     }
     if (border == 0 && (k == 3 || k == 5 || k == 7) && W % 4 == 0 && aligned(y, 16) && tmap_ok(x, x_sp, x_sh, 4)) {
         WM_EP_CHECK(ep, "wm_gaussblur");
-        if (k == 3) return launch_blur_tma<3>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
-        if (k == 5) return launch_blur_tma<5>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
-        return launch_blur_tma<7>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+        if (k == 3) return launch_blur_tma<3, false>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+        if (k == 5) return launch_blur_tma<5, false>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+        return launch_blur_tma<7, false>(x, x_sp, x_sh, y, N, H, W, taps_host, ep, st);
+    }
+    if (border == 0 && (k == 3 || k == 5 || k == 7) && !wants_store_ep(ep) && aligned(x, 4) && aligned(y, 4)) {
+        // rows that are not 16-byte aligned (W % 4 != 0, odd strides): same ring and stencil, fed by cp.async
+        if (k == 3) return launch_blur_tma<3, true>(x, x_sp, x_sh, y, N, H, W, taps_host, nullptr, st);
+        if (k == 5) return launch_blur_tma<5, true>(x, x_sp, x_sh, y, N, H, W, taps_host, nullptr, st);
+        return launch_blur_tma<7, true>(x, x_sp, x_sh, y, N, H, W, taps_host, nullptr, st);
     }
     WM_EP_REJECT(ep, "wm_gaussblur (generic path)");
     const int IW = BL_TW + 2 * r, IH = BL_TH + 2 * r;

@@ -2,25 +2,17 @@
 //
 // Replaces MiddleBlur.forward (noise_layers/middle_filter.py:11-13 -> kornia MedianBlur), which
 // materialises a one-hot conv2d expansion of k*k times the image (288 / 672 B/px forward) and
-// then sorts along it.  Here a CTA stages a halo tile in shared memory; a thread walks down a
-// column strip, sorts each k-wide window ROW once (shared by the k vertically adjacent outputs)
-// and selects the median from the k sorted rows with a pruned min/max network
-// (3x3: FMNMX3 + XOR middle-of-three, 5x5: generated median_net.cuh) — pure selection, so the
+// then sorts along it.  Here persistent CTAs stage halo tiles in a shared-memory ring (TMA; cp.async when the rows
+// are not 16-byte aligned); a thread walks down a column strip, sorts each k-wide window ROW once (shared by the k
+// vertically adjacent outputs) and selects the median from the k sorted rows with a pruned min/max network
+// (3x3: FMNMX3 + middle-of-three, 5x5: generated median_pair_net.cuh) — pure selection, so the
 // forward is bit-exact.  Optionally it records, per output, the raster position of the FIRST
-// window element equal to the median (uint8); the backward is a deterministic gather through it.
-#include "median_net.cuh"
+// window element equal to the median (uint8, row stride idx_sh); the backward is a deterministic gather through it.
 #include "median_pair_net.cuh"
 #include "tma.cuh"
 #include "wm_common.cuh"
 
 namespace wm {
-
-constexpr int MD_TW = 128, MD_TH = 32, MD_THREADS = 256, MD_STRIP = MD_TH * MD_TW / MD_THREADS;  // 16 rows/thread
-
-struct MedArgs {
-    const float* x; int64_t x_sp, x_sh;
-    float* y; uint8_t* idx; int N, H, W;
-};
 
 __device__ __forceinline__ float mid3(float a, float b, float c, float lo, float hi) {
     // the element that is neither the min nor the max: XOR of the five bit patterns
@@ -64,71 +56,6 @@ template <class CE> __device__ __forceinline__ void sort5(float (&v)[5], const C
 template <bool INT> struct ce_pick { using type = CeMinMax; static __device__ __forceinline__ type make(int, int) { return type(); } };
 template <> struct ce_pick<true> { using type = CeIntSum; static __device__ __forceinline__ type make(int one, int neg1) { return type{one, neg1}; } };
 
-template <int K, bool WANT_IDX>
-__global__ void __launch_bounds__(MD_THREADS) median_fwd_kernel(const MedArgs a) {
-    constexpr int R = K / 2, IW = MD_TW + 2 * R, IH = MD_TH + 2 * R;
-    __shared__ float tile[IH * IW];
-    const int tiles_x = (a.W + MD_TW - 1) / MD_TW;
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const int n = blockIdx.y;
-    const int x0 = tx * MD_TW, y0 = ty * MD_TH;
-    const float* src = a.x + int64_t(n) * a.x_sp;
-    for (int i = threadIdx.x; i < IH * IW; i += MD_THREADS) {
-        const int ly = i / IW, lx = i - ly * IW;
-        const int gy = y0 + ly - R, gx = x0 + lx - R;
-        tile[i] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? __ldg(src + int64_t(gy) * a.x_sh + gx) : 0.f;
-    }
-    __syncthreads();
-    const int lx = threadIdx.x % MD_TW, strip = threadIdx.x / MD_TW;
-    const int ly0 = strip * MD_STRIP;
-    const int gx = x0 + lx;
-    float* dst = a.y + int64_t(n) * a.H * a.W;
-    uint8_t* dsti = WANT_IDX ? a.idx + int64_t(n) * a.H * a.W : nullptr;
-
-    float rows[K][K];       // ring of the K sorted window rows
-#pragma unroll
-    for (int j = 0; j < K - 1; ++j) {
-#pragma unroll
-        for (int c = 0; c < K; ++c) rows[j][c] = tile[(ly0 + j) * IW + lx + c];
-        if constexpr (K == 3) sort3(rows[j][0], rows[j][1], rows[j][2]);
-        else sort5(rows[j], CeMinMax());
-    }
-#pragma unroll
-    for (int s = 0; s < MD_STRIP; ++s) {
-        const int ly = ly0 + s;
-        constexpr int KM1 = K - 1;
-        const int slot = (s + KM1) % K;     // compile-time after unrolling: replaces the oldest row
-#pragma unroll
-        for (int c = 0; c < K; ++c) rows[slot][c] = tile[(ly + K - 1) * IW + lx + c];
-        float med;
-        if constexpr (K == 3) {
-            sort3(rows[slot][0], rows[slot][1], rows[slot][2]);
-            med = med3(fmax3(rows[0][0], rows[1][0], rows[2][0]),
-                       med3(rows[0][1], rows[1][1], rows[2][1]),
-                       fmin3(rows[0][2], rows[1][2], rows[2][2]));
-        } else {
-            sort5(rows[slot], CeMinMax());
-            float v[25];
-#pragma unroll
-            for (int j = 0; j < 5; ++j)
-#pragma unroll
-                for (int c = 0; c < 5; ++c) v[5 * j + c] = rows[j][c];
-            med = median25_sorted_groups(v);
-        }
-        const int gy = y0 + ly;
-        if (gy < a.H && gx < a.W) {
-            dst[int64_t(gy) * a.W + gx] = med;
-            if (WANT_IDX) {
-                int pos = 0;
-#pragma unroll
-                for (int j = K * K - 1; j >= 0; --j)
-                    pos = (tile[(ly + j / K) * IW + lx + j % K] == med) ? j : pos;
-                dsti[int64_t(gy) * a.W + gx] = (uint8_t)pos;
-            }
-        }
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // 3x3 fast path (16-byte aligned rows): persistent CTAs fed by a ring of TMA-staged halo tiles
@@ -146,6 +73,8 @@ struct MedTArgs {
     float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
     StoreEp ep;
     int one, neg1;      // +1 / -1 as launch parameters (FMA-pipe integer sums, see CeIntSum)
+    int64_t idx_sh;     // row stride of the arg-median plane in bytes (>= W; a multiple of 16 keeps the backward's idx ring on TMA)
+    RaggedSrc rag;      // RAGGED instantiations: source planes (rows not 16-byte aligned, no tensor map)
 };
 // middle of three as a + b + c - min - max on the bit patterns: four IMADs on the FMA pipe instead of two LOP3 on the
 // ALU pipe, which the arg-median search saturates (102 -> 96 us at 64x3x512x512 with the plane; without it the
@@ -159,12 +88,13 @@ __device__ __forceinline__ float mid3_sum(float a, float b, float c, float lo, f
     return __int_as_float(s);
 }
 
-template <bool WANT_IDX, bool EP>
+// RAGGED (rows not 16-byte aligned): ring fed by cp.async, scalar stores (tma.cuh: stage_box_cpasync).
+template <bool WANT_IDX, bool EP, bool RAGGED = false>
 __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[MT_STAGES];
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    if (!RAGGED && tid == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
         for (int s = 0; s < MT_STAGES; ++s) mbar_init(&full[s], 1);
@@ -175,21 +105,27 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
     auto issue = [&](int64_t t, int s) {
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float));
-        tma_load_3d(bufs + s * MT_STRIDE, &tmap, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
+        if (RAGGED) {       // every thread; an empty group keeps the per-thread group count in step with the ring
+            if (t < a.total) stage_box_cpasync<MT_THREADS>(bufs + s * MT_STRIDE, a.rag, n, a.H, a.W, tx * MT_TW - MT_HALO, ty * MT_TH - 1, MT_BW, MT_BH);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float));
+            tma_load_3d(bufs + s * MT_STRIDE, &tmap, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
+        }
     };
-    if (tid == 0) {
+    if (RAGGED || tid == 0) {
 #pragma unroll
         for (int s = 0; s < MT_STAGES; ++s) {
             const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
-            if (t < a.total) issue(t, s);
+            if (RAGGED || t < a.total) issue(t, s);
         }
     }
     const int cg = tid & 31, strip = tid >> 5;
     int it = 0;
     for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
         const int s = it % MT_STAGES;
-        mbar_wait(&full[s], (it / MT_STAGES) & 1);
+        if (RAGGED) { cpasync_wait<MT_STAGES - 1>(); __syncthreads(); }
+        else mbar_wait(&full[s], (it / MT_STAGES) & 1);
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
@@ -211,6 +147,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
         load_row(1, 1);
         const bool col_ok = gx < a.W;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
+        const int64_t ibase = (int64_t(n) * a.H + gy0) * a.idx_sh + gx;
 #pragma unroll
         for (int r = 0; r < MT_ROWS; ++r) {
             load_row(r + 2, (r + 2) % 3);
@@ -243,14 +180,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
                     o = a.ep.from_input ? ep_apply4v(o, make_float4(c[1], c[2], c[3], c[4]), a.ep)
                                         : ep_apply4(o, a.ep.x + obase + int64_t(r) * a.W, a.ep);
                 }
-                stg128(a.y + obase + int64_t(r) * a.W, o);
-                if (WANT_IDX) *reinterpret_cast<uint32_t*>(a.idx + obase + int64_t(r) * a.W) = packed;
+                if (RAGGED) st4_ragged(a.y + obase + int64_t(r) * a.W, o, gx, a.W);
+                else stg128(a.y + obase + int64_t(r) * a.W, o);
+                if (WANT_IDX) {
+                    uint8_t* ip = a.idx + ibase + int64_t(r) * a.idx_sh;
+                    if (!RAGGED || (a.idx_sh & 3) == 0) *reinterpret_cast<uint32_t*>(ip) = packed;   // bytes past W land in the row's padding
+                    else {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) if (gx + c4 < a.W) ip[c4] = uint8_t(packed >> (8 * c4));
+                    }
+                }
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(MT_STAGES) * gridDim.x;
-            if (t2 < a.total) issue(t2, s);
+            if (RAGGED || t2 < a.total) issue(t2, s);
         }
     }
 }
@@ -264,7 +209,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
 // either window — and each output is then the median of those six and its own sorted row
 // (median_pair_net.cuh, generated; the merged row pair (r+3, r+4) of one step is reused as the pair
 // (r+1, r+2) of the next: 30 + 36 + 2 x 10 min/max per pair of outputs against 2 x 110 for the
-// single-output network of median_net.cuh).  The raw rows stay in registers for the arg-median search.  The row loop
+// one-output-at-a-time network).  The raw rows stay in registers for the arg-median search.  The row loop
 // is unrolled by 3 pairs so that ring slots are compile-time indices.
 //
 // The kernel is bound by the ALU pipe (FMNMX, FSET) and then by instruction issue, not by HBM (ncu: ALU 89 %, FMA
@@ -289,11 +234,13 @@ struct Med5Args {
     float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
     int one, neg1;
     StoreEp ep;
+    int64_t idx_sh;     // row stride of the arg-median plane in bytes
+    RaggedSrc rag;      // RAGGED instantiations: source planes
 };
 
 // One 128 x 36 tile of one plane: `col` = the lane's window column in the staged box (row 0 = image row gy0 - 2).
 template <bool WANT_IDX, bool EP>
-__device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col, int64_t obase, int rows_ok) {
+__device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col, int64_t obase, int64_t ibase, int rows_ok) {
     // with the arg-median search on the ALU pipe too, every comparator moves its max to the FMA pipe; without it the
     // last network keeps plain FMNMX pairs (measured: 338 -> 261 us with, 231 -> 172 us without the plane at 64x3x504x512)
     const auto ce_s = ce_pick<true>::make(a.one, a.neg1);
@@ -311,8 +258,8 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col
 #pragma unroll
     for (int j = 0; j < 4; ++j) load_row(j, j);
     float* const yb = a.y + obase;
-    uint8_t* const ib = WANT_IDX ? a.idx + obase : nullptr;
-    int off = 0;
+    uint8_t* const ib = WANT_IDX ? a.idx + ibase : nullptr;
+    int off = 0, ioff = 0;
     float mp[10];                                      // rows r+1, r+2 merged (kept from the previous step)
 #pragma unroll
     for (int k = 0; k < 5; ++k) { mp[k] = srt[1][k]; mp[5 + k] = srt[2][k]; }
@@ -354,20 +301,20 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col
                 }
                 if (r + o < rows_ok) {
                     yb[off] = EP ? ep_apply(med, a.ep.from_input ? col[(r + o + 2) * M5_BW + 2] : a.ep.x[obase + off], a.ep) : med;
-                    if (WANT_IDX) ib[off] = (uint8_t)pos;
+                    if (WANT_IDX) ib[ioff] = (uint8_t)pos;
                 }
-                off += a.W;
+                off += a.W; ioff += int(a.idx_sh);
             }
         }
     }
 }
 
-template <bool WANT_IDX, bool EP>
+template <bool WANT_IDX, bool EP, bool RAGGED = false>
 __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Med5Args a) {
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[M5_STAGES];
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    if (!RAGGED && tid == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
         for (int s = 0; s < M5_STAGES; ++s) mbar_init(&full[s], 1);
@@ -378,21 +325,42 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
     auto issue = [&](int64_t t, int s) {
         const int m = int(t / per_plane), rem = int(t - int64_t(m) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], M5_STRIDE * sizeof(float));
-        tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, m5_row0(ty, a.H) - 2, 2 * m, &full[s]);
+        if (RAGGED) {       // both planes of the pair, one commit group (a plane past N arrives as zeros)
+            if (t < a.total) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int n = 2 * m + hf;
+                    float* dst = bufs + s * M5_STRIDE + hf * (M5_BW * M5_BH);
+                    if (n < a.N) {
+                        const float* plane = a.rag.x + int64_t(n) * a.rag.sp;
+                        for (int i = threadIdx.x; i < M5_BW * M5_BH; i += M5_THREADS) {
+                            const int ly = i / M5_BW, lx = i - ly * M5_BW, gy = m5_row0(ty, a.H) - 2 + ly, gx = tx * M5_TW - M5_HALO + lx;
+                            const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                            const float* src = ok ? plane + int64_t(gy) * a.rag.sh + gx : plane;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + i)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            mbar_expect_tx(&full[s], M5_STRIDE * sizeof(float));
+            tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, m5_row0(ty, a.H) - 2, 2 * m, &full[s]);
+        }
     };
-    if (tid == 0) {
+    if (RAGGED || tid == 0) {
 #pragma unroll
         for (int s = 0; s < M5_STAGES; ++s) {
             const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
-            if (t < a.total) issue(t, s);
+            if (RAGGED || t < a.total) issue(t, s);
         }
     }
     const int c = tid & 127, half = tid >> 7;
     int it = 0;
     for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
         const int s = it % M5_STAGES;
-        mbar_wait(&full[s], (it / M5_STAGES) & 1);
+        if (RAGGED) { cpasync_wait<M5_STAGES - 1>(); __syncthreads(); }
+        else mbar_wait(&full[s], (it / M5_STAGES) & 1);
         const int m = int(t / per_plane), rem = int(t - int64_t(m) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int n = 2 * m + half, gx = tx * M5_TW + c, gy0 = m5_row0(ty, a.H);
@@ -400,11 +368,11 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         const float* col = bufs + s * M5_STRIDE + half * (M5_BW * M5_BH) + M5_HALO - 2 + c;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
         const int rows_ok = (gx < a.W && n < a.N) ? rows_tile : 0;          // this lane stores output rows r < rows_ok
-        median5_tile<WANT_IDX, EP>(a, col, obase, rows_ok);
+        median5_tile<WANT_IDX, EP>(a, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
         __syncthreads();
-        if (tid == 0) {
+        if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(M5_STAGES) * gridDim.x;
-            if (t2 < a.total) issue(t2, s);
+            if (RAGGED || t2 < a.total) issue(t2, s);
         }
     }
 }
@@ -420,9 +388,12 @@ template <int K> constexpr int mb_istride() { return ((MB_IBW * mb_bh<K>() + 127
 
 struct MedBArgs {
     float* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
+    RaggedSrc rag;      // RAGGED: the cotangent planes (rows not 16-byte aligned); the idx plane always has a tensor map
 };
 
-template <int K>
+// RAGGED: the (gy) ring is filled by cp.async, the idx ring still by TMA (the forward wrote the arg-median plane with
+// a 16-byte row stride), and gx leaves by scalar stores.
+template <int K, bool RAGGED = false>
 __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                                        const __grid_constant__ CUtensorMap tm_i,
                                                                        const MedBArgs a) {
@@ -432,7 +403,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
     __shared__ uint64_t full[MB_STAGES];
     const int tid = threadIdx.x;
     if (tid == 0) {
-        tma_prefetch_desc(&tm_g);
+        if (!RAGGED) tma_prefetch_desc(&tm_g);
         tma_prefetch_desc(&tm_i);
 #pragma unroll
         for (int s = 0; s < MB_STAGES; ++s) mbar_init(&full[s], 1);
@@ -443,21 +414,31 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
     auto issue = [&](int64_t t, int s) {
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        mbar_expect_tx(&full[s], MT_BW * BH * sizeof(float) + MB_IBW * BH);
-        tma_load_3d(bufs + s * GS, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - R, n, &full[s]);
-        tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
+        if (RAGGED) {
+            if (t < a.total) stage_box_cpasync<MT_THREADS>(bufs + s * GS, a.rag, n, a.H, a.W, tx * MT_TW - MT_HALO, ty * MT_TH - R, MT_BW, BH);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            if (tid == 0 && t < a.total) {
+                mbar_expect_tx(&full[s], MB_IBW * BH);
+                tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
+            }
+        } else {
+            mbar_expect_tx(&full[s], MT_BW * BH * sizeof(float) + MB_IBW * BH);
+            tma_load_3d(bufs + s * GS, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - R, n, &full[s]);
+            tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
+        }
     };
-    if (tid == 0) {
+    if (RAGGED || tid == 0) {
 #pragma unroll
         for (int s = 0; s < MB_STAGES; ++s) {
             const int64_t t = int64_t(blockIdx.x) + int64_t(s) * gridDim.x;
-            if (t < a.total) issue(t, s);
+            if (RAGGED || t < a.total) issue(t, s);
         }
     }
     const int cg = tid & 31, strip = tid >> 5;
     int it = 0;
     for (int64_t t = blockIdx.x; t < a.total; t += gridDim.x, ++it) {
         const int s = it % MB_STAGES;
+        if (RAGGED) { cpasync_wait<MB_STAGES - 1>(); __syncthreads(); }
         mbar_wait(&full[s], (it / MB_STAGES) & 1);
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
@@ -510,29 +491,32 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
                     }
                 op[c4] = acc;
             }
-            if (col_ok && gy0 + r < a.H) stg128(dst + int64_t(r) * a.W, o);
+            if (col_ok && gy0 + r < a.H) {
+                if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
+                else stg128(dst + int64_t(r) * a.W, o);
+            }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(MB_STAGES) * gridDim.x;
-            if (t2 < a.total) issue(t2, s);
+            if (RAGGED || t2 < a.total) issue(t2, s);
         }
     }
 }
 
-template <int K>
-static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, cudaStream_t st) {
-    CUtensorMap tg, ti;
-    int rc = tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, mb_bh<K>());
-    if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * W, W, MB_IBW, mb_bh<K>());
+template <int K, bool RAGGED>
+static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, cudaStream_t st) {
+    CUtensorMap tg{}, ti;
+    int rc = RAGGED ? 0 : tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, mb_bh<K>());
+    if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * idx_sh, idx_sh, MB_IBW, mb_bh<K>());
     if (rc) { set_error("wm_median_bwd: cuTensorMapEncodeTiled failed (%d)", rc); return WM_E_ARG; }
-    MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0};
+    MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, RaggedSrc{gy, int64_t(H) * W, W}};
     ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
     const size_t smem = sizeof(float) * size_t(MB_STAGES) * mb_gstride<K>() + size_t(MB_STAGES) * mb_istride<K>();
-    cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
     const int64_t cap = int64_t(sm_count()) * 2;
-    median_bwd_tma_kernel<K><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
+    median_bwd_tma_kernel<K, RAGGED><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
     WM_LAUNCH_CHECK("wm_median_bwd(tma)");
     return WM_OK;
 }
@@ -540,7 +524,7 @@ static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, float* gx,
 // gx[p] = sum over outputs q with p in window(q) and argmedian(q) == p of gy[q]
 template <int K>
 __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ idx,
-                                                         float* __restrict__ gx, int N, int H, int W) {
+                                                         int64_t idx_sh, float* __restrict__ gx, int N, int H, int W) {
     constexpr int R = K / 2;
     const int64_t total = int64_t(N) * H * W;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -556,7 +540,7 @@ __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict
                     // (h, w) sits at window position (R - dy, R - dx) of output (qh, qw)
                     const int want = (R - dy) * K + (R - dx);
                     const int64_t q = base + int64_t(qh) * W + qw;
-                    if (idx[q] == want) acc += gy[q];
+                    if (idx[(base / W + qh) * idx_sh + qw] == want) acc += gy[q];
                 }
             }
         gx[i] = acc;
@@ -567,78 +551,81 @@ __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict
 
 using namespace wm;
 
-extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx,
+template <bool RAGGED>
+static int launch_median3(const CUtensorMap& tm, MedTArgs& ta, cudaStream_t st) {
+    const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
+    auto kern = ta.ep.x ? (ta.idx ? median3_tma_kernel<true, true, RAGGED> : median3_tma_kernel<false, true, RAGGED>)
+                        : (ta.idx ? median3_tma_kernel<true, false, RAGGED> : median3_tma_kernel<false, false, RAGGED>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    kern<<<(unsigned)(ta.total < cap ? ta.total : cap), MT_THREADS, smem, st>>>(tm, ta);
+    WM_LAUNCH_CHECK("wm_median_fwd(3x3)");
+    return WM_OK;
+}
+template <bool RAGGED>
+static int launch_median5(const CUtensorMap& tm, Med5Args& ta, cudaStream_t st) {
+    const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
+    auto kern = ta.ep.x ? (ta.idx ? median5_tma_kernel<true, true, RAGGED> : median5_tma_kernel<false, true, RAGGED>)
+                        : (ta.idx ? median5_tma_kernel<true, false, RAGGED> : median5_tma_kernel<false, false, RAGGED>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    kern<<<(unsigned)(ta.total < cap ? ta.total : cap), M5_THREADS, smem, st>>>(tm, ta);
+    WM_LAUNCH_CHECK("wm_median_fwd(5x5)");
+    return WM_OK;
+}
+
+extern "C" int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh,
                              int N, int H, int W, int k, const wm_store_epilogue* ep, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_median_fwd: null pointer");
     WM_EP_CHECK(ep, "wm_median_fwd");
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_fwd: kernel size must be 3 or 5 (got %d)", k);
-    WM_REQUIRE(N >= 0 && N <= 65535 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd: bad shape N=%d H=%d W=%d", N, H, W);
-    if (N == 0) return WM_OK;
+    WM_REQUIRE(N >= 0 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd: bad shape N=%d H=%d W=%d", N, H, W);
+    WM_REQUIRE(!idx || idx_sh >= W, WM_E_ARG, "wm_median_fwd: the arg-median plane's row stride (%lld) must be >= W", (long long)idx_sh);
     cudaStream_t st = (cudaStream_t)stream;
-    if (k == 3 && W % 4 == 0 && aligned(y, 16) && (!idx || aligned(idx, 4)) && tmap_ok(x, x_sp, x_sh, 4)) {
-        CUtensorMap tm;
-        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, MT_BW, MT_BH)) {
+    // rows on 16-byte boundaries: TMA-fed ring; anything else (W % 4 != 0, odd strides): the same kernels fed by cp.async
+    const bool tma = W % 4 == 0 && aligned(y, 16) && tmap_ok(x, x_sp, x_sh, 4) && (k == 5 || !idx || (aligned(idx, 4) && idx_sh % 4 == 0));
+    if (!tma) WM_EP_REJECT(ep, "wm_median_fwd (rows not 16-byte aligned)");
+    CUtensorMap tm{};
+    if (tma)
+        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, k == 3 ? MT_BW : M5_BW,
+                                 k == 3 ? MT_BH : M5_BH, k == 3 ? 1 : 2)) {
             set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
-        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, StoreEp{nullptr, 0, 0, 0}, 1, -1};
+    StoreEp sep = tma ? make_store_ep(ep) : StoreEp{nullptr, 0, 0, 0};
+    sep.from_input = sep.x == x && x_sh == W && x_sp == int64_t(H) * W;
+    if (k == 3) {
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, sep, 1, -1, idx_sh, RaggedSrc{x, x_sp, x_sh}};
         ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
-        ta.ep = make_store_ep(ep);
-        ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
-        const size_t smem = sizeof(float) * size_t(MT_STAGES) * MT_STRIDE;
-        auto kern = ta.ep.x ? (idx ? median3_tma_kernel<true, true> : median3_tma_kernel<false, true>)
-                            : (idx ? median3_tma_kernel<true, false> : median3_tma_kernel<false, false>);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
-        const int64_t cap = int64_t(sm_count()) * 2;
-        kern<<<(unsigned)(ta.total < cap ? ta.total : cap), MT_THREADS, smem, st>>>(tm, ta);
-        WM_LAUNCH_CHECK("wm_median_fwd(tma)");
-        return WM_OK;
+        return tma ? launch_median3<false>(tm, ta, st) : launch_median3<true>(tm, ta, st);
     }
-    if (k == 5 && tmap_ok(x, x_sp, x_sh, 4)) {
-        CUtensorMap tm;
-        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, M5_BW, M5_BH, 2)) {
-            set_error("wm_median_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
-            return WM_E_ARG;
-        }
-        Med5Args ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_ROWS - 1) / M5_ROWS, 0, 1, -1, StoreEp{nullptr, 0, 0, 0}};
-        ta.total = int64_t((N + 1) / 2) * ta.tiles_x * ta.tiles_y;
-        ta.ep = make_store_ep(ep);
-        ta.ep.from_input = ta.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
-        const size_t smem = sizeof(float) * size_t(M5_STAGES) * M5_STRIDE;
-        auto kern = ta.ep.x ? (idx ? median5_tma_kernel<true, true> : median5_tma_kernel<false, true>)
-                            : (idx ? median5_tma_kernel<true, false> : median5_tma_kernel<false, false>);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd");
-        const int64_t cap = int64_t(sm_count()) * 2;
-        kern<<<(unsigned)(ta.total < cap ? ta.total : cap), M5_THREADS, smem, st>>>(tm, ta);
-        WM_LAUNCH_CHECK("wm_median_fwd(tma5)");
-        return WM_OK;
-    }
-    WM_EP_REJECT(ep, "wm_median_fwd (generic path)");
-    MedArgs a{x, x_sp, x_sh, y, idx, N, H, W};
-    const int tiles = ((W + MD_TW - 1) / MD_TW) * ((H + MD_TH - 1) / MD_TH);
-    dim3 grid(tiles, N);
-    if (k == 3) { if (idx) median_fwd_kernel<3, true><<<grid, MD_THREADS, 0, st>>>(a); else median_fwd_kernel<3, false><<<grid, MD_THREADS, 0, st>>>(a); }
-    else        { if (idx) median_fwd_kernel<5, true><<<grid, MD_THREADS, 0, st>>>(a); else median_fwd_kernel<5, false><<<grid, MD_THREADS, 0, st>>>(a); }
-    WM_LAUNCH_CHECK("wm_median_fwd");
-    return WM_OK;
+    Med5Args ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_ROWS - 1) / M5_ROWS, 0, 1, -1, sep, idx_sh, RaggedSrc{x, x_sp, x_sh}};
+    ta.total = int64_t((N + 1) / 2) * ta.tiles_x * ta.tiles_y;
+    return tma ? launch_median5<false>(tm, ta, st) : launch_median5<true>(tm, ta, st);
 }
 
-extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int k, void* stream) {
+extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, int k, void* stream) {
     if (N == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && idx && gx, WM_E_NULL, "wm_median_bwd: null pointer");
     WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_bwd: kernel size must be 3 or 5 (got %d)", k);
+    WM_REQUIRE(idx_sh >= W, WM_E_ARG, "wm_median_bwd: the arg-median plane's row stride (%lld) must be >= W", (long long)idx_sh);
     const int64_t total = int64_t(N) * H * W;
     if (total <= 0) return WM_OK;
-    if (W % 16 == 0 && aligned(gx, 16) && tmap_ok(gy, int64_t(H) * W, W, 4) && tmap_ok(idx, int64_t(H) * W, W, 1))
-        return k == 3 ? launch_median_bwd_tma<3>(gy, idx, gx, N, H, W, (cudaStream_t)stream)
-                      : launch_median_bwd_tma<5>(gy, idx, gx, N, H, W, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tmap_ok(idx, int64_t(H) * idx_sh, idx_sh, 1)) {         // idx rows on 16-byte boundaries (the forward's padded stride)
+        if (W % 4 == 0 && aligned(gx, 16) && tmap_ok(gy, int64_t(H) * W, W, 4))
+            return k == 3 ? launch_median_bwd_tma<3, false>(gy, idx, idx_sh, gx, N, H, W, st)
+                          : launch_median_bwd_tma<5, false>(gy, idx, idx_sh, gx, N, H, W, st);
+        return k == 3 ? launch_median_bwd_tma<3, true>(gy, idx, idx_sh, gx, N, H, W, st)
+                      : launch_median_bwd_tma<5, true>(gy, idx, idx_sh, gx, N, H, W, st);
+    }
     const int64_t want = (total + 255) / 256, cap = int64_t(sm_count()) * 32;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (k == 3) median_bwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, idx, gx, N, H, W);
-    else median_bwd_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, idx, gx, N, H, W);
+    if (k == 3) median_bwd_kernel<3><<<grid, 256, 0, st>>>(gy, idx, idx_sh, gx, N, H, W);
+    else median_bwd_kernel<5><<<grid, 256, 0, st>>>(gy, idx, idx_sh, gx, N, H, W);
     WM_LAUNCH_CHECK("wm_median_bwd");
     return WM_OK;
 }

@@ -95,6 +95,33 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int
         ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// ---- planes whose rows are NOT 16-byte aligned (dense W % 4 != 0): no tensor map exists for them, so the same ring
+// of halo tiles is filled by every thread of the CTA with 4-byte cp.async (LDGSTS; source size 0 = zero fill outside
+// the plane, i.e. the zero padding), one commit group per tile.  The stencil code behind the ring is unchanged; only
+// its 128-bit global stores become scalar (the output rows are not 16-byte aligned either).
+struct RaggedSrc { const float* x; int64_t sp, sh; };      // plane n at x + n * sp, rows sh apart
+template <int NT>
+__device__ __forceinline__ void stage_box_cpasync(float* dst, const RaggedSrc& g, int n, int H, int W,
+                                                  int x0, int y0, int bw, int bh) {
+    const float* plane = g.x + int64_t(n) * g.sp;
+    for (int i = threadIdx.x; i < bw * bh; i += NT) {
+        const int ly = i / bw, lx = i - ly * bw, gy = y0 + ly, gx = x0 + lx;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const float* src = ok ? plane + int64_t(gy) * g.sh + gx : plane;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + i)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void cpasync_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+// 4 values at p .. p+3 of an output row that may end inside the group (columns gx .. gx+3 of a W-wide row)
+__device__ __forceinline__ void st4_ragged(float* p, const float4 v, int gx, int W) {
+    if (gx < W) p[0] = v.x;
+    if (gx + 1 < W) p[1] = v.y;
+    if (gx + 2 < W) p[2] = v.z;
+    if (gx + 3 < W) p[3] = v.w;
+}
+
 __device__ __forceinline__ float4 ldg128_nc(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));

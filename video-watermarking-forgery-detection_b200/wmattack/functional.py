@@ -96,16 +96,6 @@ def _flat(t: torch.Tensor, who: str) -> torch.Tensor:
     return _f32(t).contiguous()
 
 
-def _pad_w(t: torch.Tensor, mult: int) -> torch.Tensor:
-    """Zero-pad the last axis to a multiple of `mult` (one copy).  Layers whose border rule IS zero padding
-    (GaussianBlur, MedianBlur, the 8x8 JPEG family's ZeroPad2d) give identical results on the padded
-    tensor, whose rows are 16-byte aligned and therefore take the TMA kernels; the caller slices the result back
-    as a view.  Used by the median filter, where it pays for the copy (64x3x510x510: 5x5 forward 662 -> 490 us,
-    backward 1245 -> 411 us; 3x3 backward 671 -> 381 us); blur and the 8x8 JPEG family keep their ragged-row kernels."""
-    pad = (-t.shape[-1]) % mult
-    return F.pad(t, (0, pad)) if pad else t
-
-
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -423,32 +413,37 @@ def gaussian_blur(x: torch.Tensor, taps: Sequence[float], border: int = 0) -> to
     return _BlurFn.apply(x, taps if isinstance(taps, tuple) else tuple(float(t) for t in taps), border)
 
 
+def _idx_plane(b: int, c: int, h: int, w: int, device) -> torch.Tensor:
+    """Arg-median plane with 16-byte rows (the bytes past W are padding): the backward's idx ring stays on TMA for any W."""
+    return torch.empty((b, c, h, -(-w // 16) * 16), device=device, dtype=torch.uint8)
+
+
 class _MedianFn(torch.autograd.Function):
+    """Any geometry goes to the ring kernels: TMA-fed when the rows sit on 16-byte boundaries, cp.async-fed otherwise
+    (W % 4 != 0, odd strides) — no padding copy either way."""
+
     @staticmethod
     def forward(ctx, x, k):
         need_idx = bool(ctx.needs_input_grad[0])
-        _check_cuda(x, "median blur")
-        w0 = x.shape[-1]
-        if k == 5 or need_idx:      # ragged rows: the padded (TMA) path wins for 5x5 and whenever a backward follows
-            x = _pad_w(x, 4)
         x, sp, sh = _planes(x, "median blur")
         b, c, h, w = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
-        idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8) if need_idx else None
-        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), b * c, h, w, k, None, _stream())
-        ctx.k, ctx.w0 = k, w0
+        idx = _idx_plane(b, c, h, w, x.device) if need_idx else None
+        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), idx.shape[-1] if need_idx else 0,
+                  b * c, h, w, k, None, _stream())
+        ctx.k = k
         if need_idx:
             ctx.save_for_backward(idx)
-        return y if w == w0 else y[..., :w0]
+        return y
 
     @staticmethod
     def backward(ctx, gy):
         (idx,) = ctx.saved_tensors
-        gy = _flat(_pad_w(gy, 4) if idx.shape[-1] != gy.shape[-1] else gy, "median blur backward")   # idx has the padded width
+        gy = _flat(gy, "median blur backward")
         b, c, h, w = gy.shape
         gx = torch.empty_like(gy)
-        _lib.call("wm_median_bwd", gy.data_ptr(), idx.data_ptr(), gx.data_ptr(), b * c, h, w, ctx.k, _stream())
-        return (gx if w == ctx.w0 else gx[..., :ctx.w0]), None
+        _lib.call("wm_median_bwd", gy.data_ptr(), idx.data_ptr(), idx.shape[-1], gx.data_ptr(), b * c, h, w, ctx.k, _stream())
+        return gx, None
 
 
 def median_blur(x: torch.Tensor, k: int) -> torch.Tensor:
@@ -462,9 +457,9 @@ def median_blur_with_index(x: torch.Tensor, k: int):
     x, sp, sh = _planes(x.detach(), "median blur")
     b, c, h, w = x.shape
     y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
-    idx = torch.empty((b, c, h, w), device=x.device, dtype=torch.uint8)
-    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), idx.data_ptr(), b * c, h, w, k, None, _stream())
-    return y, idx
+    idx = _idx_plane(b, c, h, w, x.device)
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), idx.data_ptr(), idx.shape[-1], b * c, h, w, k, None, _stream())
+    return y, idx[..., :w]
 
 
 # --------------------------------------------------------------------------------------
@@ -1068,7 +1063,7 @@ def median_blur_into(x, k, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if k not in (3, 5) or sp % 4 or sh % 4 or x.data_ptr() % 16 or (k == 3 and w % 4) or not _out_ok(out, x.shape):
         return False
-    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, b * c, h, w, k, _ep_arg(ep), _stream())
+    _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, out.data_ptr(), None, 0, b * c, h, w, k, _ep_arg(ep), _stream())
     return True
 
 
