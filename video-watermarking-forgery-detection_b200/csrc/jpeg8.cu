@@ -262,7 +262,9 @@ constexpr int J8P_THREADS = 128, J8P_BLOCKS = 64, J8P_CHUNKS = 48;
 // [B,3,Hp,W] in coefficient-image order).  2: JpegSS backward from that state: the cotangent runs
 // through inv_color^T -> DCT -> times ss'(q) -> IDCT -> fwd_color^T, i.e. the linear pipeline with a
 // per-coefficient "mask" read from global memory (the quantisation steps cancel); no recompute.
-template <int VARIANT, int DMODE>
+// VEC = false: rows that are not 32-byte aligned or a width that is not a multiple of 8 (scalar, predicated row
+// access; the missing columns / rows of the last blocks are the zero padding of noise_layers/jpeg.py:171-173).
+template <int VARIANT, int DMODE, bool VEC = true>
 __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args a) {
     extern __shared__ float4 smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
     const int b = int(m / per), rem = int(m - int64_t(b) * per), by = rem / a.Wb;
     const int row0 = by * 8, col0 = (rem - by * a.Wb) * 8;
     const float* xr = a.x + int64_t(b) * a.x_sb + int64_t(row0 + 4 * h) * a.x_sh + col0;
+    const int ncol = min(8, a.W - col0);
 
     // ---- rows 4h .. 4h+3: colour transform + row DCT of the three channels -> scratch --------------
 #pragma unroll 2
@@ -283,9 +286,9 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
         const bool ok = active && (row0 + r) < a.H;
         const float* p = xr + int64_t(i) * a.x_sh;
         float R[8], G[8], Bl[8];
-        j8_load_row<true>(p, ok, 8, R);
-        j8_load_row<true>(p + a.x_sc, ok, 8, G);
-        j8_load_row<true>(p + 2 * a.x_sc, ok, 8, Bl);
+        j8_load_row<VEC>(p, ok, ncol, R);
+        j8_load_row<VEC>(p + a.x_sc, ok, ncol, G);
+        j8_load_row<VEC>(p + 2 * a.x_sc, ok, ncol, Bl);
         float y[8], u[8], v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -367,20 +370,20 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
             oB[c] = fmaf(a.inv[6], y[c], fmaf(a.inv[7], u[c], a.inv[8] * v[c]));
         }
         if (a.ep.x && ok) { ep_apply_n<8>(oR, xR.v, a.ep); ep_apply_n<8>(oG, xG.v, a.ep); ep_apply_n<8>(oB, xB.v, a.ep); }   // (dense, same layout as out)
-        j8_store_row<true>(p, ok, 8, oR);
-        j8_store_row<true>(p + plane, ok, 8, oG);
-        j8_store_row<true>(p + 2 * plane, ok, 8, oB);
+        j8_store_row<VEC>(p, ok, ncol, oR);
+        j8_store_row<VEC>(p + plane, ok, ncol, oG);
+        j8_store_row<VEC>(p + 2 * plane, ok, ncol, oB);
     }
 }
 
-template <int VARIANT, int DMODE = 0>
+template <int VARIANT, int DMODE = 0, bool VEC = true>
 static int j8_pair_launch(const J8Args& a, cudaStream_t st, const char* who) {
     if (a.n_blk == 0) return WM_OK;
     const size_t smem = size_t(J8P_CHUNKS) * J8P_BLOCKS * sizeof(float4);
-    cudaError_t e = cudaFuncSetAttribute(jpeg8_pair_kernel<VARIANT, DMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(jpeg8_pair_kernel<VARIANT, DMODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
     const int64_t blocks = (a.n_blk + J8P_BLOCKS - 1) / J8P_BLOCKS;
-    jpeg8_pair_kernel<VARIANT, DMODE><<<(unsigned)blocks, J8P_THREADS, smem, st>>>(a);
+    jpeg8_pair_kernel<VARIANT, DMODE, VEC><<<(unsigned)blocks, J8P_THREADS, smem, st>>>(a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
 }
@@ -557,10 +560,10 @@ static int j8_fwd_dispatch(const J8Args& a, bool vec, bool qout, cudaStream_t st
 }
 
 static int j8_fwd_any(const J8Args& a, int variant, int submode, bool vec, bool qout, cudaStream_t st, const char* who) {
-    if (vec && !qout && submode == 0) {          // fast path: two threads per block
-        if (variant == WM_JPEG8_HARD) return j8_pair_launch<WM_JPEG8_HARD>(a, st, who);
-        if (variant == WM_JPEG8_SS) return j8_pair_launch<WM_JPEG8_SS>(a, st, who);
-        if (variant == WM_JPEG8_MASK) return j8_pair_launch<WM_JPEG8_MASK>(a, st, who);
+    if (!qout && submode == 0) {                 // two threads per block; ragged rows take its scalar-access instantiation
+        if (variant == WM_JPEG8_HARD) return vec ? j8_pair_launch<WM_JPEG8_HARD>(a, st, who) : j8_pair_launch<WM_JPEG8_HARD, 0, false>(a, st, who);
+        if (variant == WM_JPEG8_SS) return vec ? j8_pair_launch<WM_JPEG8_SS>(a, st, who) : j8_pair_launch<WM_JPEG8_SS, 0, false>(a, st, who);
+        if (variant == WM_JPEG8_MASK) return vec ? j8_pair_launch<WM_JPEG8_MASK>(a, st, who) : j8_pair_launch<WM_JPEG8_MASK, 0, false>(a, st, who);
     }
 #define J8_CASE(V, S) if (variant == V && submode == S) return j8_fwd_dispatch<V, S>(a, vec, qout, st, who);
     J8_CASE(WM_JPEG8_HARD, 0) J8_CASE(WM_JPEG8_HARD, 2)
