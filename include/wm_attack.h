@@ -249,9 +249,10 @@ int wm_interp_is_tiled(int Hin, int Win, int Hout, int Wout, int N);
 /* ------------------------------------------------------------------------------------------
  * Fused Resize round trip (Resize.forward, noise_layers/resize.py:38-53):
  *   y = clamp( interpolate( interpolate(x, (Hm, Wm)), (H, W) ), 0, 1 )   in ONE kernel,
- * x: N planes [H, W] (plane stride x_sp, row stride x_sh, multiples of 4), y dense [N, H, W].
- * Supported when wm_resize_is_fused(...) == 1 (W % 4 == 0, both ratios Hm/H, Wm/W within
- * [0.45, 2.2]); otherwise compose two wm_interp_fwd calls.
+ * x: N planes [H, W] (plane stride x_sp, row stride x_sh), y dense [N, H, W].
+ * Supported when wm_resize_is_fused(...) == 1 (both ratios Hm/H, Wm/W within [0.45, 2.2]); otherwise compose two
+ * wm_interp_fwd calls.  Rows on 16-byte boundaries (W % 4 == 0, aligned x / y) are staged by TMA, any other geometry
+ * by the same kernel fed with cp.async (no store epilogue there).
  * tables: device workspace of wm_resize_table_floats(H, W, Hm, Wm) floats filled once per
  *   geometry by wm_resize_tables (band starts + weights of the per-axis operators U*D and
  *   their transposes); it may be cached and shared by any number of fwd/bwd calls.

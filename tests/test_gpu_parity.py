@@ -453,6 +453,14 @@ def test_ragged_width_ring_kernels():
                 y, gx = fwd_bwd(wmattack.MiddleBlur(k), xx, g)
                 yo, idx = O.median_blur(xx, k, return_index=True)
                 assert torch.equal(y, yo) and torch.equal(gx, O.median_blur_backward(g, idx, k))
+        # fused Resize round trip on the same ragged geometry (cp.async-fed instantiation), both directions of scaling
+        if min(shape[2:]) >= 20:
+            for ratio in (0.75, 1.5):
+                m = wmattack.Resize()
+                y, gx = fwd_bwd(lambda t: m(t, resize_ratio=ratio), x, g)
+                yo, go = oracle_fwd_bwd(lambda t: O.resize(t, ratio), x, g)
+                assert md(y, yo) <= 2e-5, (shape, ratio)
+                _assert_resize_grad(gx, go, x, ratio, "bicubic", coord_tol(shape[2], shape[3], ratio, 1e-5), f"ragged resize {shape} r={ratio}")
     # odd row stride: a column slice of a wider tensor
     wide = rnd((1, 3, 40, 203), 35).to(DEV)
     view = wide[..., 3:201]

@@ -31,6 +31,17 @@ __device__ __forceinline__ float med3(float a, float b, float c) {
 __device__ __forceinline__ float feq(float a, float b) {
     float d; asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d;
 }
+// packed fp32x2 FMA (FFMA2): two independent IEEE fmas per issue slot
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+}
 // code = sum_j match_j * 2^(n-1-j) (exact in fp32 for n <= 24): raster index of the FIRST match
 __device__ __forceinline__ int first_match(float code, int n) {
     return n - 1 - ((__float_as_int(code) >> 23) - 127);
@@ -447,6 +458,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
         const uint8_t* icol = ibufs + s * IS + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
         float g[K][WC];       // window columns -R .. 4+R-1 of the lane's 4 columns
         int ix[K][WC];
+        float fx[K == 5 ? K : 1][WC];      // 5x5: the positions as floats (FSET masks for the packed accumulation below)
         auto load_row = [&](int row, int slot) {
             const float* p = gcol + row * MT_BW;
             const float4 c = *reinterpret_cast<const float4*>(p);
@@ -459,6 +471,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
                 g[slot][R - 1 - i] = p[-1 - i]; g[slot][R + 4 + i] = p[4 + i];
                 ix[slot][R - 1 - i] = q[-1 - i]; ix[slot][R + 4 + i] = q[4 + i];
             }
+            if (K == 5) {
+#pragma unroll
+                for (int i = 0; i < WC; ++i) fx[slot][i] = __int2float_rn(ix[slot][i]);
+            }
         };
 #pragma unroll
         for (int j = 0; j < K - 1; ++j) load_row(j, j);
@@ -469,27 +485,39 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
             load_row(r + K - 1, (r + K - 1) % K);
             float4 o;
             float* op = &o.x;
+            if (K == 5) {
+                // 25-term gather, two adjacent outputs per packed FMA: acc2 += {[idx == want], [idx' == want]} * {g, g'}
+                // (fma(1, g, acc) == acc + g bit for bit, fma(0, g, acc) == acc for finite g): 2 FSET + 1 FFMA2 per
+                // pair of terms instead of 2 compares + 2 predicated adds; same summation order per output.
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float acc = 0.f;
+                for (int c2 = 0; c2 < 4; c2 += 2) {
+                    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int dy = -R; dy <= R; ++dy)
+                    for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
-                    for (int dx = -R; dx <= R; ++dx) {
-                        // q = p + (dy, dx): tile row r + R + dy = ring slot (r + R + dy) % K; p is at
-                        // window position (R - dy, R - dx) of q
-                        const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
-                        if (K == 5) {
-                            // compare + PREDICATED add (2 instructions, one on the half-rate ALU pipe) instead of the
-                            // compare + select + add the compiler emits: the 25-term gather is ALU-bound (1386 -> 866 us
-                            // at 64x3x1080x1920); the 9-term one is HBM-bound and keeps the select form
-                            asm("{\n .reg .pred p;\n setp.eq.s32 p, %1, %2;\n @p add.f32 %0, %0, %3;\n}"
-                                : "+f"(acc) : "r"(ix[slot][c4 + R + dx]), "r"(want), "f"(g[slot][c4 + R + dx]));
-                        } else {
+                        for (int dx = -R; dx <= R; ++dx) {
+                            const int slot = (r + R + dy) % K, col = c2 + R + dx;
+                            const float want = float((R - dy) * K + (R - dx));
+                            acc = ffma2(make_float2(feq(fx[slot][col], want), feq(fx[slot][col + 1], want)),
+                                        make_float2(g[slot][col], g[slot][col + 1]), acc);
+                        }
+                    op[c2] = acc.x; op[c2 + 1] = acc.y;
+                }
+            } else {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int dy = -R; dy <= R; ++dy)
+#pragma unroll
+                        for (int dx = -R; dx <= R; ++dx) {
+                            // q = p + (dy, dx): tile row r + R + dy = ring slot (r + R + dy) % K; p is at
+                            // window position (R - dy, R - dx) of q
+                            const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
                             acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
                         }
-                    }
-                op[c4] = acc;
+                    op[c4] = acc;
+                }
             }
             if (col_ok && gy0 + r < a.H) {
                 if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);

@@ -146,7 +146,10 @@ template <int BT> struct RBGeom {
 };
 
 // DIR 0: forward (clamp, mask out)   DIR 1: adjoint (cotangent masked in shared memory, no clamp)
-template <int BT, int DIR>
+// RAGGED: rows that are not 16-byte aligned (W % 4 != 0, odd strides) have no tensor map: the source tile is staged by
+// 4-byte cp.async from every thread (zero fill outside the plane) and the output leaves by scalar stores; the mask
+// words (rows of whole 16-byte groups for any W) stay on TMA.
+template <int BT, int DIR, bool RAGGED = false>
 __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_mask,
                                                                   const RBArgs a) {
     using G = RBGeom<BT>;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     }
     if (tid < G::NQ) yloq[tid] = min(max(__ldg(a.loy + min(oy0 + 4 * tid, a.H - 1)) - ys, 0), G::IH - BTV);
     if (tid == 0) {
-        tma_prefetch_desc(&tmap);
+        if (!RAGGED) tma_prefetch_desc(&tmap);
         mbar_init(&full, 1);
         mbar_fence_init();
     }
@@ -224,16 +227,25 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 
     const bool masked = DIR == 1 && a.mask != nullptr;
     const int mt0 = max(xs, 0) >> 7;                                 // first 128-column mask tile of the staged region
-    auto request = [&](int plane) {
-        mbar_expect_tx(&full, G::IW * G::IH * sizeof(float) + (masked ? 12 * G::IH * sizeof(uint32_t) : 0));
-        tma_load_3d(in, &tmap, xs, ys, plane, &full);
-        if (masked) tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
+    auto request = [&](int plane) {        // TMA: thread 0 only.  RAGGED: every thread (its share of the cp.async copies)
+        if (RAGGED) {
+            stage_box_cpasync<RB_THREADS>(in, RaggedSrc{a.src, a.s_sp, a.s_sh}, plane, a.H, a.W, xs, ys, G::IW, G::IH);
+            if (masked && tid == 0) {
+                mbar_expect_tx(&full, 12 * G::IH * sizeof(uint32_t));
+                tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
+            }
+        } else {
+            mbar_expect_tx(&full, G::IW * G::IH * sizeof(float) + (masked ? 12 * G::IH * sizeof(uint32_t) : 0));
+            tma_load_3d(in, &tmap, xs, ys, plane, &full);
+            if (masked) tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
+        }
     };
     int n = blockIdx.z;
-    if (tid == 0 && n < a.N) request(n);
+    if ((RAGGED || tid == 0) && n < a.N) request(n);
     for (int it = 0; n < a.N; n += gridDim.z, ++it) {
-        // ---- stage: the TMA box of this plane was requested one plane ago -----------------------
-        mbar_wait(&full, it & 1);
+        // ---- stage: the box of this plane was requested one plane ago ---------------------------
+        if (RAGGED) { cpasync_wait<0>(); __syncthreads(); }
+        if (!RAGGED || masked) mbar_wait(&full, it & 1);
         if (masked) {
             // gy .* mask in place; the 4 ballot words of a (row, 128-column tile) sit in one uint4 of mb
             constexpr int C4 = G::IW / 4;
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         }
         __syncthreads();
         // `in` is dead: prefetch the next plane's tile while the V pass runs
-        if (tid == 0 && n + gridDim.z < a.N) request(n + gridDim.z);
+        if ((RAGGED || tid == 0) && n + gridDim.z < a.N) request(n + gridDim.z);
 
         // ---- V pass: rows 4p .. 4p+3 x 4 columns per lane from one shared window of tmp --------------
         {
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                 // store epilogue: x at the output positions is requested now (L2 hits: the tile was just
                 // staged from the same lines) so that its latency hides under the window loop
                 float4 xe[4];
-                if (DIR == 0 && a.ep.x) {
+                if (!RAGGED && DIR == 0 && a.ep.x) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         xe[k] = (okc && 4 * qd + k < th) ? ldg128_nc(a.ep.x + (drow - a.dst) + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -318,7 +330,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
                         const float4 c = clamp01_nan4(acc);
-                        if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4v(c, xe[k], a.ep) : c);
+                        if (RAGGED) { if (okc && okr) st4_ragged(drow + k * a.W, c, ox0 + 4 * lane, a.W); }
+                        else if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4v(c, xe[k], a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc.y);
@@ -329,7 +342,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                             if (lane < 4 && okr) mrow[k * mrow_k] = w;
                         }
                     } else if (okc && okr) {
-                        stg128(drow + k * a.W, acc);
+                        if (RAGGED) st4_ragged(drow + k * a.W, acc, ox0 + 4 * lane, a.W);
+                        else stg128(drow + k * a.W, acc);
                     }
                 }
             }
@@ -396,7 +410,7 @@ static void rb_prove(const float* tx, const float* ty, int H, int W, int* flag, 
 }
 
 static inline bool rb_ok(int H, int W, int Hm, int Wm, int N) {
-    if (H <= 0 || W <= 0 || Hm <= 0 || Wm <= 0 || N <= 0 || W % 4 != 0) return false;
+    if (H <= 0 || W <= 0 || Hm <= 0 || Wm <= 0 || N <= 0) return false;
     const float rh = (float)Hm / (float)H, rw = (float)Wm / (float)W;
     return rh >= RB_RATIO_MIN && rh <= RB_RATIO_MAX && rw >= RB_RATIO_MIN && rw <= RB_RATIO_MAX &&
            (H + RB_TH - 1) / RB_TH <= 65535 && tmap_encoder() != nullptr;
@@ -414,16 +428,16 @@ static inline int rb_band(int H, int W, int Hm, int Wm) {
 
 static inline RBAxis rb_axis(int n, int nm) { return RBAxis{n, nm, (float)n / (float)nm, (float)nm / (float)n}; }
 
-template <int BT, int DIR>
+template <int BT, int DIR, bool RAGGED>
 static int rb_launch(const RBArgs& a, const CUtensorMap& tm, const CUtensorMap& tmm, cudaStream_t st, const char* who) {
     const size_t smem = RBGeom<BT>::smem;
-    cudaError_t e = cudaFuncSetAttribute(rb_banded_kernel<BT, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rb_banded_kernel<BT, DIR, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
     // persistent over planes: ~2 CTAs per SM in total, each tile position walks its share of planes
     const int pos = a.tiles_x * a.tiles_y;
     int gz = (2 * sm_count()) / pos;
     gz = gz < 1 ? 1 : (gz > a.N ? a.N : gz);
-    rb_banded_kernel<BT, DIR><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, tmm, a);
+    rb_banded_kernel<BT, DIR, RAGGED><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, tmm, a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
 }
@@ -472,7 +486,7 @@ extern "C" int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int
     return WM_OK;
 }
 
-static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* dst, uint32_t* mask, const float* tables,
+static int rb_run(int dir, bool ragged, const float* src, int64_t s_sp, int64_t s_sh, float* dst, uint32_t* mask, const float* tables,
                   int N, int H, int W, int Hm, int Wm, const wm_store_epilogue* ep, void* stream, const char* who) {
     const int BT = rb_band(H, W, Hm, Wm);
     const float* fx = tables; const float* fy = fx + rb_axis_words(W, BT);
@@ -490,8 +504,9 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
     cudaStream_t st = (cudaStream_t)stream;
 #define RB_CASE(B)                                                                                                  \
     case B:                                                                                                         \
-        rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh, RBGeom<B>::IW,          \
-                         RBGeom<B>::IH);                                                                            \
+        if (!ragged)                                                                                                \
+            rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh, RBGeom<B>::IW,      \
+                             RBGeom<B>::IH);                                                                        \
         if (!rc && dir == 1 && mask)                                                                                \
             rc = tmap_planes(&tmm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, mask, N, H, 4 * a.tiles_x,                    \
                              int64_t(H) * 4 * a.tiles_x, 4 * a.tiles_x, 12, RBGeom<B>::IH);                         \
@@ -499,7 +514,8 @@ static int rb_run(int dir, const float* src, int64_t s_sp, int64_t s_sh, float* 
             set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, rc);                                           \
             return WM_E_ARG;                                                                                        \
         }                                                                                                           \
-        return dir == 0 ? rb_launch<B, 0>(a, tm, tmm, st, who) : rb_launch<B, 1>(a, tm, tmm, st, who);
+        if (ragged) return dir == 0 ? rb_launch<B, 0, true>(a, tm, tmm, st, who) : rb_launch<B, 1, true>(a, tm, tmm, st, who); \
+        return dir == 0 ? rb_launch<B, 0, false>(a, tm, tmm, st, who) : rb_launch<B, 1, false>(a, tm, tmm, st, who);
     switch (BT) {
         RB_CASE(8)
         RB_CASE(10)
@@ -519,11 +535,13 @@ extern "C" int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* 
     WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_fwd: mode must be 0 (bilinear) or 1 (bicubic)");
     if (N == 0) return WM_OK;
     WM_REQUIRE(rb_ok(H, W, Hm, Wm, N), WM_E_SHAPE,
-               "wm_resize_fwd: geometry H=%d W=%d mid=%dx%d N=%d is outside the fused range (W %% 4 == 0, ratio %.2f..%.2f); "
+               "wm_resize_fwd: geometry H=%d W=%d mid=%dx%d N=%d is outside the fused range (ratio %.2f..%.2f); "
                "use wm_interp_fwd twice", H, W, Hm, Wm, N, RB_RATIO_MIN, RB_RATIO_MAX);
-    WM_REQUIRE(tmap_ok(x, x_sp, x_sh, 4) && aligned(y, 16) && (!maskbits || aligned(maskbits, 16)), WM_E_ALIGN,
-               "wm_resize_fwd: x, y, maskbits must be 16-byte aligned with strides multiples of 4 elements");
-    return rb_run(0, x, x_sp, x_sh, y, maskbits, tables, N, H, W, Hm, Wm, ep, stream, "wm_resize_fwd");
+    WM_REQUIRE(!maskbits || aligned(maskbits, 16), WM_E_ALIGN, "wm_resize_fwd: maskbits must be 16-byte aligned");
+    // rows on 16-byte boundaries: TMA; otherwise (W % 4 != 0, odd strides) the cp.async-fed instantiation
+    const bool ragged = !(W % 4 == 0 && tmap_ok(x, x_sp, x_sh, 4) && aligned(y, 16));
+    if (ragged) WM_EP_REJECT(ep, "wm_resize_fwd (rows not 16-byte aligned)");
+    return rb_run(0, ragged, x, x_sp, x_sh, y, maskbits, tables, N, H, W, Hm, Wm, ep, stream, "wm_resize_fwd");
 }
 
 extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
@@ -535,7 +553,7 @@ extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* g
     WM_REQUIRE(rb_ok(H, W, Hm, Wm, N), WM_E_SHAPE,
                "wm_resize_bwd: geometry H=%d W=%d mid=%dx%d N=%d is outside the fused range; use wm_interp_bwd twice",
                H, W, Hm, Wm, N);
-    WM_REQUIRE(aligned(gy, 16) && aligned(gx, 16) && (!maskbits || aligned(maskbits, 16)), WM_E_ALIGN,
-               "wm_resize_bwd: gy, gx, maskbits must be 16-byte aligned");
-    return rb_run(1, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, nullptr, stream, "wm_resize_bwd");
+    WM_REQUIRE(!maskbits || aligned(maskbits, 16), WM_E_ALIGN, "wm_resize_bwd: maskbits must be 16-byte aligned");
+    const bool ragged = !(W % 4 == 0 && aligned(gy, 16) && aligned(gx, 16));
+    return rb_run(1, ragged, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, nullptr, stream, "wm_resize_bwd");
 }

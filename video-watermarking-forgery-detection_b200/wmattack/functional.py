@@ -828,8 +828,8 @@ def resize_roundtrip(x, mid_hw, mode: str = "bicubic"):
     h, w = x.shape[2:]
     mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
     n = x.shape[0] * x.shape[1]
-    if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and x.stride(2) % 4 == 0 and x.stride(1) % 4 == 0 \
-            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 \
+    # any width / stride: rows off the 16-byte grid take the kernel's cp.async-fed instantiation (decided by the library)
+    if _lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) \
             and _resize_tables(x.device, h, w, mid_hw, _MODES[mode]) is not None:
         return _ResizeFusedFn.apply(x, mid_hw, _MODES[mode])
     mid = interpolate(x, mid_hw, mode)
@@ -1082,8 +1082,8 @@ def resize_roundtrip_into(x, mid_hw, mode, out, ep=None) -> bool:
     mid_hw = (int(mid_hw[0]), int(mid_hw[1]))
     n = x.shape[0] * x.shape[1]
     x, sp, sh = _planes(x, "resize")
-    if not (_lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and sp % 4 == 0 and sh % 4 == 0
-            and x.data_ptr() % 16 == 0 and _out_ok(out, x.shape)):
+    if not (_lib.load().wm_resize_is_fused(h, w, mid_hw[0], mid_hw[1], n) and w % 4 == 0 and sp % 4 == 0 and sh % 4 == 0
+            and x.data_ptr() % 16 == 0 and _out_ok(out, x.shape)):       # the store epilogue needs the TMA-fed instantiation
         return False
     tables = _resize_tables(x.device, h, w, mid_hw, _MODES[mode])
     if tables is None:
