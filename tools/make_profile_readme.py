@@ -1,10 +1,10 @@
-"""Regenerates profiles/README.md from profiles/bench_r1_1gpu.json + profiles/ncu_r1_launches.csv
-(keeps the hand-written "Other BASELINE shapes" section)."""
+"""Regenerates profiles/README.md from profiles/bench_r2_1gpu.json + profiles/ncu_r2_launches.csv
+(keeps the hand-written sections from "## Experiments" on)."""
 import collections, csv, json, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
-d = json.load(open(os.path.join(P, "bench_r1_1gpu.json")))
-lines = [l for l in open(os.path.join(P, "ncu_r1_launches.csv")) if not l.startswith("==")]
+d = json.load(open(os.path.join(P, "bench_r2_1gpu.json")))
+lines = [l for l in open(os.path.join(P, "ncu_r2_launches.csv")) if not l.startswith("==")]
 agg = collections.OrderedDict()
 for row in csv.DictReader(lines):
     if row.get("Metric Name") != "gpu__time_duration.sum":
@@ -14,14 +14,17 @@ for row in csv.DictReader(lines):
     agg.setdefault(row["Kernel Name"], []).append(v)
 tot = sum(sum(v) for k, v in agg.items() if "wm::" in k)
 old = open(os.path.join(P, "README.md")).read() if os.path.exists(os.path.join(P, "README.md")) else ""
-tail = old[old.index("## Other BASELINE shapes"):] if "## Other BASELINE shapes" in old else ""
-out = ["# Round-1 measurements (B200, 64x3x512x512 fp32, BASELINE config 2)", "",
-       "Source files: `bench_r1_1gpu.json` (python bench.py), `bench_r1_2gpu.json`, `bench_r1_8gpu.json`,",
-       "`ncu_r1_launches.csv` (ncu --metrics gpu__time_duration.sum --clock-control none, same command),",
-       "`ncu_r1_*.txt` (ncu --set full summaries per kernel), `ncu_traffic.json` (DRAM bytes per launch).", "",
-       f"Step = {d['ms_per_step']} ms, value = {d['value']} Mpix/s on 1 GPU (8 GPUs: bench_r1_8gpu.json), e2e (pinned fp32 host input, "
-       f"H2D inside the timed region) = {d['e2e']['value']} Mpix/s, e2e_u8 (8-bit host frames) = {d['e2e_u8']['value']} Mpix/s, "
-       f"CPU oracle port = {d['cpu_baseline']['value']} Mpix/s on {d['cpu_baseline']['cores']} threads.", "",
+tail = old[old.index("## Experiments"):] if "## Experiments" in old else ""
+out = ["# Round-2 measurements (B200, 64x3x512x512 fp32, BASELINE config 2: 7 layers, 14 kernels per step)", "",
+       "Source files: `bench_r2_1gpu.json` (python bench.py --steps 20 --warmup 5), `bench_r2_2gpu.json` (torchrun, 2 ranks),",
+       "`ncu_r2_launches.csv` (ncu --metrics gpu__time_duration.sum --clock-control none, same command),",
+       "`ncu_r2_*.txt` (ncu --set full summaries of the kernels changed in round 2; `ncu_r1_*.txt` for the others),",
+       "`ncu_traffic.json` (DRAM bytes per launch).  All produced by `tools/gpu_profile_r2.sh`.  Round-1 records are kept",
+       "(`bench_r1_*.json`, `ncu_r1_*`, `sweep_r1.md`).", "",
+       f"Step = {d['ms_per_step']} ms, value = {d['value']} Mpix/s on 1 GPU, whole-step roofline fraction {d['roofline']['whole_step']['frac']}; "
+       f"e2e (pinned fp32 host batch in AND 201 MB result out, inside the timed region) = {d['e2e']['value']} Mpix/s, e2e_u8 (8-bit host frames) = {d['e2e_u8']['value']} Mpix/s; "
+       f"the unmodified reference on the host cores = {d['cpu_baseline']['value']} Mpix/s on {d['cpu_baseline']['cores']} threads, run eagerly on the same B200 = "
+       f"{d['reference_gpu_eager']['value']} Mpix/s.", "",
        "## Per layer, CUDA-event time inside the timed region (fraction of the measured 6536.7 GB/s copy peak on ALGORITHMIC bytes)", "",
        "| layer.direction | us | alg. GB/s | frac |", "|---|---|---|---|"]
 for k, v in d["kernels"].items():
