@@ -13,7 +13,7 @@ def run(layer, x, **kw):
     y.backward(torch.rand_like(y))
     assert torch.isfinite(y).all() and torch.isfinite(xx.grad).all(), (type(layer).__name__, tuple(x.shape), kw)
     return y
-for shape in ((2, 3, 48, 64), (1, 3, 70, 132), (1, 3, 33, 20), (2, 3, 128, 256)):
+for shape in ((2, 3, 48, 64), (1, 3, 70, 132), (1, 3, 33, 20), (2, 3, 128, 256), (1, 3, 37, 131), (2, 3, 70, 510)):
     x = torch.rand(*shape, device=dev)
     h, w = shape[2:]
     if h % 16 == 0 and w % 16 == 0:
