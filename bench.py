@@ -251,7 +251,8 @@ def ours(args, rank, world, dev):
     e2e = run_e2e(args, dj, comb, g, rank, world, dev, px_step)
     e2e_u8 = run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=True)
     extras = {}
-    for name, fn in (("config1", lambda: config1_gpu(dev)), ("config3", lambda: config3(world, dev)),
+    for name, fn in (("config2_natural", lambda: config2_natural(args, dj, comb, g, world, dev, px_step)),
+                     ("config1", lambda: config1_gpu(dev)), ("config3", lambda: config3(world, dev)),
                      ("config5", lambda: config5(rank, world, dev)),
                      ("train_step", lambda: train_step_leg(args, rank, world, dev))):
         if name in args.skip:
@@ -405,6 +406,34 @@ def load_ncu_traffic(kernel_key):
 
 
 # ----------------------------------------------------------------------- extra legs (configs 1, 3, 5)
+def config2_natural(args, dj, comb, g, world, dev, px_step):
+    """The headline step on NATURAL-LIKE frames (SURVEY 8(d) "value distributions"): low-pass filtered noise quantised to
+    k/255 — post-Quantization statistics, where the median windows tie, most DCT coefficients fall in the zero bin and
+    the clamps of Resize / Gaussian noise rarely fire.  The kernels are data-oblivious except for rare-path branches."""
+    gen = torch.Generator(dev).manual_seed(7)
+    x = torch.rand(B, 3, H, W, device=dev, generator=gen)
+    k = torch.ones(3, 1, 9, 9, device=dev) / 81.0
+    for _ in range(2):                                       # two 9x9 box blurs: smooth, image-like spectrum
+        x = torch.nn.functional.conv2d(x, k, padding=4, groups=3)
+    x = (x - x.amin()) / (x.amax() - x.amin())
+    x = (torch.round(x * 255) / 255).contiguous().requires_grad_(True)
+    for s in range(max(2, args.warmup // 2)):
+        run_step(dj, comb, x, g, s)
+    torch.cuda.synchronize()
+    ms = timed(lambda: [run_step(dj, comb, x, g, s) for s in range(4)], max(1, args.steps // 4), 0, world, dev) / 4
+    ties = float((wmattack_unique_fraction(x.detach()[:2])))
+    return {"workload": "the config-2 step on smooth frames quantised to k/255 (two 9x9 box blurs of uniform noise)",
+            "ms_per_step": round(ms, 4), "value": round(world * px_step / ms / 1e3, 1), "unit": "Mpix/s",
+            "fraction_of_3x3_windows_with_a_repeated_value": round(ties, 3)}
+
+
+def wmattack_unique_fraction(x):
+    """Fraction of 3x3 windows that hold a repeated value (what makes a median window tie)."""
+    u = torch.nn.functional.unfold(x.reshape(-1, 1, *x.shape[2:]), 3, padding=1)          # [N, 9, L]
+    srt = u.sort(dim=1).values
+    return (srt[:, 1:] == srt[:, :-1]).any(dim=1).float().mean()
+
+
 def config1_gpu(dev):
     """BASELINE config 1's workload (DiffJPEG q50 fwd+bwd, 16x3x256x256) on this GPU, eager and as a
     replayed CUDA graph (at this size the call is launch-bound)."""

@@ -129,18 +129,21 @@ typedef struct wm_jpeg8_params {
     int subsample;        /* 0, or 2 = in-block chroma decimation of jpeg.py:202-211 */
 } wm_jpeg8_params;
 
-int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
+/* x_dtype / gx_dtype (WM_DT_*): float16 / bfloat16 images and gradients are read / stored directly on the vector
+ * path (W % 8 == 0, subsample == 0, pointers aligned to 8 elements, strides multiples of 8); any other geometry
+ * takes float32 only (WM_E_ARG otherwise).  wm_jpeg8_bwd reads x (float32) only for JpegSS without saved state. */
+int wm_jpeg8_fwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                  float* y, int B, int H, int W, const wm_jpeg8_params* params_host,
                  const wm_store_epilogue* ep, void* stream);
 int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
                  const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh,
-                 float* gx, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
+                 void* gx, int gx_dtype, int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
 /* JpegSS training pair: the forward also saves ss'(q) of every coefficient (d: [B,3,ceil8(H),W],
  * 12 B/px) and the backward runs from gy + d alone (no x, no recompute).  Fast-path geometry only:
  * W % 8 == 0, subsample == 0, 32-byte aligned pointers, strides multiples of 8. */
-int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
+int wm_jpeg8_fwd_save(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
                       int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
-int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, float* gx,
+int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, void* gx, int gx_dtype,
                        int B, int H, int W, const wm_jpeg8_params* params_host, void* stream);
 /* std_quantization output (noise_layers/jpeg.py:52-82) as a [B,3,Hp,Wp] coefficient image,
  * Hp/Wp = H/W rounded up to x8: the integer-exact parity target for Jpeg. */
@@ -186,8 +189,9 @@ int wm_median_bwd(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx
 #define WM_RNG_FROM_DEVICE 0xFFFFFFFFFFFFFFFFull
 int wm_rng_reserve(uint64_t* state, uint64_t* slot, uint64_t count, void* stream);
 
-/* Gaussian (noise_layers/gaussian.py:10-17, clamp=1) and GN (noise_layers/gaussian_noise.py:13-16, clamp=0) */
-int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
+/* Gaussian (noise_layers/gaussian.py:10-17, clamp=1) and GN (noise_layers/gaussian_noise.py:13-16, clamp=0).
+ * x_dtype / gx_dtype (WM_DT_*): the image may be float16 / bfloat16, the masked gradient is stored in that type. */
+int wm_gaussnoise_fwd(const void* x, int x_dtype, float* y, int64_t n, float mean, float std, int clamp,
                       uint64_t seed, uint64_t offset, const float* inject,
                       const wm_store_epilogue* ep, void* stream);
 int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, float mean, float std,
@@ -196,9 +200,9 @@ int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int64_t n, flo
  * bit per value — the pass mask of torch.clamp's backward, 0 <= x + noise <= 1 — into maskbits
  * (4 * ceil(n / 128) words, 16-byte aligned: word 4*(i/128) + j holds value i + 4*l + j at bit l), and the
  * backward is gx = bit ? gy : 0: it reads neither x nor regenerates the noise. */
-int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
+int wm_gaussnoise_fwd_mask(const void* x, int x_dtype, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
                            uint64_t seed, uint64_t offset, const float* inject, void* stream);
-int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, float* gx, int64_t n, void* stream);
+int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, void* gx, int gx_dtype, int64_t n, void* stream);
 /* SaltPepper (noise_layers/salt_pepper_noise.py:11-19) */
 int wm_saltpepper_fwd(const float* x, float* y, int64_t n, float prob,
                       uint64_t seed, uint64_t offset, const float* inject, void* stream);
@@ -281,7 +285,7 @@ int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, i
  *   (same fp32 operation order).  The backward is the identity on x (straight-through), so
  *   the K slices of a bank reduce with wm_slice_sum: out[i] = sum_k g[k*n + i].
  * Tamper / splice (models/IRNcrop_model.py:348, models/IRNp_model.py:600):
- *   out = a * (1 - mask) + b * mask,  a, b: [B, C, H, W], mask: [B, 1, H, W], H*W % 4 == 0.
+ *   out = a * (1 - mask) + b * mask,  a, b: [B, C, H, W], mask: [B, 1, H, W] (any H*W; vector kernel when H*W % 4 == 0).
  *   bwd: ga = gy * (1 - mask), gb = gy * mask (either may be NULL).
  * ------------------------------------------------------------------------------------------ */
 /* 8-bit frames -> [0,1] float32, dst[i] = src[i] / 255 (data format on the host side of the path:

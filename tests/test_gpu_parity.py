@@ -412,6 +412,44 @@ def test_diffjpeg_reads_half_inputs_and_stores_half_gradients(dt):
         assert torch.equal(m(clip[:, :, 1]), m(clip[:, :, 1].float()))
 
 
+@pytest.mark.parametrize("dt", (torch.bfloat16, torch.float16))
+def test_jpeg8_family_reads_half_inputs_and_stores_half_gradients(dt):
+    """Same boundary property for the 8x8 JPEG family (vector path): bit-identical to casting outside the kernels."""
+    x = rnd((2, 3, 40, 64), 24).to(DEV).to(dt)
+    g = rnd((2, 3, 40, 64), 25).to(DEV)
+    for layer in (wmattack.JpegCompression(DEV), wmattack.JpegMask(50), wmattack.JpegSS(50), wmattack.Jpeg(50)):
+        xa = x.clone().requires_grad_(True)
+        ya = layer(xa)
+        ya.backward(g)
+        xb = x.float().requires_grad_(True)
+        yb = layer(xb)
+        yb.backward(g)
+        assert ya.dtype == torch.float32 and torch.equal(ya, yb), type(layer).__name__
+        assert xa.grad.dtype == dt and torch.equal(xa.grad, xb.grad.to(dt)), type(layer).__name__
+    # a ragged width converts outside (float32 path) and still returns the gradient in the input's type
+    xr = rnd((1, 3, 21, 30), 26).to(DEV).to(dt).requires_grad_(True)
+    wmattack.JpegMask(50)(xr).backward(rnd((1, 3, 21, 30), 27).to(DEV))
+    assert xr.grad.dtype == dt and torch.isfinite(xr.grad.float()).all()
+
+
+@pytest.mark.parametrize("dt", (torch.bfloat16, torch.float16))
+def test_gaussian_noise_reads_half_inputs_and_stores_half_gradients(dt):
+    x = rnd((2, 3, 24, 37), 28).to(DEV).to(dt)                  # odd element count: the tail path too
+    g = rnd((2, 3, 24, 37), 29).to(DEV)
+    noise = (torch.randn(2, 3, 24, 37, generator=torch.Generator().manual_seed(30)) * 0.3).to(DEV)
+    for layer in (wmattack.Gaussian(), wmattack.GN(0.0025)):
+        kw = {"noise": noise}
+        arg = (lambda t: t) if isinstance(layer, wmattack.Gaussian) else (lambda t: (t, None))
+        xa = x.clone().requires_grad_(True)
+        ya = layer(arg(xa), **kw)
+        ya.backward(g)
+        xb = x.float().requires_grad_(True)
+        yb = layer(arg(xb), **kw)
+        yb.backward(g)
+        assert ya.dtype == torch.float32 and torch.equal(ya, yb), type(layer).__name__
+        assert xa.grad.dtype == dt and torch.equal(xa.grad, xb.grad.to(dt)), type(layer).__name__
+
+
 @pytest.mark.parametrize("k", (3, 5))
 def test_median_forward_bit_exact(k):
     for xn in ("x2028", "xs32"):
@@ -569,6 +607,20 @@ def test_cropout_and_dropout_gradients():
     WF.dropout_mask(x, c, m).sum().backward()
     assert float(x.grad[..., :12].min()) == 1 and float(x.grad[..., 12:].max()) == 0
     assert float(c.grad[..., :12].max()) == 0 and float(c.grad[..., 12:].min()) == 1
+    # odd plane size (H*W % 4 != 0: planes do not start on 16-byte boundaries): mask dropout and splice, values + gradients
+    xo, co, go = rnd((2, 3, 7, 9), 3), rnd((2, 3, 7, 9), 4), rnd((2, 3, 7, 9), 5)
+    mo = (rnd((7, 9), 6) > 0.5).float()
+    a, b = xo.to(DEV).requires_grad_(True), co.to(DEV).requires_grad_(True)
+    y = WF.dropout_mask(a, b, mo.to(DEV))
+    y.backward(go.to(DEV))
+    assert torch.equal(y.detach().cpu(), O.dropout_mask(xo, co, mo))
+    assert torch.equal(a.grad.cpu(), go * mo) and torch.equal(b.grad.cpu(), go * (1 - mo))
+    ms = (rnd((2, 1, 7, 9), 7) > 0.7).float()
+    a, b = xo.to(DEV).requires_grad_(True), co.to(DEV).requires_grad_(True)
+    out = wmattack.Splice()(a, b, ms.to(DEV))
+    out.backward(go.to(DEV))
+    assert torch.equal(out.detach().cpu(), xo * (1 - ms) + co * ms)
+    assert torch.equal(a.grad.cpu(), go * (1 - ms)) and torch.equal(b.grad.cpu(), go * ms)
 
 
 # ============================================================================= resize / crop
@@ -958,6 +1010,19 @@ def test_attack_epilogue_bank_and_splice_match_the_trainer_arithmetic():
         parts.append(wmattack.AttackEpilogue()(x.to(DEV), s))
     assert torch.equal(yb.detach(), torch.cat(parts, 0))
     assert md(xx.grad, gk.view(5, 2, 3, 40, 64).sum(0)) <= 1e-6
+    # odd element count per image: the slices of the K-way batch do not start on 16-byte boundaries (scalar epilogue / sum)
+    xo = rnd((1, 3, 7, 9), 57)
+    lo = [wmattack.JpegMask(50), wmattack.MiddleBlur(3), wmattack.GaussianBlur(), wmattack.Identity()]
+    xa = xo.to(DEV).requires_grad_(True)
+    yo = wmattack.AttackBank(lo)(xa)
+    go = rnd((4, 3, 7, 9), 58)
+    yo.backward(go.to(DEV))
+    ref = []
+    for layer in lo:
+        sim = layer(xo.to(DEV)).cpu()
+        ref.append(((xo + (torch.clamp(sim, 0, 1) - xo)) * 255.).round() / 255.)
+    assert torch.equal(yo.detach().cpu(), torch.cat(ref, 0))
+    assert md(xa.grad, go.sum(0, keepdim=True)) <= 1e-6
 
 
 @pytest.mark.parametrize("mode", (0, 1, 3))

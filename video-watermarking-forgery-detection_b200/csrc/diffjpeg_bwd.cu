@@ -17,9 +17,10 @@ __device__ __forceinline__ float clamp_tie_mask_mul(float g, float u) {
     return open_in ? g : (closed_in ? 0.5f * g : 0.f);
 }
 
-template <int ROUND>
+template <int ROUND, bool TYPED = false>
 __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJArgs a) {
     constexpr int NT = DJB_THREADS;
+    const int odt = TYPED ? a.out_dt : WM_DT_F32;
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
 
     // ---- forward recompute: Y -> SC_Y (column-inverse-transformed), chroma -> SC_CB/SC_CR,
     //      round'(q) -> SC_DY / SC_DC
-    dj_load_block<NT>(a, t, scr);
+    dj_load_block<NT, TYPED>(a, t, scr);
     dj_luma_columns<ROUND, false, true, NT>(scr, f);
     QuadCoef qx, qy;
     quad_coef_init(qx, t.bx);
@@ -146,9 +147,9 @@ __global__ void __launch_bounds__(DJB_THREADS, 3) diffjpeg_bwd_kernel(const DJAr
             }
             if (t.active) {
                 const int64_t p = go + int64_t(r) * a.W;
-                st8_typed(a.out, p, oR, a.out_dt);
-                st8_typed(a.out, p + plane, oG, a.out_dt);
-                st8_typed(a.out, p + 2 * plane, oB, a.out_dt);
+                st8_typed(a.out, p, oR, odt);
+                st8_typed(a.out, p + plane, oG, odt);
+                st8_typed(a.out, p + 2 * plane, oB, odt);
             }
         }
     }
@@ -162,8 +163,10 @@ __device__ __forceinline__ float code_mul(float g, unsigned code) {      // 0 ->
     return (code & 1u) ? g : ((code & 2u) ? 0.5f * g : 0.f);
 }
 
+template <bool TYPED = false>
 __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const DJArgs a) {
     constexpr int NT = DJ_THREADS;
+    const int odt = TYPED ? a.out_dt : WM_DT_F32;
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
@@ -285,9 +288,9 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_bwd_saved_kernel(const
             }
             if (t.active) {
                 const int64_t p = go + int64_t(r) * a.W;
-                st8_typed(a.out, p, oR, a.out_dt);
-                st8_typed(a.out, p + plane, oG, a.out_dt);
-                st8_typed(a.out, p + 2 * plane, oB, a.out_dt);
+                st8_typed(a.out, p, oR, odt);
+                st8_typed(a.out, p + plane, oG, odt);
+                st8_typed(a.out, p + 2 * plane, oB, odt);
             }
         }
     }
@@ -311,7 +314,8 @@ extern "C" int wm_diffjpeg_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc
     a.dY = const_cast<float*>(dY); a.dC = const_cast<float*>(dC);
     a.cm = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(clamp_codes));
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
-    return dj_launch(diffjpeg_bwd_saved_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd_saved");
+    if (gx_dtype != WM_DT_F32) return dj_launch(diffjpeg_bwd_saved_kernel<true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd_saved");
+    return dj_launch(diffjpeg_bwd_saved_kernel<false>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd_saved");
 }
 
 
@@ -328,5 +332,6 @@ extern "C" int wm_diffjpeg_bwd(const void* x, int x_dtype, int64_t x_sb, int64_t
     a.x = x; a.x_dt = x_dtype; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh;
     a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = reinterpret_cast<float*>(gx); a.out_dt = gx_dtype;
     const size_t smem = SC_BWD_CHUNKS * DJB_THREADS * sizeof(float4);
-    DJ_DISPATCH_ROUND(diffjpeg_bwd_kernel, a, DJB_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd")
+    if (x_dtype != WM_DT_F32 || gx_dtype != WM_DT_F32) { DJ_DISPATCH_ROUND_T(diffjpeg_bwd_kernel, true, a, DJB_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd") }
+    DJ_DISPATCH_ROUND_T(diffjpeg_bwd_kernel, false, a, DJB_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_bwd")
 }

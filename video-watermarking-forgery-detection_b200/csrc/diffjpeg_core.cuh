@@ -194,16 +194,19 @@ __device__ __forceinline__ void dj_consume_pair(const RowPair& p, int rp, float4
 // Phase 1: stream the 8 RGB rows of the thread's block, two rows at a time, always one pair
 // of loads (6 x LDG.E.256) in flight ahead of the arithmetic.  Rolled (2 iterations) to keep
 // the kernel inside the instruction cache.
-template <int NT>
+// TYPED = false: the image is float32 and the element-type switch folds away at compile time (the float32 kernels
+// are exactly the pre-typed ones); TYPED = true instantiations read a.x_dt / store a.out_dt elements.
+template <int NT, bool TYPED = false>
 __device__ __forceinline__ void dj_load_block(const DJArgs& a, const DJThread& t, float4* scr) {
     const int64_t xr = int64_t(t.b) * a.x_sb + int64_t(t.row0) * a.x_sh + t.col0;
+    const int xdt = TYPED ? a.x_dt : WM_DT_F32;
     RowPair A, B;
-    dj_load_pair(A, a.x, xr, a.x_sh, a.x_sc, t.active, a.x_dt);
+    dj_load_pair(A, a.x, xr, a.x_sh, a.x_sc, t.active, xdt);
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        dj_load_pair(B, a.x, xr + int64_t(4 * it + 2) * a.x_sh, a.x_sh, a.x_sc, t.active, a.x_dt);
+        dj_load_pair(B, a.x, xr + int64_t(4 * it + 2) * a.x_sh, a.x_sh, a.x_sc, t.active, xdt);
         dj_consume_pair<NT>(A, 2 * it, scr);
-        if (it == 0) dj_load_pair(A, a.x, xr + int64_t(4) * a.x_sh, a.x_sh, a.x_sc, t.active, a.x_dt);
+        if (it == 0) dj_load_pair(A, a.x, xr + int64_t(4) * a.x_sh, a.x_sh, a.x_sc, t.active, xdt);
         dj_consume_pair<NT>(B, 2 * it + 1, scr);
     }
 }
@@ -497,6 +500,15 @@ static inline int dj_launch(K kernel, const DJArgs& a, int threads, size_t smem,
 }
 
 }  // namespace wm
+
+#define DJ_DISPATCH_ROUND_T(KERNEL, TYPED, ...)                                               \
+    switch (rounding) {                                                                       \
+        case WM_ROUND_ONLY_AT_0: return dj_launch(KERNEL<WM_ROUND_ONLY_AT_0, TYPED>, __VA_ARGS__);   \
+        case WM_ROUND_CUBIC:     return dj_launch(KERNEL<WM_ROUND_CUBIC, TYPED>, __VA_ARGS__);       \
+        case WM_ROUND_HARD:      return dj_launch(KERNEL<WM_ROUND_HARD, TYPED>, __VA_ARGS__);        \
+        case WM_ROUND_FOURIER:   return dj_launch(KERNEL<WM_ROUND_FOURIER, TYPED>, __VA_ARGS__);     \
+        default: set_error("unknown rounding mode %d", rounding); return WM_E_ARG;            \
+    }
 
 #define DJ_DISPATCH_ROUND(KERNEL, ...)                                                        \
     switch (rounding) {                                                                       \

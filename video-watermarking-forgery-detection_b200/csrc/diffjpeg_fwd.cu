@@ -3,13 +3,13 @@
 
 namespace wm {
 
-template <int ROUND, bool EP = false>
+template <int ROUND, bool EP = false, bool TYPED = false>
 __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_kernel(const DJArgs a) {
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
     const float f = a.factor_ps ? __ldg(a.factor_ps + t.b) : a.factor;
-    dj_load_block<DJ_THREADS>(a, t, scr);
+    dj_load_block<DJ_THREADS, TYPED>(a, t, scr);
     dj_luma_columns<ROUND, false, false, DJ_THREADS>(scr, f);
     QuadCoef qx, qy;
     quad_coef_init(qx, t.bx);
@@ -20,13 +20,13 @@ __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_kernel(const DJArg
 
 // Forward that also saves what the backward needs (7 B/px: round'(q) of every coefficient and the
 // clamp codes), so that wm_diffjpeg_bwd_saved can skip the forward recomputation.
-template <int ROUND>
+template <int ROUND, bool TYPED = false>
 __global__ void __launch_bounds__(DJ_THREADS, 4) diffjpeg_fwd_save_kernel(const DJArgs a) {
     extern __shared__ float4 smem[];
     float4* scr = smem + threadIdx.x;
     const DJThread t = dj_locate(a);
     const float f = a.factor_ps ? __ldg(a.factor_ps + t.b) : a.factor;
-    dj_load_block<DJ_THREADS>(a, t, scr);
+    dj_load_block<DJ_THREADS, TYPED>(a, t, scr);
     dj_luma_columns_save<ROUND, DJ_THREADS>(scr, f, a.dY + (int64_t(t.b) * a.H + t.row0) * a.W + t.col0, a.W, t.active);
     QuadCoef qx, qy;
     quad_coef_init(qx, t.bx);
@@ -53,7 +53,8 @@ extern "C" int wm_diffjpeg_fwd_save(const void* x, int x_dtype, int64_t x_sb, in
     a.x = x; a.x_dt = x_dtype; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sh = x_sh; a.out = y;
     a.dY = dY; a.dC = dC; a.cm = reinterpret_cast<unsigned long long*>(clamp_codes);
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
-    DJ_DISPATCH_ROUND(diffjpeg_fwd_save_kernel, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd_save")
+    if (x_dtype != WM_DT_F32) { DJ_DISPATCH_ROUND_T(diffjpeg_fwd_save_kernel, true, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd_save") }
+    DJ_DISPATCH_ROUND_T(diffjpeg_fwd_save_kernel, false, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd_save")
 }
 
 
@@ -68,6 +69,16 @@ extern "C" int wm_diffjpeg_fwd(const void* x, int x_dtype, int64_t x_sb, int64_t
     const size_t smem = SC_FWD_CHUNKS * DJ_THREADS * sizeof(float4);
     WM_EP_CHECK(ep, "wm_diffjpeg_fwd");
     a.ep = make_store_ep(ep);
+    WM_REQUIRE(!a.ep.x || x_dtype == WM_DT_F32, WM_E_ARG, "wm_diffjpeg_fwd: the store epilogue needs a float32 image");
+    if (x_dtype != WM_DT_F32) {
+        switch (rounding) {
+            case WM_ROUND_ONLY_AT_0: return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_ONLY_AT_0, false, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_CUBIC:     return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_CUBIC, false, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_HARD:      return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_HARD, false, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            case WM_ROUND_FOURIER:   return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_FOURIER, false, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");
+            default: set_error("unknown rounding mode %d", rounding); return WM_E_ARG;
+        }
+    }
     if (a.ep.x) {
         switch (rounding) {
             case WM_ROUND_ONLY_AT_0: return dj_launch(diffjpeg_fwd_kernel<WM_ROUND_ONLY_AT_0, true>, a, DJ_THREADS, smem, (cudaStream_t)stream, "wm_diffjpeg_fwd");

@@ -29,6 +29,41 @@ __device__ __forceinline__ void st4(float* p, int64_t i, int64_t n, float4 v) {
     if (i + 2 < n) p[i + 2] = v.z;
 }
 
+// typed variants (float16 / bfloat16 boundary tensors): 4 elements = one 64-bit access; tails element by element
+__device__ __forceinline__ float half_bits_to_float(uint32_t h16, int dt) {
+    if (dt == WM_DT_BF16) return __uint_as_float(h16 << 16);
+    float f; asm("{\n .reg .b16 t;\n cvt.u16.u32 t, %1;\n cvt.f32.f16 %0, t;\n}" : "=f"(f) : "r"(h16)); return f;
+}
+__device__ __forceinline__ uint32_t float_to_half_bits(float v, int dt) {
+    uint32_t r;
+    if (dt == WM_DT_BF16) asm("{\n .reg .b16 t;\n cvt.rn.bf16.f32 t, %1;\n cvt.u32.u16 %0, t;\n}" : "=r"(r) : "f"(v));
+    else asm("{\n .reg .b16 t;\n cvt.rn.f16.f32 t, %1;\n cvt.u32.u16 %0, t;\n}" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float4 ld4t(const void* p, int64_t i, int64_t n, int dt) {
+    if (dt == WM_DT_F32) return ld4(reinterpret_cast<const float*>(p), i, n);
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    if (i + 3 < n) {
+        const uint2 w = *reinterpret_cast<const uint2*>(q + i);
+        return make_float4(half_bits_to_float(w.x & 0xffffu, dt), half_bits_to_float(w.x >> 16, dt),
+                           half_bits_to_float(w.y & 0xffffu, dt), half_bits_to_float(w.y >> 16, dt));
+    }
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) r.x = half_bits_to_float(q[i], dt);
+    if (i + 1 < n) r.y = half_bits_to_float(q[i + 1], dt);
+    if (i + 2 < n) r.z = half_bits_to_float(q[i + 2], dt);
+    return r;
+}
+__device__ __forceinline__ void st4t(void* p, int64_t i, int64_t n, float4 v, int dt) {
+    if (dt == WM_DT_F32) { st4(reinterpret_cast<float*>(p), i, n, v); return; }
+    uint16_t* q = reinterpret_cast<uint16_t*>(p);
+    const uint32_t a = float_to_half_bits(v.x, dt), b = float_to_half_bits(v.y, dt), c = float_to_half_bits(v.z, dt), d = float_to_half_bits(v.w, dt);
+    if (i + 3 < n) { *reinterpret_cast<uint2*>(q + i) = make_uint2(a | (b << 16), c | (d << 16)); return; }
+    if (i < n) q[i] = (uint16_t)a;
+    if (i + 1 < n) q[i + 1] = (uint16_t)b;
+    if (i + 2 < n) q[i + 2] = (uint16_t)c;
+}
+
 #define WM_EW_LOOP(i)                                                                         \
     for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;             \
          i += int64_t(gridDim.x) * blockDim.x * 4)
@@ -36,15 +71,16 @@ __device__ __forceinline__ void st4(float* p, int64_t i, int64_t n, float4 v) {
 // ---- Gaussian / GN ---------------------------------------------------------------------------
 // fwd: y = [clamp01](x + mean + std * N);  bwd: gx = gy * 1[0 <= x + noise <= 1] (torch.clamp is
 // inclusive) or gy when not clamped.
-template <bool BWD, bool EP>
-__global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+template <bool BWD, bool EP, bool TYPED = false>
+__global__ void __launch_bounds__(256) gaussnoise_kernel(const void* __restrict__ x, int x_dt_, const float* __restrict__ gy,
                                                          float* __restrict__ out, int64_t n, float mean, float std,
                                                          int clamp, uint64_t seed, uint64_t offset,
                                                          const float* __restrict__ inject, const StoreEp ep) {
     resolve_rng(seed, offset);
     const Philox ph(seed);
+    const int x_dt = TYPED ? x_dt_ : WM_DT_F32;     // float32 instantiation: the element-type switch folds away
     WM_EW_LOOP(i) {
-        const float4 xv = ld4(x, i, n);             // requested first: the latency hides under Philox + Box-Muller
+        const float4 xv = ld4t(x, i, n, x_dt);      // requested first: the latency hides under Philox + Box-Muller
         float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (BWD) gv = ld4(gy, i, n);
         float4 nz;
@@ -73,20 +109,22 @@ __global__ void __launch_bounds__(256) gaussnoise_kernel(const float* __restrict
 // regenerates the noise (12 + 0.4 B/px instead of 24 B/px read, no Philox / Box-Muller).
 // Layout: a warp handles 128 consecutive values per step; word 4*(i/128) + j holds, at bit l, the value
 // i + 4*l + j (one ballot per j).
-__global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+template <bool TYPED>
+__global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const void* __restrict__ x, int x_dt_, float* __restrict__ out,
                                                                   uint32_t* __restrict__ maskbits, int64_t n, float mean,
                                                                   float std, uint64_t seed, uint64_t offset,
                                                                   const float* __restrict__ inject) {
     resolve_rng(seed, offset);
     const Philox ph(seed);
     const int lane = threadIdx.x & 31;
+    const int x_dt = TYPED ? x_dt_ : WM_DT_F32;
     // a warp takes 256 consecutive values per step as two independent 128-value halves: the kernel is bound by
     // instruction issue (Philox + Box-Muller), and the second half shares the loop and index arithmetic of the first
     for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 8; base < n;
          base += int64_t(gridDim.x) * blockDim.x * 8) {               // warp-uniform trip count (ballots below)
         float4 xv[2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) xv[h] = ld4(x, base + 128 * h + 4 * lane, n);    // requested first: the latency hides under Philox
+        for (int h = 0; h < 2; ++h) xv[h] = ld4t(x, base + 128 * h + 4 * lane, n, x_dt);    // requested first: the latency hides under Philox
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t i = base + 128 * h + 4 * lane;
@@ -104,9 +142,11 @@ __global__ void __launch_bounds__(256) gaussnoise_mask_fwd_kernel(const float* _
         }
     }
 }
+template <bool TYPED>
 __global__ void __launch_bounds__(256) gaussnoise_mask_bwd_kernel(const float* __restrict__ gy, const uint32_t* __restrict__ maskbits,
-                                                                  float* __restrict__ gx, int64_t n) {
+                                                                  void* __restrict__ gx, int gx_dt_, int64_t n) {
     const int lane = threadIdx.x & 31;
+    const int gx_dt = TYPED ? gx_dt_ : WM_DT_F32;
     for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) * 4; base < n;
          base += int64_t(gridDim.x) * blockDim.x * 4) {
         const int64_t i = base + 4 * lane;
@@ -114,7 +154,7 @@ __global__ void __launch_bounds__(256) gaussnoise_mask_bwd_kernel(const float* _
         float4 g = ld4(gy, i, n);
         g.x = (m.x >> lane) & 1u ? g.x : 0.f; g.y = (m.y >> lane) & 1u ? g.y : 0.f;
         g.z = (m.z >> lane) & 1u ? g.z : 0.f; g.w = (m.w >> lane) & 1u ? g.w : 0.f;
-        st4(gx, i, n, g);
+        st4t(gx, i, n, g, gx_dt);
     }
 }
 
@@ -185,6 +225,18 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(const float* __restri
     }
 }
 
+// H*W not a multiple of 4: planes do not start on 16-byte boundaries, one element per thread
+template <bool BWD>
+__global__ void __launch_bounds__(256) dropout_mask_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                  const float* __restrict__ mask, float* __restrict__ o1,
+                                                                  float* __restrict__ o2, int64_t n, int64_t hw) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const float m = mask[i % hw];
+        if (!BWD) o1[i] = a[i] * m + b[i] * (1.f - m);           // same expression as the vector kernel
+        else { if (o1) o1[i] = a[i] * m; if (o2) o2[i] = a[i] * (1.f - m); }
+    }
+}
+
 __global__ void __launch_bounds__(256) bernoulli_kernel(float* __restrict__ mask, int64_t n, float keep,
                                                         uint64_t seed, uint64_t offset) {
     resolve_rng(seed, offset);
@@ -239,6 +291,22 @@ __global__ void __launch_bounds__(256) attack_epilogue_kernel(const float* __res
         st4(out, i, n, make_float4(q[0], q[1], q[2], q[3]));
     }
 }
+// slices of a K-way batch whose per-image element count is odd do not start on 16-byte boundaries: one element per thread
+__global__ void __launch_bounds__(256) attack_epilogue_scalar_kernel(const float* __restrict__ x, const float* __restrict__ sim,
+                                                                     float* __restrict__ out, int64_t n, int clamp01, int quant) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        float q[1] = {epilogue1(x[i], sim[i], clamp01, 0)};
+        if (quant) quant255_n<1>(q);
+        out[i] = q[0];
+    }
+}
+__global__ void __launch_bounds__(256) slice_sum_scalar_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n, int K) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        float acc = g[i];
+        for (int k = 1; k < K; ++k) acc += g[int64_t(k) * n + i];
+        out[i] = acc;
+    }
+}
 // out[i] = sum_k g[k * n + i]   (straight-through backward of the K-way bank: every slice passes gy to x)
 __global__ void __launch_bounds__(256) slice_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n, int K) {
     WM_EW_LOOP(i) {
@@ -277,6 +345,18 @@ __global__ void __launch_bounds__(256) splice_kernel(const float* __restrict__ a
             if (o1) *reinterpret_cast<float4*>(o1 + i) = make_float4(r1[0], r1[1], r1[2], r1[3]);
             if (o2) *reinterpret_cast<float4*>(o2 + i) = make_float4(r2[0], r2[1], r2[2], r2[3]);
         }
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) splice_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ m, float* __restrict__ o1, float* __restrict__ o2,
+                                                            int64_t n, int64_t hw, int C) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t plane = i / hw, bi = plane / C;
+        const float mv = m[bi * hw + (i - plane * hw)], av = a[i];
+        if (!BWD) o1[i] = __fadd_rn(__fmul_rn(av, __fsub_rn(1.f, mv)), __fmul_rn(b[i], mv));
+        else { if (o1) o1[i] = __fmul_rn(av, __fsub_rn(1.f, mv)); if (o2) o2[i] = __fmul_rn(av, mv); }
     }
 }
 
@@ -340,18 +420,21 @@ using namespace wm;
          for (const void* p__ : ps__) WM_REQUIRE(p__ == nullptr || aligned(p__, 16), WM_E_ALIGN, \
              "%s: pointers must be 16-byte aligned", who); } while (0)
 
-extern "C" int wm_gaussnoise_fwd(const float* x, float* y, int64_t n, float mean, float std, int clamp,
+extern "C" int wm_gaussnoise_fwd(const void* x, int x_dtype, float* y, int64_t n, float mean, float std, int clamp,
                                  uint64_t seed, uint64_t offset, const float* inject,
                                  const wm_store_epilogue* ep_in, void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y, WM_E_NULL, "wm_gaussnoise_fwd: null pointer");
+    WM_REQUIRE(dtype_ok(x_dtype), WM_E_ARG, "wm_gaussnoise_fwd: unknown element type %d", x_dtype);
     WM_EP_CHECK(ep_in, "wm_gaussnoise_fwd");
     EW_ALIGN_CHECK("wm_gaussnoise_fwd", x, y, inject);
     if (n <= 0) return WM_OK;
     StoreEp ep = make_store_ep(ep_in);
-    ep.from_input = ep.x == x;
-    if (ep.x) gaussnoise_kernel<false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
-    else gaussnoise_kernel<false, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
+    ep.from_input = ep.x == x && x_dtype == WM_DT_F32;
+    WM_REQUIRE(!ep.x || x_dtype == WM_DT_F32, WM_E_ARG, "wm_gaussnoise_fwd: the store epilogue needs a float32 image");
+    if (x_dtype != WM_DT_F32) gaussnoise_kernel<false, false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
+    else if (ep.x) gaussnoise_kernel<false, true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
+    else gaussnoise_kernel<false, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, nullptr, y, n, mean, std, clamp, seed, offset, inject, ep);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd");
     return WM_OK;
 }
@@ -365,25 +448,29 @@ extern "C" int wm_gaussnoise_bwd(const float* x, const float* gy, float* gx, int
         cudaError_t e = cudaMemcpyAsync(gx, gy, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
         return e == cudaSuccess ? WM_OK : cuda_fail(e, "wm_gaussnoise_bwd");
     }
-    gaussnoise_kernel<true, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, mean, std, clamp, seed, offset, inject,
+    gaussnoise_kernel<true, false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, WM_DT_F32, gy, gx, n, mean, std, clamp, seed, offset, inject,
                                                                                   StoreEp{nullptr, 0, 0});
     WM_LAUNCH_CHECK("wm_gaussnoise_bwd");
     return WM_OK;
 }
-extern "C" int wm_gaussnoise_fwd_mask(const float* x, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
+extern "C" int wm_gaussnoise_fwd_mask(const void* x, int x_dtype, float* y, uint32_t* maskbits, int64_t n, float mean, float std,
                                       uint64_t seed, uint64_t offset, const float* inject, void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && y && maskbits, WM_E_NULL, "wm_gaussnoise_fwd_mask: null pointer");
+    WM_REQUIRE(dtype_ok(x_dtype), WM_E_ARG, "wm_gaussnoise_fwd_mask: unknown element type %d", x_dtype);
     EW_ALIGN_CHECK("wm_gaussnoise_fwd_mask", x, y, inject, maskbits);
-    gaussnoise_mask_fwd_kernel<<<ew_grid((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, maskbits, n, mean, std, seed, offset, inject);
+    if (x_dtype != WM_DT_F32) gaussnoise_mask_fwd_kernel<true><<<ew_grid((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, maskbits, n, mean, std, seed, offset, inject);
+    else gaussnoise_mask_fwd_kernel<false><<<ew_grid((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, maskbits, n, mean, std, seed, offset, inject);
     WM_LAUNCH_CHECK("wm_gaussnoise_fwd_mask");
     return WM_OK;
 }
-extern "C" int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, float* gx, int64_t n, void* stream) {
+extern "C" int wm_gaussnoise_bwd_mask(const float* gy, const uint32_t* maskbits, void* gx, int gx_dtype, int64_t n, void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && gx && maskbits, WM_E_NULL, "wm_gaussnoise_bwd_mask: null pointer");
+    WM_REQUIRE(dtype_ok(gx_dtype), WM_E_ARG, "wm_gaussnoise_bwd_mask: unknown element type %d", gx_dtype);
     EW_ALIGN_CHECK("wm_gaussnoise_bwd_mask", gy, gx, maskbits);
-    gaussnoise_mask_bwd_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, maskbits, gx, n);
+    if (gx_dtype != WM_DT_F32) gaussnoise_mask_bwd_kernel<true><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, maskbits, gx, gx_dtype, n);
+    else gaussnoise_mask_bwd_kernel<false><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(gy, maskbits, gx, gx_dtype, n);
     WM_LAUNCH_CHECK("wm_gaussnoise_bwd_mask");
     return WM_OK;
 }
@@ -442,9 +529,13 @@ extern "C" int wm_dropout_mask_fwd(const float* noised, const float* cover, cons
                                    int64_t planes, int64_t hw, void* stream) {
     if (planes * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(noised && cover && mask_hw && y, WM_E_NULL, "wm_dropout_mask_fwd: null pointer");
-    WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_fwd: H*W must be a multiple of 4");
     EW_ALIGN_CHECK("wm_dropout_mask_fwd", noised, cover, mask_hw, y);
     if (planes <= 0 || hw <= 0) return WM_OK;
+    if (hw % 4 != 0 && planes != 1) {
+        dropout_mask_scalar_kernel<false><<<ew_grid(planes * hw), 256, 0, (cudaStream_t)stream>>>(noised, cover, mask_hw, y, nullptr, planes * hw, hw);
+        WM_LAUNCH_CHECK("wm_dropout_mask_fwd");
+        return WM_OK;
+    }
     dim3 grid(ew_grid((hw + 3) / 4), (unsigned)planes);
     dropout_mask_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(noised, cover, mask_hw, y, nullptr, hw);
     WM_LAUNCH_CHECK("wm_dropout_mask_fwd");
@@ -454,9 +545,13 @@ extern "C" int wm_dropout_mask_bwd(const float* gy, const float* mask_hw, float*
                                    int64_t planes, int64_t hw, void* stream) {
     if (planes * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && mask_hw && (g_noised || g_cover), WM_E_NULL, "wm_dropout_mask_bwd: null pointer");
-    WM_REQUIRE(hw % 4 == 0 || planes == 1, WM_E_ALIGN, "wm_dropout_mask_bwd: H*W must be a multiple of 4");
     EW_ALIGN_CHECK("wm_dropout_mask_bwd", gy, mask_hw, g_noised, g_cover);
     if (planes <= 0 || hw <= 0) return WM_OK;
+    if (hw % 4 != 0 && planes != 1) {
+        dropout_mask_scalar_kernel<true><<<ew_grid(planes * hw), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask_hw, g_noised, g_cover, planes * hw, hw);
+        WM_LAUNCH_CHECK("wm_dropout_mask_bwd");
+        return WM_OK;
+    }
     dim3 grid(ew_grid((hw + 3) / 4), (unsigned)planes);
     dropout_mask_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask_hw, g_noised, g_cover, hw);
     WM_LAUNCH_CHECK("wm_dropout_mask_bwd");
@@ -495,8 +590,13 @@ extern "C" int wm_attack_epilogue_fwd(const float* x, const float* sim, float* o
                                       void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(x && sim && out, WM_E_NULL, "wm_attack_epilogue_fwd: null pointer");
-    EW_ALIGN_CHECK("wm_attack_epilogue_fwd", x, sim, out);
     if (n <= 0) return WM_OK;
+    if (!(aligned(x, 16) && aligned(sim, 16) && aligned(out, 16))) {
+        WM_REQUIRE(aligned(x, 4) && aligned(sim, 4) && aligned(out, 4), WM_E_ALIGN, "wm_attack_epilogue_fwd: pointers must be 4-byte aligned");
+        attack_epilogue_scalar_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, sim, out, n, clamp01, quantize);
+        WM_LAUNCH_CHECK("wm_attack_epilogue_fwd");
+        return WM_OK;
+    }
     attack_epilogue_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, sim, out, n, clamp01, quantize);
     WM_LAUNCH_CHECK("wm_attack_epilogue_fwd");
     return WM_OK;
@@ -504,9 +604,13 @@ extern "C" int wm_attack_epilogue_fwd(const float* x, const float* sim, float* o
 extern "C" int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream) {
     if (n <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(g && out, WM_E_NULL, "wm_slice_sum: null pointer");
-    WM_REQUIRE(K >= 1 && n % 4 == 0, WM_E_ARG, "wm_slice_sum: K >= 1 and n %% 4 == 0 required (K=%d n=%lld)", K, (long long)n);
-    EW_ALIGN_CHECK("wm_slice_sum", g, out);
+    WM_REQUIRE(K >= 1, WM_E_ARG, "wm_slice_sum: K >= 1 required (K=%d)", K);
     if (n <= 0) return WM_OK;
+    if (n % 4 != 0 || !aligned(g, 16) || !aligned(out, 16)) {       // odd slices: not on 16-byte boundaries
+        slice_sum_scalar_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(g, out, n, K);
+        WM_LAUNCH_CHECK("wm_slice_sum");
+        return WM_OK;
+    }
     slice_sum_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(g, out, n, K);
     WM_LAUNCH_CHECK("wm_slice_sum");
     return WM_OK;
@@ -515,10 +619,15 @@ extern "C" int wm_splice_fwd(const float* a, const float* b, const float* mask, 
                              void* stream) {
     if (B * C * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(a && b && mask && out, WM_E_NULL, "wm_splice_fwd: null pointer");
-    WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_fwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
+    WM_REQUIRE(C >= 1, WM_E_SHAPE, "wm_splice_fwd: C must be >= 1");
     EW_ALIGN_CHECK("wm_splice_fwd", a, b, mask, out);
     const int64_t n = B * C * hw;
     if (n <= 0) return WM_OK;
+    if (hw % 4 != 0) {
+        splice_scalar_kernel<false><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(a, b, mask, out, nullptr, n, hw, C);
+        WM_LAUNCH_CHECK("wm_splice_fwd");
+        return WM_OK;
+    }
     splice_kernel<false><<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, mask, out, nullptr, n, hw, C);
     WM_LAUNCH_CHECK("wm_splice_fwd");
     return WM_OK;
@@ -527,10 +636,15 @@ extern "C" int wm_splice_bwd(const float* gy, const float* mask, float* ga, floa
                              void* stream) {
     if (B * C * hw <= 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(gy && mask && (ga || gb), WM_E_NULL, "wm_splice_bwd: null pointer");
-    WM_REQUIRE(C >= 1 && hw % 4 == 0, WM_E_SHAPE, "wm_splice_bwd: H*W must be a multiple of 4 (got %lld)", (long long)hw);
+    WM_REQUIRE(C >= 1, WM_E_SHAPE, "wm_splice_bwd: C must be >= 1");
     EW_ALIGN_CHECK("wm_splice_bwd", gy, mask, ga, gb);
     const int64_t n = B * C * hw;
     if (n <= 0) return WM_OK;
+    if (hw % 4 != 0) {
+        splice_scalar_kernel<true><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask, ga, gb, n, hw, C);
+        WM_LAUNCH_CHECK("wm_splice_bwd");
+        return WM_OK;
+    }
     splice_kernel<true><<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(gy, nullptr, mask, ga, gb, n, hw, C);
     WM_LAUNCH_CHECK("wm_splice_bwd");
     return WM_OK;

@@ -20,6 +20,7 @@ struct J8Args {
     const float* x; int64_t x_sb, x_sc, x_sh;
     const float* gy; int64_t g_sb, g_sc, g_sh;
     float* out;        // y / gx, dense [B,3,H,W]
+    int x_dt, out_dt;  // element types of x and out (WM_DT_*): the two-threads-per-block kernel reads / stores them directly
     float* coef;       // optional [B,3,Hp,Wp] quantised coefficient image
     int B, H, W, Hb, Wb; int64_t n_blk;
     float fwd[9], inv[9];
@@ -264,8 +265,10 @@ constexpr int J8P_THREADS = 128, J8P_BLOCKS = 64, J8P_CHUNKS = 48;
 // per-coefficient "mask" read from global memory (the quantisation steps cancel); no recompute.
 // VEC = false: rows that are not 32-byte aligned or a width that is not a multiple of 8 (scalar, predicated row
 // access; the missing columns / rows of the last blocks are the zero padding of noise_layers/jpeg.py:171-173).
-template <int VARIANT, int DMODE, bool VEC = true>
+// TYPED = false: float32 in and out, the element-type switches fold away (the kernel of the headline path).
+template <int VARIANT, int DMODE, bool VEC = true, bool TYPED = false>
 __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args a) {
+    const int xdt = TYPED ? a.x_dt : WM_DT_F32, odt = TYPED ? a.out_dt : WM_DT_F32;
     extern __shared__ float4 smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane >> 4, bic = warp * 16 + (lane & 15);          // half, block in CTA
@@ -276,7 +279,8 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
     const int per = a.Hb * a.Wb;
     const int b = int(m / per), rem = int(m - int64_t(b) * per), by = rem / a.Wb;
     const int row0 = by * 8, col0 = (rem - by * a.Wb) * 8;
-    const float* xr = a.x + int64_t(b) * a.x_sb + int64_t(row0 + 4 * h) * a.x_sh + col0;
+    const int64_t xo = int64_t(b) * a.x_sb + int64_t(row0 + 4 * h) * a.x_sh + col0;       // element offset (a.x_dt elements)
+    const float* xr = a.x + xo;
     const int ncol = min(8, a.W - col0);
 
     // ---- rows 4h .. 4h+3: colour transform + row DCT of the three channels -> scratch --------------
@@ -286,9 +290,17 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
         const bool ok = active && (row0 + r) < a.H;
         const float* p = xr + int64_t(i) * a.x_sh;
         float R[8], G[8], Bl[8];
-        j8_load_row<VEC>(p, ok, ncol, R);
-        j8_load_row<VEC>(p + a.x_sc, ok, ncol, G);
-        j8_load_row<VEC>(p + 2 * a.x_sc, ok, ncol, Bl);
+        if (VEC) {          // float32 / float16 / bfloat16 rows, 8 elements per load
+            const int64_t po = xo + int64_t(i) * a.x_sh;
+            f8 tr{}, tg{}, tb{};
+            if (ok) { tr = ld8_typed(a.x, po, xdt); tg = ld8_typed(a.x, po + a.x_sc, xdt); tb = ld8_typed(a.x, po + 2 * a.x_sc, xdt); }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { R[c] = tr.v[c]; G[c] = tg.v[c]; Bl[c] = tb.v[c]; }
+        } else {
+            j8_load_row<false>(p, ok, ncol, R);
+            j8_load_row<false>(p + a.x_sc, ok, ncol, G);
+            j8_load_row<false>(p + 2 * a.x_sc, ok, ncol, Bl);
+        }
         float y[8], u[8], v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -370,22 +382,37 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
             oB[c] = fmaf(a.inv[6], y[c], fmaf(a.inv[7], u[c], a.inv[8] * v[c]));
         }
         if (a.ep.x && ok) { ep_apply_n<8>(oR, xR.v, a.ep); ep_apply_n<8>(oG, xG.v, a.ep); ep_apply_n<8>(oB, xB.v, a.ep); }   // (dense, same layout as out)
-        j8_store_row<VEC>(p, ok, ncol, oR);
-        j8_store_row<VEC>(p + plane, ok, ncol, oG);
-        j8_store_row<VEC>(p + 2 * plane, ok, ncol, oB);
+        if (VEC) {
+            if (ok) {
+                const int64_t po = p - a.out;                    // element offset, a.out_dt elements
+                f8 tr, tg, tb;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { tr.v[c] = oR[c]; tg.v[c] = oG[c]; tb.v[c] = oB[c]; }
+                st8_typed(a.out, po, tr, odt); st8_typed(a.out, po + plane, tg, odt); st8_typed(a.out, po + 2 * plane, tb, odt);
+            }
+        } else {
+            j8_store_row<false>(p, ok, ncol, oR);
+            j8_store_row<false>(p + plane, ok, ncol, oG);
+            j8_store_row<false>(p + 2 * plane, ok, ncol, oB);
+        }
     }
 }
 
-template <int VARIANT, int DMODE = 0, bool VEC = true>
-static int j8_pair_launch(const J8Args& a, cudaStream_t st, const char* who) {
+template <int VARIANT, int DMODE, bool VEC, bool TYPED>
+static int j8_pair_launch_t(const J8Args& a, cudaStream_t st, const char* who) {
     if (a.n_blk == 0) return WM_OK;
     const size_t smem = size_t(J8P_CHUNKS) * J8P_BLOCKS * sizeof(float4);
-    cudaError_t e = cudaFuncSetAttribute(jpeg8_pair_kernel<VARIANT, DMODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(jpeg8_pair_kernel<VARIANT, DMODE, VEC, TYPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
     const int64_t blocks = (a.n_blk + J8P_BLOCKS - 1) / J8P_BLOCKS;
-    jpeg8_pair_kernel<VARIANT, DMODE, VEC><<<(unsigned)blocks, J8P_THREADS, smem, st>>>(a);
+    jpeg8_pair_kernel<VARIANT, DMODE, VEC, TYPED><<<(unsigned)blocks, J8P_THREADS, smem, st>>>(a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
+}
+template <int VARIANT, int DMODE = 0, bool VEC = true>
+static int j8_pair_launch(const J8Args& a, cudaStream_t st, const char* who) {
+    if (VEC && (a.x_dt != WM_DT_F32 || a.out_dt != WM_DT_F32)) return j8_pair_launch_t<VARIANT, DMODE, VEC, VEC>(a, st, who);
+    return j8_pair_launch_t<VARIANT, DMODE, VEC, false>(a, st, who);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -535,8 +562,8 @@ static int j8_fill(J8Args& a, const float* x, int64_t sb, int64_t sc, int64_t sh
     return WM_OK;
 }
 
-static bool j8_vec_ok(const float* p, int64_t sb, int64_t sc, int64_t sh, int W) {
-    return aligned(p, 32) && W % 8 == 0 && sb % 8 == 0 && sc % 8 == 0 && sh % 8 == 0;
+static bool j8_vec_ok(const void* p, int64_t sb, int64_t sc, int64_t sh, int W, int dt = WM_DT_F32) {
+    return aligned(p, 8 * dtype_size(dt)) && W % 8 == 0 && sb % 8 == 0 && sc % 8 == 0 && sh % 8 == 0;
 }
 
 template <typename K>
@@ -578,15 +605,23 @@ static int j8_fwd_any(const J8Args& a, int variant, int submode, bool vec, bool 
 
 using namespace wm;
 
-extern "C" int wm_jpeg8_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
+// typed x / gx (WM_DT_F16 / WM_DT_BF16) exist on the vector path of the two-threads-per-block kernel only
+#define J8_TYPED_CHECK(dt, ok, who)                                                                                    \
+    WM_REQUIRE(dtype_ok(dt), WM_E_ARG, "%s: unknown element type %d", who, dt);                                         \
+    WM_REQUIRE((dt) == WM_DT_F32 || (ok), WM_E_ARG,                                                                     \
+               "%s: float16 / bfloat16 tensors need the vector path (W %% 8 == 0, no subsampling, pointers aligned to 8 elements)", who)
+
+extern "C" int wm_jpeg8_fwd(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y,
                             int B, int H, int W, const wm_jpeg8_params* p, const wm_store_epilogue* ep, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
-    if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd")) return rc;
+    if (int rc = j8_fill(a, reinterpret_cast<const float*>(x), x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd")) return rc;
     WM_EP_CHECK(ep, "wm_jpeg8_fwd");
     WM_REQUIRE(y != nullptr, WM_E_NULL, "wm_jpeg8_fwd: null output");
     a.out = y;
-    const bool vec = j8_vec_ok(x, x_sb, x_sc, x_sh, W) && aligned(y, 32);
+    const bool vec = dtype_ok(x_dtype) && j8_vec_ok(x, x_sb, x_sc, x_sh, W, x_dtype) && aligned(y, 32);
+    J8_TYPED_CHECK(x_dtype, vec && p->subsample == 0, "wm_jpeg8_fwd");
+    a.x_dt = x_dtype;
     if (vec && p->subsample == 0) a.ep = make_store_ep(ep);           // the two-threads-per-block kernel applies it
     else WM_EP_REJECT(ep, "wm_jpeg8_fwd (ragged / subsampled path)");
     return j8_fwd_any(a, p->variant, p->subsample, vec, false, (cudaStream_t)stream, "wm_jpeg8_fwd");
@@ -604,14 +639,15 @@ extern "C" int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, in
 }
 
 extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
-                            const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, float* gx,
+                            const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, void* gx, int gx_dtype,
                             int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(p != nullptr && gx != nullptr && gy != nullptr, WM_E_NULL, "wm_jpeg8_bwd: null pointer");
+    WM_REQUIRE(dtype_ok(gx_dtype), WM_E_ARG, "wm_jpeg8_bwd: unknown gx element type %d", gx_dtype);
     cudaStream_t st = (cudaStream_t)stream;
     if (p->variant == WM_JPEG8_HARD) {
         // torch.round has zero gradient everywhere (noise_layers/jpeg.py:233 with round_func=torch.round)
-        cudaError_t e = cudaMemsetAsync(gx, 0, sizeof(float) * 3 * size_t(B) * H * W, st);
+        cudaError_t e = cudaMemsetAsync(gx, 0, dtype_size(gx_dtype) * 3 * size_t(B) * H * W, st);
         return e == cudaSuccess ? WM_OK : cuda_fail(e, "wm_jpeg8_bwd(memset)");
     }
     if (p->variant == WM_JPEG8_MASK) {
@@ -626,13 +662,15 @@ extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
         q.subsample = 0;
         J8Args a{};
         if (int rc = j8_fill(a, gy, g_sb, g_sc, g_sh, B, H, W, &q, "wm_jpeg8_bwd")) return rc;
-        a.out = gx;
-        const bool vec = j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 32);
+        a.out = reinterpret_cast<float*>(gx); a.out_dt = gx_dtype;
+        const bool vec = j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 8 * dtype_size(gx_dtype));
+        J8_TYPED_CHECK(gx_dtype, vec && p->subsample == 0, "wm_jpeg8_bwd");
         return j8_fwd_any(a, WM_JPEG8_MASK, p->subsample == 2 ? 3 : 0, vec, false, st, "wm_jpeg8_bwd");
     }
+    J8_TYPED_CHECK(gx_dtype, false, "wm_jpeg8_bwd (JpegSS recompute path: use the saved-state pair)");
     J8Args a{};
     if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_bwd")) return rc;
-    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = gx;
+    a.gy = gy; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sh = g_sh; a.out = reinterpret_cast<float*>(gx);
     const bool vec = j8_vec_ok(x, x_sb, x_sc, x_sh, W) && j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 32);
     const size_t smem = 80 * J8B_THREADS * sizeof(float4);
     if (p->subsample == 2)
@@ -645,22 +683,24 @@ extern "C" int wm_jpeg8_bwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t 
 // JpegSS training pair (see jpeg8_pair_kernel, DMODE 1 / 2).  Needs the fast-path geometry:
 // W % 8 == 0, 32-byte aligned base pointers, strides multiples of 8, subsample == 0.
 // d: [B, 3, ceil8(H), W] floats.
-extern "C" int wm_jpeg8_fwd_save(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
+extern "C" int wm_jpeg8_fwd_save(const void* x, int x_dtype, int64_t x_sb, int64_t x_sc, int64_t x_sh, float* y, float* d,
                                  int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     J8Args a{};
-    if (int rc = j8_fill(a, x, x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd_save")) return rc;
+    if (int rc = j8_fill(a, reinterpret_cast<const float*>(x), x_sb, x_sc, x_sh, B, H, W, p, "wm_jpeg8_fwd_save")) return rc;
     WM_REQUIRE(y && d, WM_E_NULL, "wm_jpeg8_fwd_save: null output");
+    WM_REQUIRE(dtype_ok(x_dtype), WM_E_ARG, "wm_jpeg8_fwd_save: unknown element type %d", x_dtype);
     WM_REQUIRE(p->variant == WM_JPEG8_SS && p->subsample == 0, WM_E_ARG, "wm_jpeg8_fwd_save: JpegSS without subsampling only");
-    WM_REQUIRE(j8_vec_ok(x, x_sb, x_sc, x_sh, W) && aligned(y, 32) && aligned(d, 16), WM_E_ALIGN,
-               "wm_jpeg8_fwd_save: needs W %% 8 == 0, 32-byte aligned x / y and strides multiples of 8");
-    a.out = y; a.coef = d;
+    WM_REQUIRE(j8_vec_ok(x, x_sb, x_sc, x_sh, W, x_dtype) && aligned(y, 32) && aligned(d, 16), WM_E_ALIGN,
+               "wm_jpeg8_fwd_save: needs W %% 8 == 0, x aligned to 8 elements, 32-byte aligned y and strides multiples of 8");
+    a.out = y; a.coef = d; a.x_dt = x_dtype;
     return j8_pair_launch<WM_JPEG8_SS, 1>(a, (cudaStream_t)stream, "wm_jpeg8_fwd_save");
 }
-extern "C" int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, float* gx,
+extern "C" int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, int64_t g_sh, const float* d, void* gx, int gx_dtype,
                                   int B, int H, int W, const wm_jpeg8_params* p, void* stream) {
     if (B == 0) return WM_OK;      // empty work: nothing to validate or launch
     WM_REQUIRE(p && gy && d && gx, WM_E_NULL, "wm_jpeg8_bwd_saved: null pointer");
+    WM_REQUIRE(dtype_ok(gx_dtype), WM_E_ARG, "wm_jpeg8_bwd_saved: unknown gx element type %d", gx_dtype);
     wm_jpeg8_params q = *p;              // adjoint colour matrices, as for the linear variants
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
@@ -670,8 +710,8 @@ extern "C" int wm_jpeg8_bwd_saved(const float* gy, int64_t g_sb, int64_t g_sc, i
     q.variant = WM_JPEG8_MASK; q.subsample = 0;
     J8Args a{};
     if (int rc = j8_fill(a, gy, g_sb, g_sc, g_sh, B, H, W, &q, "wm_jpeg8_bwd_saved")) return rc;
-    WM_REQUIRE(j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 32) && aligned(d, 16), WM_E_ALIGN,
-               "wm_jpeg8_bwd_saved: needs W %% 8 == 0, 32-byte aligned gy / gx and strides multiples of 8");
-    a.out = gx; a.coef = const_cast<float*>(d);
+    WM_REQUIRE(j8_vec_ok(gy, g_sb, g_sc, g_sh, W) && aligned(gx, 8 * dtype_size(gx_dtype)) && aligned(d, 16), WM_E_ALIGN,
+               "wm_jpeg8_bwd_saved: needs W %% 8 == 0, 32-byte aligned gy, gx aligned to 8 elements and strides multiples of 8");
+    a.out = reinterpret_cast<float*>(gx); a.out_dt = gx_dtype; a.coef = const_cast<float*>(d);
     return j8_pair_launch<WM_JPEG8_MASK, 2>(a, (cudaStream_t)stream, "wm_jpeg8_bwd_saved");
 }

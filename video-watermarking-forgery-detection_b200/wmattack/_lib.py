@@ -49,18 +49,18 @@ SIGNATURES = {
     "wm_diffjpeg_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, vp, vp, i32, i32, i32, i32, vp],
     "wm_diffjpeg_compress": [c_f32p, i64, i64, i64, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, i32, vp],
     "wm_diffjpeg_decompress": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, f32, c_f32p, vp],
-    "wm_jpeg8_fwd": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), epp, vp],
-    "wm_jpeg8_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
-    "wm_jpeg8_fwd_save": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
-    "wm_jpeg8_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_fwd": [vp, i32, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), epp, vp],
+    "wm_jpeg8_bwd": [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, vp, i32, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_fwd_save": [vp, i32, i64, i64, i64, c_f32p, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
+    "wm_jpeg8_bwd_saved": [c_f32p, i64, i64, i64, c_f32p, vp, i32, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_jpeg8_quantised": [c_f32p, i64, i64, i64, c_f32p, i32, i32, i32, C.POINTER(Jpeg8Params), vp],
     "wm_gaussblur": [c_f32p, i64, i64, c_f32p, i32, i32, i32, C.POINTER(f32), i32, i32, i32, epp, vp],
     "wm_median_fwd": [c_f32p, i64, i64, c_f32p, c_u8p, i64, i32, i32, i32, i32, epp, vp],
     "wm_median_bwd": [c_f32p, c_u8p, i64, c_f32p, i32, i32, i32, i32, vp],
-    "wm_gaussnoise_fwd": [c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, epp, vp],
+    "wm_gaussnoise_fwd": [vp, i32, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, epp, vp],
     "wm_gaussnoise_bwd": [c_f32p, c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
-    "wm_gaussnoise_fwd_mask": [c_f32p, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
-    "wm_gaussnoise_bwd_mask": [c_f32p, vp, c_f32p, i64, vp],
+    "wm_gaussnoise_fwd_mask": [vp, i32, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
+    "wm_gaussnoise_bwd_mask": [c_f32p, vp, vp, i32, i64, vp],
     "wm_rng_reserve": [vp, vp, u64, vp],
     "wm_saltpepper_fwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],
     "wm_saltpepper_bwd": [c_f32p, c_f32p, i64, f32, u64, u64, c_f32p, vp],

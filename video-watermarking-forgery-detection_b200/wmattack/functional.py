@@ -303,9 +303,15 @@ def make_jpeg8_params(fwd_color: Sequence[float], inv_color: Sequence[float], ta
 
 
 class _Jpeg8Fn(torch.autograd.Function):
+    """float16 / bfloat16 images are read as they are, and the gradient is stored in that type, whenever the call takes
+    the vector path of the two-threads-per-block kernel (W % 8 == 0, no in-block subsampling; JpegSS needs its
+    saved-state pair for a typed gradient); any other geometry converts to float32 first."""
+
     @staticmethod
     def forward(ctx, x, params):
-        x, sb, sc, sh = _image(x, "jpeg8")
+        typed = x.dtype in (torch.float16, torch.bfloat16) and x.shape[-1] % 8 == 0 and params.subsample == 0
+        x, sb, sc, sh = _image(x, "jpeg8", typed=typed)
+        xdt = _DT_CODE[x.dtype]
         b, c, h, w = x.shape
         if c != 3:
             raise ValueError(f"JPEG layers expect 3 channels, got {c}")
@@ -313,28 +319,30 @@ class _Jpeg8Fn(torch.autograd.Function):
         ctx.params = params
         ctx.shape = (b, h, w)
         ctx.saved_d = False
+        ctx.xdtype = x.dtype
         if params.variant == JPEG8_SS and ctx.needs_input_grad[0] and w % 8 == 0 and params.subsample == 0:
             # training pair: save ss'(q) (12 B/px); the backward then needs neither x nor a recompute
             d = torch.empty((b, 3, (h + 7) // 8 * 8, w), device=x.device, dtype=torch.float32)
-            _lib.call("wm_jpeg8_fwd_save", x.data_ptr(), sb, sc, sh, y.data_ptr(), d.data_ptr(), b, h, w,
+            _lib.call("wm_jpeg8_fwd_save", x.data_ptr(), xdt, sb, sc, sh, y.data_ptr(), d.data_ptr(), b, h, w,
                       C.byref(params), _stream())
             ctx.save_for_backward(d)
             ctx.saved_d = True
             return y
-        _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), None, _stream())
+        _lib.call("wm_jpeg8_fwd", x.data_ptr(), xdt, sb, sc, sh, y.data_ptr(), b, h, w, C.byref(params), None, _stream())
         if params.variant == JPEG8_SS:
-            ctx.save_for_backward(x)
+            ctx.save_for_backward(x)                 # ragged / subsampled JpegSS: float32 here (typed is False)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         p = ctx.params
+        gdt = _DT_CODE[ctx.xdtype]
         if ctx.saved_d:
             (d,) = ctx.saved_tensors
             b, h, w = ctx.shape
             gy, gsb, gsc, gsh = _image(gy, "jpeg8.backward")
-            gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
-            _lib.call("wm_jpeg8_bwd_saved", gy.data_ptr(), gsb, gsc, gsh, d.data_ptr(), gx.data_ptr(), b, h, w,
+            gx = torch.empty((b, 3, h, w), device=gy.device, dtype=ctx.xdtype)
+            _lib.call("wm_jpeg8_bwd_saved", gy.data_ptr(), gsb, gsc, gsh, d.data_ptr(), gx.data_ptr(), gdt, b, h, w,
                       C.byref(p), _stream())
             return gx, None
         if p.variant == JPEG8_SS:
@@ -347,8 +355,8 @@ class _Jpeg8Fn(torch.autograd.Function):
             sb = sc = sh = 0
             xp = None
         gy, gsb, gsc, gsh = _image(gy, "jpeg8.backward")
-        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=torch.float32)
-        _lib.call("wm_jpeg8_bwd", xp, sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(), b, h, w,
+        gx = torch.empty((b, 3, h, w), device=gy.device, dtype=ctx.xdtype)
+        _lib.call("wm_jpeg8_bwd", xp, sb, sc, sh, gy.data_ptr(), gsb, gsc, gsh, gx.data_ptr(), gdt, b, h, w,
                   C.byref(p), _stream())
         return gx, None
 
@@ -468,25 +476,30 @@ def median_blur_with_index(x: torch.Tensor, k: int):
 
 class _GaussNoiseFn(torch.autograd.Function):
     """Clamped layer with grad: the forward saves the clamp's 1-bit pass mask (0.4 B/px) and the backward is
-    a masked copy of gy.  regen=True keeps the save-x pair whose backward regenerates the noise by Philox."""
+    a masked copy of gy.  regen=True keeps the save-x pair whose backward regenerates the noise by Philox.
+    float16 / bfloat16 images are read as they are; the mask pair stores the gradient in that type."""
 
     @staticmethod
     def forward(ctx, x, mean, std, clamp, noise, seed, offset, regen):
-        x = _flat(x, "gaussian noise")
+        _check_cuda(x, "gaussian noise")
+        typed = x.dtype in (torch.float16, torch.bfloat16) and not (clamp and regen)
+        x = x.contiguous() if typed else _flat(x, "gaussian noise")
+        xdt = _DT_CODE[x.dtype]
         inj = _flat(noise, "gaussian noise (injected)") if noise is not None else None
         if inj is not None and inj.shape != x.shape:
             raise ValueError("injected noise must have the input's shape")
-        y = torch.empty_like(x)
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
         ctx.mode = "identity"
+        ctx.xdtype = x.dtype
         if clamp and ctx.needs_input_grad[0] and not regen:
             n = x.numel()
             mask = torch.empty(4 * ((n + 127) // 128), device=x.device, dtype=torch.int32)
-            _lib.call("wm_gaussnoise_fwd_mask", x.data_ptr(), y.data_ptr(), mask.data_ptr(), n, mean, std, seed, _off(offset),
+            _lib.call("wm_gaussnoise_fwd_mask", x.data_ptr(), xdt, y.data_ptr(), mask.data_ptr(), n, mean, std, seed, _off(offset),
                       _ptr(inj), _stream())
             ctx.save_for_backward(mask)
             ctx.mode = "mask"
             return y
-        _lib.call("wm_gaussnoise_fwd", x.data_ptr(), y.data_ptr(), x.numel(), mean, std, int(clamp), seed, _off(offset),
+        _lib.call("wm_gaussnoise_fwd", x.data_ptr(), xdt, y.data_ptr(), x.numel(), mean, std, int(clamp), seed, _off(offset),
                   _ptr(inj), None, _stream())
         ctx.meta = (mean, std, int(clamp), seed, offset)
         if clamp:
@@ -500,11 +513,12 @@ class _GaussNoiseFn(torch.autograd.Function):
         gy = _flat(gy, "gaussian noise backward")
         if ctx.mode == "identity":
             return gy, None, None, None, None, None, None, None
-        gx = torch.empty_like(gy)
         if ctx.mode == "mask":
             (mask,) = ctx.saved_tensors
-            _lib.call("wm_gaussnoise_bwd_mask", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), gy.numel(), _stream())
+            gx = torch.empty(gy.shape, device=gy.device, dtype=ctx.xdtype)
+            _lib.call("wm_gaussnoise_bwd_mask", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), _DT_CODE[ctx.xdtype], gy.numel(), _stream())
             return gx, None, None, None, None, None, None, None
+        gx = torch.empty_like(gy)
         mean, std, clamp, seed, offset = ctx.meta
         x, inj = ctx.saved_tensors
         _lib.call("wm_gaussnoise_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), gy.numel(), mean, std, clamp,
@@ -1045,7 +1059,7 @@ def jpeg8_into(x, params, out, ep=None) -> bool:
     b, c, h, w = x.shape
     if c != 3 or w % 8 or params.subsample != 0 or not _out_ok(out, x.shape):
         return False
-    _lib.call("wm_jpeg8_fwd", x.data_ptr(), sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _ep_arg(ep), _stream())
+    _lib.call("wm_jpeg8_fwd", x.data_ptr(), DT_F32, sb, sc, sh, out.data_ptr(), b, h, w, C.byref(params), _ep_arg(ep), _stream())
     return True
 
 
@@ -1072,7 +1086,7 @@ def gaussian_noise_into(x, mean, std, clamp, out, ep=None) -> bool:
     if not _out_ok(out, x.shape):
         return False
     seed, offset = next_philox_stream(x.numel(), x.device)
-    _lib.call("wm_gaussnoise_fwd", x.data_ptr(), out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
+    _lib.call("wm_gaussnoise_fwd", x.data_ptr(), DT_F32, out.data_ptr(), x.numel(), float(mean), float(std), int(clamp),
               seed, _off(offset), None, _ep_arg(ep), _stream())
     return True
 
