@@ -525,6 +525,12 @@ def test_median_backward(k):
     y, gxq = fwd_bwd(wmattack.MiddleBlur(k), xq, g)
     _, idxq = O.median_blur(xq, k, return_index=True)
     assert torch.equal(gxq, O.median_blur_backward(g, idxq, k))
+    # W % 4 == 0 but W % 16 != 0: TMA-fed rings, the arg-median plane's rows are padded to 16 bytes
+    for shape, seed in (((1, 3, 50, 132), 12), ((2, 1, 9, 20), 13)):
+        xs, gs = torch.round(rnd(shape, seed) * 11) / 11, rnd(shape, seed + 50)
+        y, gxs = fwd_bwd(wmattack.MiddleBlur(k), xs, gs)
+        yo, idxs = O.median_blur(xs, k, return_index=True)
+        assert torch.equal(y, yo) and torch.equal(gxs, O.median_blur_backward(gs, idxs, k))
 
 
 # =============================================================================== elementwise
