@@ -1686,3 +1686,15 @@ def test_fused_resize_band_proof_covers_every_ratio_the_layer_can_draw():
         yt.backward(g.to(DEV))
         assert md(y, yt) <= 1e-5, r
         _assert_resize_grad(xx.grad, xt.grad, x, r, "bicubic", 2e-5, f"r={r}")
+
+
+def test_random_shape_sweep_against_the_oracle():
+    """tools/fuzz_shapes.py: 40 random [B,3,H,W] shapes (ragged widths, 1-pixel planes, odd plane counts, strided views)
+    through blur, both medians, the 8x8 JPEG layers and the fused Resize, forward and gradient, against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_shapes.py"), "40", "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
