@@ -84,6 +84,7 @@ class Step(nn.Module):
         self.attacks = build_attacks(attack, dev)          # plain list: attack layers hold no parameters
         self.splice = wmattack.Splice()
         self.quant = wmattack.Quantization()
+        self.mix = wmattack.AttackMix() if attack == "ours" else None      # the reference arm keeps the trainer's torch ops
         self.is_invertible = nets == "reference"
         self.attack_ms = None
 
@@ -99,14 +100,17 @@ class Step(nn.Module):
         tampered = self.splice(marked, previous, mask)                       # :348  forward*(1-mask) + previous*mask
         # hybrid attack (:357-370): softmax-weighted mix of the five attacked versions, per frame
         alpha = torch.softmax(torch.randn(frames.shape[0], 5, device=frames.device), dim=1)
-        attacked = None
-        for k, layer in enumerate(self.attacks):
-            y = layer(tampered)
-            y = y[0] if isinstance(y, tuple) else y
-            term = alpha[:, k].view(-1, 1, 1, 1) * y
-            attacked = term if attacked is None else attacked + term
-        attacked = attacked + (torch.clamp(attacked, 0, 1) - attacked).detach()   # :373
-        attacked = self.quant(attacked)                                           # :374
+        if self.mix is not None:             # our arm: mix + clamp_with_grad (:373) + Quantization (:374) in one pass
+            attacked = self.mix([layer(tampered) for layer in self.attacks], alpha)
+        else:
+            attacked = None
+            for k, layer in enumerate(self.attacks):
+                y = layer(tampered)
+                y = y[0] if isinstance(y, tuple) else y
+                term = alpha[:, k].view(-1, 1, 1, 1) * y
+                attacked = term if attacked is None else attacked + term
+            attacked = attacked + (torch.clamp(attacked, 0, 1) - attacked).detach()   # :373
+            attacked = self.quant(attacked)                                           # :374
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = self.localiser(attacked)
         bce = nn.functional.binary_cross_entropy_with_logits

@@ -319,6 +319,20 @@ int wm_bank3_fwd(const float* x, int64_t x_sp, int64_t x_sh, int N, int H, int W
                  const wm_bank3_desc* desc_host, void* stream);
 int wm_attack_epilogue_fwd(const float* x, const float* sim, float* out, int64_t n, int clamp01, int quantize,
                            void* stream);
+/* Hybrid attack (models/IRNcrop_model.py:357-373, the softmax mix as intended): the convex mix of K attacked versions of a
+ * batch, followed by the trainer's clamp_with_grad and Quantization, in one pass:
+ *     mixed = sum_k alpha[b, k] * t[k];   out = Quantization( mixed + (clamp(mixed, 0, 1) - mixed).detach() )
+ * t[k]: K dense [B, chw] tensors (device pointers in the HOST struct), alpha: device [B, K]; products are added left to
+ * right in fp32 (bit-identical to the torch expression).  wm_mix_bwd writes g[k] = alpha[b, k] * gy into t[k] (a NULL
+ * member is skipped); clamp_with_grad and Quantization are straight-through. */
+#define WM_MIX_MAX 8
+typedef struct wm_mix_desc {
+    float* t[WM_MIX_MAX];
+    int K;
+    int clamp01, quantize;
+} wm_mix_desc;
+int wm_mix_fwd(const wm_mix_desc* desc_host, const float* alpha, float* out, int64_t B, int64_t chw, void* stream);
+int wm_mix_bwd(const float* gy, const float* alpha, const wm_mix_desc* grads_host, int64_t B, int64_t chw, void* stream);
 int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* stream);
 int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out, int64_t B, int C, int64_t hw,
                   void* stream);

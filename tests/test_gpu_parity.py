@@ -1031,6 +1031,35 @@ def test_attack_epilogue_bank_and_splice_match_the_trainer_arithmetic():
     assert md(xa.grad, go.sum(0, keepdim=True)) <= 1e-6
 
 
+def test_attack_mix_matches_the_trainer_arithmetic():
+    """Hybrid attack of models/IRNcrop_model.py:357-373 (as intended): softmax-weighted mix of the attacked versions,
+    clamp_with_grad, Quantization — bit-identical values to the torch expression, gradients alpha_k * gy."""
+    for shape, seed in (((3, 3, 16, 24), 71), ((2, 3, 7, 9), 72)):          # the second: odd element count (scalar path)
+        ys = [(rnd(shape, seed + k) * 1.4 - 0.2) for k in range(5)]
+        alpha = torch.softmax(torch.randn(shape[0], 5, generator=torch.Generator().manual_seed(seed)), dim=1)
+        g = rnd(shape, seed + 9)
+        yd = [y.to(DEV).requires_grad_(k != 2) for k, y in enumerate(ys)]    # one member needs no gradient
+        out = wmattack.AttackMix()(yd, alpha.to(DEV))
+        out.backward(g.to(DEV))
+        yc = [y.clone().requires_grad_(True) for y in ys]
+        mixed = None
+        for k in range(5):
+            term = alpha[:, k].view(-1, 1, 1, 1) * yc[k]
+            mixed = term if mixed is None else mixed + term
+        mixed = mixed + (torch.clamp(mixed, 0, 1) - mixed).detach()
+        ref = (mixed * 255.).round() / 255.
+        assert torch.equal(out.detach().cpu(), ref.detach())
+        for k in range(5):
+            want = alpha[:, k].view(-1, 1, 1, 1) * g
+            if k == 2:
+                assert yd[k].grad is None
+            else:
+                assert torch.equal(yd[k].grad.cpu(), want)
+    # default weights: drawn like the trainer (softmax of randn), convex
+    out = wmattack.AttackMix(clamp=False, quantize=False)([torch.ones(2, 3, 4, 4, device=DEV)] * 3)
+    assert md(out, torch.ones(2, 3, 4, 4)) <= 1e-6
+
+
 @pytest.mark.parametrize("mode", (0, 1, 3))
 def test_diffjpeg_saved_state_and_recompute_backward_agree(mode):
     """Two backward implementations of the same chain: from 7 B/px of state saved by the forward

@@ -319,6 +319,60 @@ __global__ void __launch_bounds__(256) slice_sum_kernel(const float* __restrict_
     }
 }
 
+// ---- hybrid attack: convex mix of K attacked versions (models/IRNcrop_model.py:357-373, as intended) ------------
+//   mixed = sum_k alpha[b, k] * y_k;  out = Quantization( mixed + (clamp(mixed, 0, 1) - mixed).detach() )
+// = K multiplies + K - 1 adds + the clamp_with_grad / Quantization passes of the trainer (~430 B/px at K = 5); here the
+// K tensors are read once and one is written (12 K + 12 B/px).  Same fp32 operation order (products added left to
+// right, no FMA contraction): bit-identical.  Backward: g_k = alpha[b, k] * gy (clamp_with_grad and Quantization are
+// straight-through).
+struct MixArgs { const float* y[WM_MIX_MAX]; float* g[WM_MIX_MAX]; const float* alpha; int K, clamp01, quant; int64_t chw, n; };
+
+__device__ __forceinline__ float mix_finish(float v, int clamp01) {
+    return clamp01 ? __fadd_rn(v, __fsub_rn(clamp01_nan(v), v)) : v;
+}
+template <bool VEC>
+__global__ void __launch_bounds__(256) mix_fwd_kernel(const MixArgs a, float* __restrict__ out) {
+    constexpr int E = VEC ? 4 : 1;
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * E; i < a.n; i += int64_t(gridDim.x) * blockDim.x * E) {
+        const int64_t b = i / a.chw;
+        float acc[E];
+#pragma unroll
+        for (int k = 0; k < WM_MIX_MAX; ++k) {
+            if (k < a.K) {
+                const float w = __ldg(a.alpha + b * a.K + k);
+                float v[E];
+                if (VEC) { const float4 t = *reinterpret_cast<const float4*>(a.y[k] + i); v[0] = t.x; v[1 % E] = t.y; v[2 % E] = t.z; v[3 % E] = t.w; }
+                else v[0] = a.y[k][i];
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = k == 0 ? __fmul_rn(w, v[e]) : __fadd_rn(acc[e], __fmul_rn(w, v[e]));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = mix_finish(acc[e], a.clamp01);
+        if (a.quant) quant255_n<E>(acc);
+        if (VEC) *reinterpret_cast<float4*>(out + i) = make_float4(acc[0], acc[1 % E], acc[2 % E], acc[3 % E]);
+        else out[i] = acc[0];
+    }
+}
+template <bool VEC>
+__global__ void __launch_bounds__(256) mix_bwd_kernel(const MixArgs a, const float* __restrict__ gy) {
+    constexpr int E = VEC ? 4 : 1;
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * E; i < a.n; i += int64_t(gridDim.x) * blockDim.x * E) {
+        const int64_t b = i / a.chw;
+        float g[E];
+        if (VEC) { const float4 t = *reinterpret_cast<const float4*>(gy + i); g[0] = t.x; g[1 % E] = t.y; g[2 % E] = t.z; g[3 % E] = t.w; }
+        else g[0] = gy[i];
+#pragma unroll
+        for (int k = 0; k < WM_MIX_MAX; ++k) {
+            if (k < a.K && a.g[k]) {
+                const float w = __ldg(a.alpha + b * a.K + k);
+                if (VEC) *reinterpret_cast<float4*>(a.g[k] + i) = make_float4(__fmul_rn(w, g[0]), __fmul_rn(w, g[1 % E]), __fmul_rn(w, g[2 % E]), __fmul_rn(w, g[3 % E]));
+                else a.g[k][i] = __fmul_rn(w, g[0]);
+            }
+        }
+    }
+}
+
 // ---- tamper / splice (models/IRNcrop_model.py:348, models/IRNp_model.py:600) ---------------------
 //   out = a * (1 - m) + b * m,  m: [B, 1, H, W] broadcast over the C channels of a, b: [B, C, H, W]
 // bwd: ga = gy * (1 - m), gb = gy * m.  hw % 4 == 0 keeps a float4 inside one plane.
@@ -613,6 +667,43 @@ extern "C" int wm_slice_sum(const float* g, float* out, int64_t n, int K, void* 
     }
     slice_sum_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(g, out, n, K);
     WM_LAUNCH_CHECK("wm_slice_sum");
+    return WM_OK;
+}
+static int mix_fill(MixArgs& a, const wm_mix_desc* d, const float* alpha, int64_t B, int64_t chw, bool bwd, const char* who) {
+    WM_REQUIRE(d && alpha, WM_E_NULL, "%s: null pointer", who);
+    WM_REQUIRE(d->K >= 1 && d->K <= WM_MIX_MAX, WM_E_ARG, "%s: K must be 1..%d (got %d)", who, WM_MIX_MAX, d->K);
+    a.alpha = alpha; a.K = d->K; a.clamp01 = d->clamp01; a.quant = d->quantize; a.chw = chw; a.n = B * chw;
+    for (int k = 0; k < WM_MIX_MAX; ++k) { a.y[k] = nullptr; a.g[k] = nullptr; }
+    for (int k = 0; k < d->K; ++k) {
+        WM_REQUIRE(bwd || d->t[k], WM_E_NULL, "%s: member %d is null", who, k);
+        WM_REQUIRE(aligned(d->t[k], 4), WM_E_ALIGN, "%s: member %d must be 4-byte aligned", who, k);
+        if (bwd) a.g[k] = d->t[k]; else a.y[k] = d->t[k];
+    }
+    return WM_OK;
+}
+static bool mix_vec_ok(const wm_mix_desc* d, const void* other, int64_t chw) {
+    if (chw % 4 != 0 || !aligned(other, 16)) return false;
+    for (int k = 0; k < d->K; ++k) if (!aligned(d->t[k], 16)) return false;
+    return true;
+}
+extern "C" int wm_mix_fwd(const wm_mix_desc* desc_host, const float* alpha, float* out, int64_t B, int64_t chw, void* stream) {
+    if (B * chw <= 0) return WM_OK;      // empty work: nothing to validate or launch
+    MixArgs a{};
+    if (int rc = mix_fill(a, desc_host, alpha, B, chw, false, "wm_mix_fwd")) return rc;
+    WM_REQUIRE(out && aligned(out, 4), WM_E_NULL, "wm_mix_fwd: null / misaligned output");
+    if (mix_vec_ok(desc_host, out, chw)) mix_fwd_kernel<true><<<ew_grid(a.n / 4), 256, 0, (cudaStream_t)stream>>>(a, out);
+    else mix_fwd_kernel<false><<<ew_grid(a.n), 256, 0, (cudaStream_t)stream>>>(a, out);
+    WM_LAUNCH_CHECK("wm_mix_fwd");
+    return WM_OK;
+}
+extern "C" int wm_mix_bwd(const float* gy, const float* alpha, const wm_mix_desc* grads_host, int64_t B, int64_t chw, void* stream) {
+    if (B * chw <= 0) return WM_OK;      // empty work: nothing to validate or launch
+    MixArgs a{};
+    if (int rc = mix_fill(a, grads_host, alpha, B, chw, true, "wm_mix_bwd")) return rc;
+    WM_REQUIRE(gy && aligned(gy, 4), WM_E_NULL, "wm_mix_bwd: null / misaligned gy");
+    if (mix_vec_ok(grads_host, gy, chw)) mix_bwd_kernel<true><<<ew_grid(a.n / 4), 256, 0, (cudaStream_t)stream>>>(a, gy);
+    else mix_bwd_kernel<false><<<ew_grid(a.n), 256, 0, (cudaStream_t)stream>>>(a, gy);
+    WM_LAUNCH_CHECK("wm_mix_bwd");
     return WM_OK;
 }
 extern "C" int wm_splice_fwd(const float* a, const float* b, const float* mask, float* out, int64_t B, int C, int64_t hw,

@@ -9,7 +9,7 @@ from .modules import (  # noqa: F401
     Combined, Crop, Cropout, DiffJPEG, Dropout, ElementDropout, GF, GN, Gaussian, GaussianBlur,
     Identity, Jpeg, JpegCompression, JpegMask, JpegSS, JpegTest, MaskDropout, MiddleBlur, Quantization,
     Resize, SaltPepper, compress_jpeg, decompress_jpeg, diff_round, get_random_float, get_random_int,
-    quality_to_factor, round_only_at_0, AttackBank, AttackEpilogue, Splice,
+    quality_to_factor, round_only_at_0, AttackBank, AttackEpilogue, AttackMix, Splice,
 )
 
 __all__ = [
@@ -17,5 +17,5 @@ __all__ = [
     "GaussianBlur", "Identity", "Jpeg", "JpegCompression", "JpegMask", "JpegSS", "JpegTest", "MaskDropout",
     "MiddleBlur", "Quantization", "Resize", "SaltPepper", "compress_jpeg", "decompress_jpeg", "diff_round",
     "get_random_float", "get_random_int", "quality_to_factor", "round_only_at_0", "functional",
-    "AttackBank", "AttackEpilogue", "Splice",
+    "AttackBank", "AttackEpilogue", "AttackMix", "Splice",
 ]

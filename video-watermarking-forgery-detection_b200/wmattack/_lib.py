@@ -40,6 +40,11 @@ class Bank3Desc(C.Structure):
                 ("noise_mean", f32), ("noise_std", f32), ("noise_clamp", i32), ("seed", u64), ("offset", u64),
                 ("y_identity", C.c_void_p), ("clamp01", i32), ("quantize", i32)]
 
+class MixDesc(C.Structure):
+    """Mirror of wm_mix_desc (include/wm_attack.h): the K members of a convex mix (or their gradients)."""
+    _fields_ = [("t", C.c_void_p * 8), ("K", i32), ("clamp01", i32), ("quantize", i32)]
+
+
 # name -> argtypes; every function returns int.  Kept in one table so that the CPU test-suite
 # can check that the built library exports exactly the header's entry points.
 SIGNATURES = {
@@ -76,6 +81,8 @@ SIGNATURES = {
     "wm_u8_to_unit_float": [c_u8p, c_f32p, i64, vp],
     "wm_unit_float_to_u8": [c_f32p, c_u8p, i64, vp],
     "wm_bank3_fwd": [c_f32p, i64, i64, i32, i32, i32, C.POINTER(Bank3Desc), vp],
+    "wm_mix_fwd": [C.POINTER(MixDesc), c_f32p, c_f32p, i64, i64, vp],
+    "wm_mix_bwd": [c_f32p, c_f32p, C.POINTER(MixDesc), i64, i64, vp],
     "wm_attack_epilogue_fwd": [c_f32p, c_f32p, c_f32p, i64, i32, i32, vp],
     "wm_slice_sum": [c_f32p, c_f32p, i64, i32, vp],
     "wm_splice_fwd": [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, vp],

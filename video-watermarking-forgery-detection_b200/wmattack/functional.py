@@ -911,6 +911,52 @@ def attack_bank(x, sims, clamp: bool = True, quantize: bool = True):
     return _BankFn.apply(x, clamp, quantize, *sims)
 
 
+class _MixFn(torch.autograd.Function):
+    """Convex mix of K attacked versions + clamp_with_grad + Quantization in one pass (wm_mix_fwd); the backward
+    hands alpha[b, k] * gy to every member that needs a gradient (wm_mix_bwd)."""
+
+    @staticmethod
+    def forward(ctx, alpha, clamp, quantize, *ys):
+        k = len(ys)
+        if not 1 <= k <= 8:
+            raise ValueError(f"attack mix: 1..8 members supported, got {k}")
+        ys = [_flat(y, "attack mix") for y in ys]
+        shape = ys[0].shape
+        if any(y.shape != shape for y in ys):
+            raise ValueError("attack mix: all members must have the same shape")
+        b = shape[0]
+        alpha = _flat(alpha.detach(), "attack mix weights")
+        if tuple(alpha.shape) != (b, k):
+            raise ValueError(f"attack mix: alpha must be [B, K] = {(b, k)}, got {tuple(alpha.shape)}")
+        out = torch.empty(shape, device=ys[0].device, dtype=torch.float32)
+        desc = _lib.MixDesc()
+        for i, y in enumerate(ys):
+            desc.t[i] = y.data_ptr()
+        desc.K, desc.clamp01, desc.quantize = k, int(clamp), int(quantize)
+        _lib.call("wm_mix_fwd", C.byref(desc), alpha.data_ptr(), out.data_ptr(), b, ys[0].numel() // b, _stream())
+        ctx.save_for_backward(alpha)
+        ctx.meta = (k, tuple(shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        (alpha,) = ctx.saved_tensors
+        k, shape = ctx.meta
+        gy = _flat(gy, "attack mix backward")
+        grads = [torch.empty(shape, device=gy.device, dtype=torch.float32) if ctx.needs_input_grad[3 + i] else None for i in range(k)]
+        desc = _lib.MixDesc()
+        for i, g in enumerate(grads):
+            desc.t[i] = g.data_ptr() if g is not None else None
+        desc.K = k
+        _lib.call("wm_mix_bwd", gy.data_ptr(), alpha.data_ptr(), C.byref(desc), shape[0], gy.numel() // shape[0], _stream())
+        return (None, None, None) + tuple(grads)
+
+
+def attack_mix(ys, alpha, clamp: bool = True, quantize: bool = True):
+    """Quantization(clamp_with_grad(sum_k alpha[:, k] * ys[k])) — the hybrid attack of models/IRNcrop_model.py:357-373."""
+    return _MixFn.apply(alpha, clamp, quantize, *ys)
+
+
 class _SpliceFn(torch.autograd.Function):
     """out = a * (1 - mask) + b * mask, mask [B,1,H,W] broadcast over channels
     (models/IRNcrop_model.py:348)."""

@@ -684,6 +684,22 @@ class AttackEpilogue(nn.Module):
         return F_.attack_epilogue(x, simulated, self.clamp, self.quantize)
 
 
+class AttackMix(nn.Module):
+    """The hybrid attack of the video trainer (models/IRNcrop_model.py:357-373, as intended: the loop there adds the
+    softmax weights themselves instead of the weighted images): `alpha = softmax(randn(B, K))`, the K attacked versions
+    mixed per sample, then clamp_with_grad and Quantization — one pass over the K tensors instead of ~2K + 7."""
+
+    def __init__(self, clamp: bool = True, quantize: bool = True):
+        super().__init__()
+        self.clamp, self.quantize = clamp, quantize
+
+    def forward(self, attacked: Sequence[torch.Tensor], alpha: Optional[torch.Tensor] = None):
+        attacked = [a[0] if isinstance(a, tuple) else a for a in attacked]
+        if alpha is None:                  # the trainer's draw (:358-359), one weight vector per sample
+            alpha = torch.softmax(torch.randn(attacked[0].shape[0], len(attacked), device=attacked[0].device), dim=1)
+        return F_.attack_mix(attacked, alpha, self.clamp, self.quantize)
+
+
 class AttackBank(nn.Module):
     """The K-way attack of the trainers (models/IRNp_model.py:609-680; the per-frame 5-way loop of
     models/IRNcrop_model.py:357-370): every layer attacks the SAME batch, each result is clamped,
