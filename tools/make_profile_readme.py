@@ -14,7 +14,7 @@ for row in csv.DictReader(lines):
     agg.setdefault(row["Kernel Name"], []).append(v)
 tot = sum(sum(v) for k, v in agg.items() if "wm::" in k)
 old = open(os.path.join(P, "README.md")).read() if os.path.exists(os.path.join(P, "README.md")) else ""
-tail = old[old.index("## Experiments"):] if "## Experiments" in old else ""
+tail = old[old.index("## Scaling"):] if "## Scaling" in old else ""
 out = ["# Round-2 measurements (B200, 64x3x512x512 fp32, BASELINE config 2: 7 layers, 14 kernels per step)", "",
        "Source files: `bench_r2_1gpu.json` (python bench.py --steps 20 --warmup 5), `bench_r2_2gpu.json` (torchrun, 2 ranks),",
        "`ncu_r2_launches.csv` (ncu --metrics gpu__time_duration.sum --clock-control none, same command),",
