@@ -388,7 +388,31 @@ def run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=False):
     ms = allreduce_max(t0.elapsed_time(t1), world, dev)
     nbytes = B * 3 * H * W * (1 if u8 else 4)
     per_step = ms / args.steps
+    # the link itself: the same two buffers copied up and down at once with NO kernels in between (all ranks together),
+    # so the distance of the step above from the PCIe / host-memory ceiling is explicit
+    src_h, dst_d = host[0], (stage[0] if u8 else devbuf[0])
+    src_d, dst_h = (res_dev[0] if u8 else devbuf[1]), res_host[0]
+
+    def raw_pair():
+        with torch.cuda.stream(up_stream):
+            dst_d.copy_(src_h, non_blocking=True)
+        with torch.cuda.stream(down_stream):
+            dst_h.copy_(src_d, non_blocking=True)
+    raw_pair()
+    torch.cuda.synchronize()
+    barrier(world)
+    l0 = torch.cuda.Event(enable_timing=True); l1 = torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(5):
+        raw_pair()
+    main.wait_stream(up_stream); main.wait_stream(down_stream)
+    l1.record()
+    torch.cuda.synchronize()
+    link_ms = allreduce_max(l0.elapsed_time(l1) / 5, world, dev)
     return {"value": round(world * args.steps * px_step / (ms / 1e3) / 1e6, 1), "unit": "Mpix/s",
+            "link_probe": {"ms_per_up_down_pair": round(link_ms, 4), "aggregate_GBps_each_way": round(world * nbytes / (link_ms / 1e3) / 1e9, 1),
+                           "step_over_link": round(per_step / link_ms, 3),
+                           "note": "the same buffers copied H2D and D2H concurrently with no kernels: the link ceiling of this step"},
             "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
             "ms_per_step": round(per_step, 4), "host_cpus": numa,
             "aggregate_h2d_GBps": round(world * nbytes / (per_step / 1e3) / 1e9, 1),
