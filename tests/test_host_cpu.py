@@ -42,6 +42,56 @@ def test_library_exports_every_header_symbol(lib):
     assert isinstance(lib.wm_last_error(), bytes)
 
 
+def header_prototypes():
+    """name -> list of C parameter declarations, parsed from include/wm_attack.h."""
+    src = open(os.path.join(ROOT, "include", "wm_attack.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int64_t|int|const char\s*\*)\s*(wm_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = [q.strip() for q in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params == ["void"] else params
+    return out
+
+
+def test_ctypes_signatures_match_the_header_parameter_by_parameter():
+    """The ctypes table is written by hand: every entry point must have as many arguments as its prototype, and each
+    argument the right CLASS (pointer / 64-bit integer / 32-bit integer / float) - a swapped or missing argument would
+    otherwise only show up as garbage on the GPU."""
+    import ctypes as C
+    protos = header_prototypes()
+    table = dict(_lib.SIGNATURES)
+    table.update({k: v[1] for k, v in _lib.HELPERS.items()})
+
+    def c_class(decl):
+        if "*" in decl:
+            return "ptr"
+        t = decl.replace("const", "").split()
+        if t[0] in ("int64_t", "uint64_t"):
+            return "i64"
+        if t[0] in ("int", "unsigned", "uint32_t", "int32_t"):
+            return "i32"
+        if t[0] == "float":
+            return "f32"
+        raise AssertionError(f"unparsed parameter {decl!r}")
+
+    def ct_class(t):
+        if t in (C.c_void_p, C.c_char_p) or isinstance(t, type(C.POINTER(C.c_int))) or getattr(t, "_type_", None) == "P":
+            return "ptr"
+        if t in (C.c_int64, C.c_uint64, C.c_size_t):
+            return "i64"
+        if t in (C.c_int, C.c_uint):
+            return "i32"
+        if t is C.c_float:
+            return "f32"
+        raise AssertionError(f"unclassified ctypes type {t}")
+
+    for name, argtypes in table.items():
+        assert name in protos, name
+        want = [c_class(d) for d in protos[name]]
+        got = [ct_class(t) for t in argtypes]
+        assert got == want, f"{name}: ctypes {got} vs header {want}"
+
+
 def test_invalid_arguments_fail_loudly_without_a_gpu(lib):
     # argument validation happens before any CUDA call, so it is testable on a CPU box
     with pytest.raises(_lib.WMAttackError, match="null"):
