@@ -32,6 +32,11 @@ __device__ __forceinline__ float feq(float a, float b) {
     float d; asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d;
 }
 // packed fp32x2 FMA (FFMA2): two independent IEEE fmas per issue slot
+// a0 += g0 if the low halves of (h, w) are equal, a1 += g1 if the high halves are
+__device__ __forceinline__ void add_if_eq2(float& a0, float& a1, uint32_t h, uint32_t w, float g0, float g1) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.f16x2 p|q, %2, %3;\n\t@p add.f32 %0, %0, %4;\n\t@q add.f32 %1, %1, %5;\n\t}"
+        : "+f"(a0), "+f"(a1) : "r"(h), "r"(w), "f"(g0), "f"(g1));
+}
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra, rb, rc, rd;
     asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
@@ -456,24 +461,28 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
         const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
         const float* gcol = bufs + s * GS + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
         const uint8_t* icol = ibufs + s * IS + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
-        float g[K][WC];       // window columns -R .. 4+R-1 of the lane's 4 columns
-        int ix[K][WC];
-        float fx[K == 5 ? K : 1][WC];      // 5x5: the positions as floats (FSET masks for the packed accumulation below)
+        float g[K][WC];            // window columns -R .. 4+R-1 of the lane's 4 columns
+        uint32_t hp[K][WC - 1];    // (idx[j], idx[j+1]) of adjacent window columns as a half2 of 1024 + idx (0x64nn)
         auto load_row = [&](int row, int slot) {
             const float* p = gcol + row * MT_BW;
             const float4 c = *reinterpret_cast<const float4*>(p);
             g[slot][R] = c.x; g[slot][R + 1] = c.y; g[slot][R + 2] = c.z; g[slot][R + 3] = c.w;
-            const uint8_t* q = icol + row * MB_IBW;
-            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(q);
-            ix[slot][R] = w4 & 0xff; ix[slot][R + 1] = (w4 >> 8) & 0xff; ix[slot][R + 2] = (w4 >> 16) & 0xff; ix[slot][R + 3] = w4 >> 24;
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                g[slot][R - 1 - i] = p[-1 - i]; g[slot][R + 4 + i] = p[4 + i];
-                ix[slot][R - 1 - i] = q[-1 - i]; ix[slot][R + 4 + i] = q[4 + i];
-            }
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(icol + row * MB_IBW);
+            const uint32_t wa = qw[-1], wb = qw[0], wc = qw[1], bias = 0x64646464u;
             if (K == 5) {
-#pragma unroll
-                for (int i = 0; i < WC; ++i) fx[slot][i] = __int2float_rn(ix[slot][i]);
+                const float2 l = *reinterpret_cast<const float2*>(p - 2), h = *reinterpret_cast<const float2*>(p + 4);
+                g[slot][0] = l.x; g[slot][1] = l.y; g[slot][6] = h.x; g[slot][7] = h.y;
+                const uint32_t u0 = __byte_perm(wa, wb, 0x5432), u1 = __byte_perm(wb, wc, 0x5432);   // window bytes 0..3, 4..7
+                hp[slot][0] = __byte_perm(u0, bias, 0x4140); hp[slot][1] = __byte_perm(u0, bias, 0x4241);
+                hp[slot][2] = __byte_perm(u0, bias, 0x4342); hp[slot][3] = __byte_perm(wb, bias, 0x4241);
+                hp[slot][4] = __byte_perm(u1, bias, 0x4140); hp[slot][5] = __byte_perm(u1, bias, 0x4241);
+                hp[slot][WC - 2] = __byte_perm(u1, bias, 0x4342);
+            } else {
+                g[slot][0] = p[-1]; g[slot][5] = p[4];
+                const uint32_t u0 = __byte_perm(wa, wb, 0x0043), u1 = __byte_perm(wb, wc, 0x0043);   // window bytes (0, 1), (4, 5)
+                hp[slot][0] = __byte_perm(u0, bias, 0x4140); hp[slot][1] = __byte_perm(wb, bias, 0x4140);
+                hp[slot][2] = __byte_perm(wb, bias, 0x4241); hp[slot][3] = __byte_perm(wb, bias, 0x4342);
+                hp[slot][WC - 2] = __byte_perm(u1, bias, 0x4140);
             }
         };
 #pragma unroll
@@ -485,39 +494,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
             load_row(r + K - 1, (r + K - 1) % K);
             float4 o;
             float* op = &o.x;
-            if (K == 5) {
-                // 25-term gather, two adjacent outputs per packed FMA: acc2 += {[idx == want], [idx' == want]} * {g, g'}
-                // (fma(1, g, acc) == acc + g bit for bit, fma(0, g, acc) == acc for finite g): 2 FSET + 1 FFMA2 per
-                // pair of terms instead of 2 compares + 2 predicated adds; same summation order per output.
+            // K*K-term gather, two adjacent outputs per compare: one packed half compare (HSETP2) of the two positions
+            // against the wanted one sets two predicates, each guarding a plain add - 1.5 instructions per term, fixed
+            // summation order, nothing multiplied (a non-finite cotangent elsewhere in the window cannot leak in).
+            // q = p + (dy, dx) is tile row r + R + dy = ring slot (r + R + dy) % K; p is at window position (R - dy, R - dx) of q
 #pragma unroll
-                for (int c2 = 0; c2 < 4; c2 += 2) {
-                    float2 acc = make_float2(0.f, 0.f);
+            for (int c2 = 0; c2 < 4; c2 += 2) {
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                    for (int dy = -R; dy <= R; ++dy)
+                for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
-                        for (int dx = -R; dx <= R; ++dx) {
-                            const int slot = (r + R + dy) % K, col = c2 + R + dx;
-                            const float want = float((R - dy) * K + (R - dx));
-                            acc = ffma2(make_float2(feq(fx[slot][col], want), feq(fx[slot][col + 1], want)),
-                                        make_float2(g[slot][col], g[slot][col + 1]), acc);
-                        }
-                    op[c2] = acc.x; op[c2 + 1] = acc.y;
-                }
-            } else {
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int dy = -R; dy <= R; ++dy)
-#pragma unroll
-                        for (int dx = -R; dx <= R; ++dx) {
-                            // q = p + (dy, dx): tile row r + R + dy = ring slot (r + R + dy) % K; p is at
-                            // window position (R - dy, R - dx) of q
-                            const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
-                            acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
-                        }
-                    op[c4] = acc;
-                }
+                    for (int dx = -R; dx <= R; ++dx) {
+                        const int slot = (r + R + dy) % K, col = c2 + R + dx;
+                        const uint32_t want = 0x64006400u + 0x00010001u * uint32_t((R - dy) * K + (R - dx));
+                        add_if_eq2(a0, a1, hp[slot][col], want, g[slot][col], g[slot][col + 1]);
+                    }
+                op[c2] = a0; op[c2 + 1] = a1;
             }
             if (col_ok && gy0 + r < a.H) {
                 if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
