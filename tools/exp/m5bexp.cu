@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <string>
 #include <vector>
 #include "tma.cuh"
 #include "wm_common.cuh"
@@ -131,17 +132,19 @@ __global__ void __launch_bounds__(S5_THREADS, MINB) m5b_scatter_kernel(const __g
 }
 
 // reference: plain gather in the library kernel's summation order
+template <int K>
 __global__ void m5b_ref_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ idx, int64_t idx_sh, float* __restrict__ gx,
                                int N, int H, int W) {
+    constexpr int R = K / 2;
     const int64_t total = int64_t(N) * H * W;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
         const int w = int(i % W), h = int((i / W) % H); const int64_t n = i / (int64_t(H) * W);
         float acc = 0.f;
-        for (int dy = -2; dy <= 2; ++dy)
-            for (int dx = -2; dx <= 2; ++dx) {
+        for (int dy = -R; dy <= R; ++dy)
+            for (int dx = -R; dx <= R; ++dx) {
                 const int qy = h + dy, qx = w + dx;
                 if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
-                if (idx[(n * H + qy) * idx_sh + qx] == (2 - dy) * 5 + (2 - dx)) acc += gy[(n * H + qy) * W + qx];
+                if (idx[(n * H + qy) * idx_sh + qx] == (R - dy) * K + (R - dx)) acc += gy[(n * H + qy) * W + qx];
             }
         gx[i] = acc;
     }
@@ -187,26 +190,41 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&gy, n * 4)); CK(cudaMalloc(&g0, n * 4)); CK(cudaMalloc(&g1, n * 4)); CK(cudaMalloc(&idx, n));
     CK(cudaMemcpy(gy, hg.data(), n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(idx, hi.data(), n, cudaMemcpyHostToDevice));
     printf("shape %dx3x%dx%d\n", B, H, W);
-    m5b_ref_kernel<<<148 * 8, 256>>>(gy, idx, W, g0, N, H, W);
+    m5b_ref_kernel<5><<<148 * 8, 256>>>(gy, idx, W, g0, N, H, W);
     CK(cudaDeviceSynchronize());
     std::vector<float> r0(n), r1(n);
     CK(cudaMemcpy(r0.data(), g0, n * 4, cudaMemcpyDeviceToHost));
 
-    // library kernel for the time to beat
-    if (void* lib = dlopen("video-watermarking-forgery-detection_b200/wmattack/libwmattack.so", RTLD_NOW)) {
+    // library kernels (WM_LIBS = colon-separated paths; default: the built library)
+    std::string libs = getenv("WM_LIBS") ? getenv("WM_LIBS") : "video-watermarking-forgery-detection_b200/wmattack/libwmattack.so";
+    std::vector<uint8_t> hi3(n); for (size_t i = 0; i < n; ++i) hi3[i] = hi[i] % 9;
+    uint8_t* idx3; CK(cudaMalloc(&idx3, n)); CK(cudaMemcpy(idx3, hi3.data(), n, cudaMemcpyHostToDevice));
+    float* g3; CK(cudaMalloc(&g3, n * 4));
+    m5b_ref_kernel<3><<<148 * 8, 256>>>(gy, idx3, W, g3, N, H, W);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> r3(n); CK(cudaMemcpy(r3.data(), g3, n * 4, cudaMemcpyDeviceToHost));
+    for (size_t pos = 0; pos < libs.size();) {
+        size_t e = libs.find(':', pos); if (e == std::string::npos) e = libs.size();
+        const std::string path = libs.substr(pos, e - pos); pos = e + 1;
+        void* lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!lib) { printf("%s: %s\n", path.c_str(), dlerror()); continue; }
         using bwd_t = int (*)(const float*, const uint8_t*, int64_t, float*, int, int, int, int, void*);
-        if (auto f = (bwd_t)dlsym(lib, "wm_median_bwd")) {
+        auto f = (bwd_t)dlsym(lib, "wm_median_bwd");
+        for (int k = 3; k <= 5; k += 2) {
+            const uint8_t* ip = k == 3 ? idx3 : idx; const std::vector<float>& ref = k == 3 ? r3 : r0;
             cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-            for (int i = 0; i < 3; ++i) f(gy, idx, W, g1, N, H, W, 5, nullptr);
+            CK(cudaMemset(g1, 0xff, n * 4));
+            for (int i = 0; i < 3; ++i) f(gy, ip, W, g1, N, H, W, k, nullptr);
             CK(cudaEventRecord(e0));
-            for (int i = 0; i < 20; ++i) f(gy, idx, W, g1, N, H, W, 5, nullptr);
+            for (int i = 0; i < 20; ++i) f(gy, ip, W, g1, N, H, W, k, nullptr);
             CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
             CK(cudaMemcpy(r1.data(), g1, n * 4, cudaMemcpyDeviceToHost));
-            size_t bad = 0; for (size_t i = 0; i < n; ++i) bad += memcmp(&r0[i], &r1[i], 4) != 0;
-            printf("library gather : %8.1f us   bit mismatches vs plain gather %zu\n", ms * 1000.f / 20, bad);
+            size_t bad = 0; for (size_t i = 0; i < n; ++i) bad += memcmp(&ref[i], &r1[i], 4) != 0;
+            printf("%-40s k=%d : %8.1f us   bit mismatches vs plain gather %zu\n", path.substr(path.rfind('/') + 1).c_str(), k, ms * 1000.f / 20, bad);
         }
-    } else printf("library not found (%s)\n", dlerror());
+    }
+    if (getenv("WM_LIBS")) return 0;
 
     CUtensorMap tg, ti;
     if (tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, S5_GW, S5_QH)) { fprintf(stderr, "tmap g failed\n"); return 1; }

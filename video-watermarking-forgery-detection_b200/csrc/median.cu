@@ -397,10 +397,26 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
 // Two tile rings (gy: float, idx: uint8 with a 16-byte halo); a lane owns 4 adjacent p columns and
 // walks down its strip with the last K rows of (gy, idx) in registers.  Pure gather, fixed
 // summation order: deterministic.
-constexpr int MB_STAGES = 2, MB_IBW = MT_TW + 32;
-template <int K> constexpr int mb_bh() { return MT_TH + K - 1; }
-template <int K> constexpr int mb_gstride() { return ((MT_BW * mb_bh<K>() + 31) / 32) * 32; }          // floats
-template <int K> constexpr int mb_istride() { return ((MB_IBW * mb_bh<K>() + 127) / 128) * 128; }      // bytes
+constexpr int MB_IBW = MT_TW + 32;
+#ifndef WM_MB3_TH
+#define WM_MB3_TH 64
+#define WM_MB3_STAGES 2
+#define WM_MB3_MINB 2
+#endif
+#ifndef WM_MB5_TH
+#define WM_MB5_TH 64
+#define WM_MB5_STAGES 2
+#define WM_MB5_MINB 2
+#endif
+// tile rows, ring depth and CTAs per SM of the backward, per window size
+template <int K> struct MBCfg {
+    static constexpr int TH = K == 3 ? WM_MB3_TH : WM_MB5_TH, STAGES = K == 3 ? WM_MB3_STAGES : WM_MB5_STAGES,
+                         MINB = K == 3 ? WM_MB3_MINB : WM_MB5_MINB;
+    static constexpr int ROWS = TH / (MT_THREADS / 32);            // output rows per warp strip
+    static constexpr int BH = TH + K - 1;
+    static constexpr int GS = ((MT_BW * BH + 31) / 32) * 32;       // floats per cotangent stage
+    static constexpr int IS = ((MB_IBW * BH + 127) / 128) * 128;   // bytes per idx stage
+};
 
 struct MedBArgs {
     float* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
@@ -410,10 +426,11 @@ struct MedBArgs {
 // RAGGED: the (gy) ring is filled by cp.async, the idx ring still by TMA (the forward wrote the arg-median plane with
 // a 16-byte row stride), and gx leaves by scalar stores.
 template <int K, bool RAGGED = false>
-__global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
+__global__ void __launch_bounds__(MT_THREADS, MBCfg<K>::MINB) median_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                                        const __grid_constant__ CUtensorMap tm_i,
                                                                        const MedBArgs a) {
-    constexpr int R = K / 2, BH = mb_bh<K>(), GS = mb_gstride<K>(), IS = mb_istride<K>(), WC = 4 + 2 * R;
+    using Cfg = MBCfg<K>;
+    constexpr int R = K / 2, BH = Cfg::BH, GS = Cfg::GS, IS = Cfg::IS, WC = 4 + 2 * R, MB_STAGES = Cfg::STAGES, TH = Cfg::TH, ROWS = Cfg::ROWS;
     extern __shared__ __align__(128) float bufs[];
     uint8_t* ibufs = reinterpret_cast<uint8_t*>(bufs + MB_STAGES * GS);
     __shared__ uint64_t full[MB_STAGES];
@@ -431,16 +448,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         if (RAGGED) {
-            if (t < a.total) stage_box_cpasync<MT_THREADS>(bufs + s * GS, a.rag, n, a.H, a.W, tx * MT_TW - MT_HALO, ty * MT_TH - R, MT_BW, BH);
+            if (t < a.total) stage_box_cpasync<MT_THREADS>(bufs + s * GS, a.rag, n, a.H, a.W, tx * MT_TW - MT_HALO, ty * TH - R, MT_BW, BH);
             else asm volatile("cp.async.commit_group;" ::: "memory");
             if (tid == 0 && t < a.total) {
                 mbar_expect_tx(&full[s], MB_IBW * BH);
-                tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
+                tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * TH - R, n, &full[s]);
             }
         } else {
             mbar_expect_tx(&full[s], MT_BW * BH * sizeof(float) + MB_IBW * BH);
-            tma_load_3d(bufs + s * GS, &tm_g, tx * MT_TW - MT_HALO, ty * MT_TH - R, n, &full[s]);
-            tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * MT_TH - R, n, &full[s]);
+            tma_load_3d(bufs + s * GS, &tm_g, tx * MT_TW - MT_HALO, ty * TH - R, n, &full[s]);
+            tma_load_3d(ibufs + s * IS, &tm_i, tx * MT_TW - 16, ty * TH - R, n, &full[s]);
         }
     };
     if (RAGGED || tid == 0) {
@@ -458,20 +475,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
         mbar_wait(&full[s], (it / MB_STAGES) & 1);
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
-        const float* gcol = bufs + s * GS + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
-        const uint8_t* icol = ibufs + s * IS + (strip * MT_ROWS) * MB_IBW + 16 + 4 * cg;
-        float g[K][WC];            // window columns -R .. 4+R-1 of the lane's 4 columns
-        uint32_t hp[K][WC - 1];    // (idx[j], idx[j+1]) of adjacent window columns as a half2 of 1024 + idx (0x64nn)
+        const int gx = tx * MT_TW + 4 * cg, gy0 = ty * TH + strip * ROWS;
+        const float* gcol = bufs + s * GS + (strip * ROWS) * MT_BW + MT_HALO + 4 * cg;
+        const uint8_t* icol = ibufs + s * IS + (strip * ROWS) * MB_IBW + 16 + 4 * cg;
+        float g[K][WC];                          // window columns -R .. 4+R-1 of the lane's 4 columns
+        uint32_t hp[K == 5 ? K : 1][WC - 1];     // 5x5: (idx[j], idx[j+1]) of adjacent window columns as a half2 of 1024 + idx (0x64nn)
+        int ix[K == 3 ? K : 1][WC];              // 3x3: the positions as integers
         auto load_row = [&](int row, int slot) {
             const float* p = gcol + row * MT_BW;
             const float4 c = *reinterpret_cast<const float4*>(p);
             g[slot][R] = c.x; g[slot][R + 1] = c.y; g[slot][R + 2] = c.z; g[slot][R + 3] = c.w;
-            const uint32_t* qw = reinterpret_cast<const uint32_t*>(icol + row * MB_IBW);
-            const uint32_t wa = qw[-1], wb = qw[0], wc = qw[1], bias = 0x64646464u;
+            const uint8_t* q = icol + row * MB_IBW;
             if (K == 5) {
                 const float2 l = *reinterpret_cast<const float2*>(p - 2), h = *reinterpret_cast<const float2*>(p + 4);
                 g[slot][0] = l.x; g[slot][1] = l.y; g[slot][6] = h.x; g[slot][7] = h.y;
+                const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+                const uint32_t wa = qw[-1], wb = qw[0], wc = qw[1], bias = 0x64646464u;
                 const uint32_t u0 = __byte_perm(wa, wb, 0x5432), u1 = __byte_perm(wb, wc, 0x5432);   // window bytes 0..3, 4..7
                 hp[slot][0] = __byte_perm(u0, bias, 0x4140); hp[slot][1] = __byte_perm(u0, bias, 0x4241);
                 hp[slot][2] = __byte_perm(u0, bias, 0x4342); hp[slot][3] = __byte_perm(wb, bias, 0x4241);
@@ -479,10 +498,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
                 hp[slot][WC - 2] = __byte_perm(u1, bias, 0x4342);
             } else {
                 g[slot][0] = p[-1]; g[slot][5] = p[4];
-                const uint32_t u0 = __byte_perm(wa, wb, 0x0043), u1 = __byte_perm(wb, wc, 0x0043);   // window bytes (0, 1), (4, 5)
-                hp[slot][0] = __byte_perm(u0, bias, 0x4140); hp[slot][1] = __byte_perm(wb, bias, 0x4140);
-                hp[slot][2] = __byte_perm(wb, bias, 0x4241); hp[slot][3] = __byte_perm(wb, bias, 0x4342);
-                hp[slot][WC - 2] = __byte_perm(u1, bias, 0x4140);
+                const uint32_t w4 = *reinterpret_cast<const uint32_t*>(q);
+                ix[slot][0] = q[-1]; ix[slot][1] = w4 & 0xff; ix[slot][2] = (w4 >> 8) & 0xff; ix[slot][3] = (w4 >> 16) & 0xff;
+                ix[slot][4] = w4 >> 24; ix[slot][WC - 1] = q[4];
             }
         };
 #pragma unroll
@@ -490,26 +508,43 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
         const bool col_ok = gx < a.W;
         float* dst = a.gx + (int64_t(n) * a.H + gy0) * a.W + gx;
 #pragma unroll
-        for (int r = 0; r < MT_ROWS; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             load_row(r + K - 1, (r + K - 1) % K);
             float4 o;
             float* op = &o.x;
-            // K*K-term gather, two adjacent outputs per compare: one packed half compare (HSETP2) of the two positions
-            // against the wanted one sets two predicates, each guarding a plain add - 1.5 instructions per term, fixed
-            // summation order, nothing multiplied (a non-finite cotangent elsewhere in the window cannot leak in).
             // q = p + (dy, dx) is tile row r + R + dy = ring slot (r + R + dy) % K; p is at window position (R - dy, R - dx) of q
+            if (K == 5) {
+                // 25-term gather, two adjacent outputs per compare: one packed half compare (HSETP2) of the two positions
+                // against the wanted one sets two predicates, each guarding a plain add - 1.5 instructions per term, fixed
+                // summation order, nothing multiplied (a non-finite cotangent elsewhere in the window cannot leak in).
+                // (Round 1's 2 FSET + 1 FFMA2 per pair of terms paid register-pair moves on top: 121 us against 94.)
 #pragma unroll
-            for (int c2 = 0; c2 < 4; c2 += 2) {
-                float a0 = 0.f, a1 = 0.f;
+                for (int c2 = 0; c2 < 4; c2 += 2) {
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int dy = -R; dy <= R; ++dy)
+                    for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
-                    for (int dx = -R; dx <= R; ++dx) {
-                        const int slot = (r + R + dy) % K, col = c2 + R + dx;
-                        const uint32_t want = 0x64006400u + 0x00010001u * uint32_t((R - dy) * K + (R - dx));
-                        add_if_eq2(a0, a1, hp[slot][col], want, g[slot][col], g[slot][col + 1]);
-                    }
-                op[c2] = a0; op[c2 + 1] = a1;
+                        for (int dx = -R; dx <= R; ++dx) {
+                            const int slot = (r + R + dy) % K, col = c2 + R + dx;
+                            const uint32_t want = 0x64006400u + 0x00010001u * uint32_t((R - dy) * K + (R - dx));
+                            add_if_eq2(a0, a1, hp[slot][col], want, g[slot][col], g[slot][col + 1]);
+                        }
+                    op[c2] = a0; op[c2 + 1] = a1;
+                }
+            } else {
+                // 9 terms: compare + select + add (the packed-compare form measured 3 us slower here: 85 against 82)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int dy = -R; dy <= R; ++dy)
+#pragma unroll
+                        for (int dx = -R; dx <= R; ++dx) {
+                            const int slot = (r + R + dy) % K, want = (R - dy) * K + (R - dx);
+                            acc += (ix[slot][c4 + R + dx] == want) ? g[slot][c4 + R + dx] : 0.f;
+                        }
+                    op[c4] = acc;
+                }
             }
             if (col_ok && gy0 + r < a.H) {
                 if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
@@ -527,15 +562,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median_bwd_tma_kernel(const __g
 template <int K, bool RAGGED>
 static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, cudaStream_t st) {
     CUtensorMap tg{}, ti;
-    int rc = RAGGED ? 0 : tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, mb_bh<K>());
-    if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * idx_sh, idx_sh, MB_IBW, mb_bh<K>());
+    int rc = RAGGED ? 0 : tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, MBCfg<K>::BH);
+    if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * idx_sh, idx_sh, MB_IBW, MBCfg<K>::BH);
     if (rc) { set_error("wm_median_bwd: cuTensorMapEncodeTiled failed (%d)", rc); return WM_E_ARG; }
-    MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, RaggedSrc{gy, int64_t(H) * W, W}};
+    MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MBCfg<K>::TH - 1) / MBCfg<K>::TH, 0, RaggedSrc{gy, int64_t(H) * W, W}};
     ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
-    const size_t smem = sizeof(float) * size_t(MB_STAGES) * mb_gstride<K>() + size_t(MB_STAGES) * mb_istride<K>();
+    const size_t smem = size_t(MBCfg<K>::STAGES) * (sizeof(float) * MBCfg<K>::GS + MBCfg<K>::IS);
     cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
-    const int64_t cap = int64_t(sm_count()) * 2;
+    const int64_t cap = int64_t(sm_count()) * MBCfg<K>::MINB;
     median_bwd_tma_kernel<K, RAGGED><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
     WM_LAUNCH_CHECK("wm_median_bwd(tma)");
     return WM_OK;
