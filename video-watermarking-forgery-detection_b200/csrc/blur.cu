@@ -83,7 +83,12 @@ __global__ void __launch_bounds__(BL_THREADS) gaussblur_kernel(const BlurArgs a)
 // the last K horizontally filtered rows in registers; every output row costs one LDS.128 (+2R
 // scalar neighbours) and one coalesced STG.128 — x is read from HBM once, y written once.
 // ---------------------------------------------------------------------------------------------
-constexpr int BT_TW = 128, BT_TH = 64, BT_HALO = 4, BT_BW = BT_TW + 2 * BT_HALO, BT_THREADS = 256, BT_ROWS = 8;
+#ifndef WM_BT_TH
+#define WM_BT_TH 64
+#define WM_BT_STAGES 3
+#define WM_BT_MINB 2
+#endif
+constexpr int BT_TW = 128, BT_TH = WM_BT_TH, BT_HALO = 4, BT_BW = BT_TW + 2 * BT_HALO, BT_THREADS = 256, BT_ROWS = BT_TH / (BT_THREADS / 32);
 
 struct BlurTArgs {
     float* y; int N, H, W, tiles_x, tiles_y; int64_t total;
@@ -92,13 +97,13 @@ struct BlurTArgs {
     RaggedSrc rag;      // RAGGED instantiation only: the source planes (no tensor map for rows that are not 16-byte aligned)
 };
 
-template <int K> constexpr int bt_stages() { return K <= 5 ? 3 : 2; }
+template <int K> constexpr int bt_stages() { return K <= 5 ? WM_BT_STAGES : 2; }
 template <int K> constexpr int bt_stage_floats() { return ((BT_BW * (BT_TH + K - 1) + 31) / 32) * 32; }
 
 // RAGGED = rows not 16-byte aligned (W % 4 != 0): the ring is filled by cp.async instead of TMA (stage_box_cpasync) and
 // the output leaves by scalar stores; everything between is the same code.
 template <int K, bool RAGGED>
-__global__ void __launch_bounds__(BT_THREADS, 2) gaussblur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BlurTArgs a) {
+__global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BlurTArgs a) {
     constexpr int R = K / 2, BH = BT_TH + 2 * R, S = bt_stages<K>(), STRIDE = bt_stage_floats<K>();
     extern __shared__ __align__(128) float bufs[];
     __shared__ uint64_t full[S];
@@ -211,7 +216,7 @@ static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y,
     const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
     cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
-    const int64_t cap = int64_t(sm_count()) * 2;
+    const int64_t cap = int64_t(sm_count()) * WM_BT_MINB;
     const unsigned grid = (unsigned)(a.total < cap ? a.total : cap);
     gaussblur_tma_kernel<K, RAGGED><<<grid, BT_THREADS, smem, st>>>(tm, a);
     WM_LAUNCH_CHECK("wm_gaussblur(tma)");
