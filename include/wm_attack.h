@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WM_ABI_VERSION 3
+#define WM_ABI_VERSION 4
 
 #define WM_OK 0
 #define WM_E_NULL (-1)      /* required pointer is NULL */
@@ -162,6 +162,13 @@ int wm_jpeg8_quantised(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sh,
 int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
                  const float* taps_host, int k, int border, int adjoint,
                  const wm_store_epilogue* ep, void* stream);
+/* The same filter at the autocast boundary (models/IRNcrop_model.py:340: the attacks run under torch.cuda.amp.autocast):
+ * x_dtype / y_dtype are WM_DT_*; ONE side may be float16 / bfloat16 - a typed SOURCE is staged by TMA as it is and widened
+ * on the way to registers (the forward of a half image), a typed RESULT is rounded to nearest even in the store (the
+ * gradient of a half image) - instead of a separate .float() / .to(dtype) pass over the tensor.  Zero border, k in {3,5,7},
+ * rows on 16-byte boundaries (W % 8 == 0 for a 2-byte side, aligned strides); WM_E_ALIGN otherwise (convert first). */
+int wm_gaussblur_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, void* y, int y_dtype, int N, int H, int W,
+                       const float* taps_host, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * k x k median, zero padding, k in {3,5}  (MiddleBlur, noise_layers/middle_filter.py:5-13 ->
@@ -174,6 +181,13 @@ int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, in
 int wm_median_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh,
                   int N, int H, int W, int k, const wm_store_epilogue* ep, void* stream);
 int wm_median_bwd(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, int k, void* stream);
+/* Autocast boundary: float16 / bfloat16 source planes through the same TMA ring (widening is exact: the median and its
+ * position are those of the float32 image), and gx stored in that type.  Rows on 16-byte boundaries only (W % 8 == 0 for
+ * the 2-byte planes; WM_E_ALIGN otherwise); WM_DT_F32 forwards to the entry points above. */
+int wm_median_fwd_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh,
+                        int N, int H, int W, int k, void* stream);
+int wm_median_bwd_typed(const float* gy, const uint8_t* idx, int64_t idx_sh, void* gx, int gx_dtype, int N, int H, int W, int k,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise attacks over n contiguous floats.  Randomness: Philox4x32-10 keyed by `seed`,
@@ -275,6 +289,13 @@ int wm_resize_fwd(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, i
                   int mode, uint32_t* maskbits, const float* tables, const wm_store_epilogue* ep, void* stream);
 int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* gx, int N, int H, int W, int Hm, int Wm,
                   int mode, const float* tables, void* stream);
+/* Autocast boundary: float16 / bfloat16 source planes staged as they are (widened in the row pass), and the adjoint's
+ * result stored in that type.  Rows on 16-byte boundaries only (WM_E_ALIGN otherwise), fused geometries only, no store
+ * epilogue; WM_DT_F32 forwards to the entry points above. */
+int wm_resize_fwd_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
+                        int mode, uint32_t* maskbits, const float* tables, void* stream);
+int wm_resize_bwd_typed(const float* gy, const uint32_t* maskbits, void* gx, int gx_dtype, int N, int H, int W, int Hm, int Wm,
+                        int mode, const float* tables, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Neighbours of the attack layer in the trainers' step (SURVEY 8f "next" rows).

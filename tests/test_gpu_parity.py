@@ -450,6 +450,52 @@ def test_gaussian_noise_reads_half_inputs_and_stores_half_gradients(dt):
         assert xa.grad.dtype == dt and torch.equal(xa.grad, xb.grad.to(dt)), type(layer).__name__
 
 
+@pytest.mark.parametrize("dt", (torch.bfloat16, torch.float16))
+def test_ring_layers_read_half_inputs_and_store_half_gradients(dt):
+    """The TMA-staged layers at the autocast boundary (models/IRNcrop_model.py:340): a float16 / bfloat16 image is
+    staged as it is and widened in the kernel (exact), the gradient is stored in that type - bit-identical to the
+    float32 path on the widened image, with torch's round-to-nearest-even cast of its gradient."""
+    import wmattack._lib as L
+    for shape, seed in (((2, 3, 80, 136), 41), ((1, 3, 37, 264), 42), ((1, 3, 130, 8), 43)):
+        x = (rnd(shape, seed) * 1.2 - 0.1).to(DEV).to(dt)
+        g = rnd(shape, seed + 100).to(DEV)
+        layers = [(wmattack.GaussianBlur(3), {}), (wmattack.GaussianBlur(7), {}), (wmattack.MiddleBlur(3), {}), (wmattack.MiddleBlur(5), {}),
+                  (wmattack.Resize(), {"resize_ratio": 0.75}), (wmattack.Resize(), {"resize_ratio": 1.5}),
+                  (wmattack.Resize(interpolation_method="bilinear"), {"resize_ratio": 0.5})]
+        for layer, kw in layers:
+            name = f"{type(layer).__name__} {kw} {shape}"
+            n0 = L.launch_count
+            xa = x.clone().requires_grad_(True)
+            ya = layer(xa, **kw)
+            ya.backward(g)
+            xb = x.float().requires_grad_(True)
+            yb = layer(xb, **kw)
+            yb.backward(g)
+            assert ya.dtype == torch.float32 and torch.equal(ya, yb), name
+            assert xa.grad.dtype == dt and torch.equal(xa.grad, xb.grad.to(dt)), name
+    # a frame of a half clip, read in place through its strides; a width off the 16-byte grid converts first
+    clip = rnd((2, 3, 3, 40, 64), 44).to(DEV).to(dt)
+    for layer in (wmattack.GaussianBlur(3), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5)):
+        assert torch.equal(layer(clip[:, :, 1]), layer(clip[:, :, 1].float()))
+    odd = rnd((1, 3, 33, 20), 45).to(DEV).to(dt)
+    for layer in (wmattack.GaussianBlur(3), wmattack.MiddleBlur(5)):
+        xa = odd.clone().requires_grad_(True)
+        layer(xa).sum().backward()
+        assert torch.equal(layer(odd), layer(odd.float())) and xa.grad.dtype == dt
+
+
+def test_typed_ring_entry_points_reject_unaligned_rows():
+    import ctypes as C
+    from wmattack import _lib
+    x = torch.zeros(1, 3, 16, 20, device=DEV, dtype=torch.float16)       # 40-byte rows
+    y = torch.zeros(1, 3, 16, 20, device=DEV)
+    taps = (C.c_float * 3)(0.25, 0.5, 0.25)
+    with pytest.raises(Exception, match="16-byte"):
+        _lib.call("wm_gaussblur_typed", x.data_ptr(), 1, 320, 20, y.data_ptr(), 0, 3, 16, 20, taps, 3, None)
+    with pytest.raises(Exception, match="16-byte"):
+        _lib.call("wm_median_fwd_typed", x.data_ptr(), 1, 320, 20, y.data_ptr(), None, 0, 3, 16, 20, 3, None)
+
+
 @pytest.mark.parametrize("k", (3, 5))
 def test_median_forward_bit_exact(k):
     for xn in ("x2028", "xs32"):

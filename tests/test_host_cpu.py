@@ -38,7 +38,7 @@ def test_library_exports_every_header_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"libwmattack.so does not export {n}"
     assert set(_lib.SIGNATURES) | set(_lib.HELPERS) == names - {"wm_version", "wm_last_error"}
-    assert lib.wm_version() == 3
+    assert lib.wm_version() == 4
     assert isinstance(lib.wm_last_error(), bytes)
 
 

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BL_THREADS) gaussblur_kernel(const BlurArgs a)
 constexpr int BT_TW = 128, BT_TH = WM_BT_TH, BT_HALO = 4, BT_BW = BT_TW + 2 * BT_HALO, BT_THREADS = 256, BT_ROWS = BT_TH / (BT_THREADS / 32);
 
 struct BlurTArgs {
-    float* y; int N, H, W, tiles_x, tiles_y; int64_t total;
+    void* y; int N, H, W, tiles_x, tiles_y; int64_t total;
     float taps[8];
     StoreEp ep;
     RaggedSrc rag;      // RAGGED instantiation only: the source planes (no tensor map for rows that are not 16-byte aligned)
@@ -99,13 +99,25 @@ struct BlurTArgs {
 
 template <int K> constexpr int bt_stages() { return K <= 5 ? WM_BT_STAGES : 2; }
 template <int K> constexpr int bt_stage_floats() { return ((BT_BW * (BT_TH + K - 1) + 31) / 32) * 32; }
+// stage stride in elements: whole 128-byte lines for 4-byte and for 2-byte elements
+// a TMA box must START on a 16-byte boundary of its row (measured: a 2-byte box at an 8-byte offset is an illegal
+// instruction), so the halo of a 2-byte tile is 8 elements
+template <int DT> constexpr int bt_halo() { return DT == WM_DT_F32 ? BT_HALO : 8; }
+template <int DT> constexpr int bt_bw() { return BT_TW + 2 * bt_halo<DT>(); }
+template <int K, int DT> constexpr int bt_stage_elems() { return DT == WM_DT_F32 ? bt_stage_floats<K>() : ((bt_bw<DT>() * (BT_TH + K - 1) + 63) / 64) * 64; }
 
 // RAGGED = rows not 16-byte aligned (W % 4 != 0): the ring is filled by cp.async instead of TMA (stage_box_cpasync) and
 // the output leaves by scalar stores; everything between is the same code.
-template <int K, bool RAGGED>
+// IDT / ODT = element type of the source planes (the ring holds them as they are; widened on the way to registers)
+// and of the result (float32 unless the caller wants the gradient in the autocast type).  Typed instantiations are
+// TMA-only and take no store epilogue.
+template <int K, bool RAGGED, int IDT = WM_DT_F32, int ODT = WM_DT_F32>
 __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BlurTArgs a) {
-    constexpr int R = K / 2, BH = BT_TH + 2 * R, S = bt_stages<K>(), STRIDE = bt_stage_floats<K>();
-    extern __shared__ __align__(128) float bufs[];
+    constexpr int R = K / 2, BH = BT_TH + 2 * R, S = bt_stages<K>(), STRIDE = bt_stage_elems<K, IDT>(), ES = tile_elem_size<IDT>();
+    constexpr bool PLAIN = IDT == WM_DT_F32 && ODT == WM_DT_F32;
+    constexpr int HALO = bt_halo<IDT>(), BW = bt_bw<IDT>();            // staged columns of a tile row (elements)
+    static_assert(PLAIN || !RAGGED, "typed planes need 16-byte rows");
+    extern __shared__ __align__(128) unsigned char bufs[];
     __shared__ uint64_t full[S];
     const int tid = threadIdx.x;
     if (!RAGGED && tid == 0) {
@@ -120,11 +132,11 @@ __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(c
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         if (RAGGED) {       // every thread; an empty group keeps the per-thread group count in step with the ring
-            if (t < a.total) stage_box_cpasync<BT_THREADS>(bufs + s * STRIDE, a.rag, n, a.H, a.W, tx * BT_TW - BT_HALO, ty * BT_TH - R, BT_BW, BH);
+            if (t < a.total) stage_box_cpasync<BT_THREADS>(reinterpret_cast<float*>(bufs) + s * STRIDE, a.rag, n, a.H, a.W, tx * BT_TW - HALO, ty * BT_TH - R, BW, BH);
             else asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
-            mbar_expect_tx(&full[s], BT_BW * BH * sizeof(float));
-            tma_load_3d(bufs + s * STRIDE, &tmap, tx * BT_TW - BT_HALO, ty * BT_TH - R, n, &full[s]);
+            mbar_expect_tx(&full[s], BW * BH * ES);
+            tma_load_3d(bufs + size_t(s) * STRIDE * ES, &tmap, tx * BT_TW - HALO, ty * BT_TH - R, n, &full[s]);
         }
     };
     if (RAGGED || tid == 0) {
@@ -146,14 +158,15 @@ __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(c
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * BT_TW + 4 * cg, gy0 = ty * BT_TH + strip * BT_ROWS;
-        const float* col = bufs + s * STRIDE + (strip * BT_ROWS) * BT_BW + BT_HALO + 4 * cg;
+        const unsigned char* stage = bufs + size_t(s) * STRIDE * ES;
+        const int col = (strip * BT_ROWS) * BW + HALO + 4 * cg;            // element index of this lane's first column
         auto hpass = [&](int row, float (&o)[4]) {
-            const float* p = col + row * BT_BW;
+            const int p = col + row * BW;
             float win[4 + 2 * R];
-            const float4 c = *reinterpret_cast<const float4*>(p);
+            const float4 c = tile_ld4<IDT>(stage, p);
             win[R] = c.x; win[R + 1] = c.y; win[R + 2] = c.z; win[R + 3] = c.w;
 #pragma unroll
-            for (int i = 0; i < R; ++i) { win[R - 1 - i] = p[-1 - i]; win[R + 4 + i] = p[4 + i]; }
+            for (int i = 0; i < R; ++i) { win[R - 1 - i] = tile_ld1<IDT>(stage, p - 1 - i); win[R + 4 + i] = tile_ld1<IDT>(stage, p + 4 + i); }
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 float acc = w[0] * win[c4];
@@ -165,7 +178,8 @@ __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(c
         float h[K][4];
 #pragma unroll
         for (int j = 0; j < K - 1; ++j) hpass(j, h[j]);
-        float* dst = a.y + (int64_t(n) * a.H + gy0) * a.W + gx;
+        const int64_t doff = (int64_t(n) * a.H + gy0) * a.W + gx;               // element offset of the lane's first output
+        float* dst = reinterpret_cast<float*>(a.y) + doff;                        // (float32 results)
         const bool col_ok = gx < a.W;
 #pragma unroll
         for (int r = 0; r < BT_ROWS; ++r) {
@@ -180,11 +194,11 @@ __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(c
                 op[c4] = acc;
             }
             if (col_ok && gy0 + r < a.H) {
-                if (a.ep.x)      // x at the output position is the centre of the staged tile row
-                    o = a.ep.from_input ? ep_apply4v(o, *reinterpret_cast<const float4*>(col + (r + R) * BT_BW), a.ep)
-                                        : ep_apply4(o, a.ep.x + (dst - a.y) + int64_t(r) * a.W, a.ep);
+                if (PLAIN && a.ep.x)      // x at the output position is the centre of the staged tile row
+                    o = a.ep.from_input ? ep_apply4v(o, tile_ld4<IDT>(stage, col + (r + R) * BW), a.ep)
+                                        : ep_apply4(o, a.ep.x + doff + int64_t(r) * a.W, a.ep);
                 if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
-                else stg128(dst + int64_t(r) * a.W, o);
+                else stg4_typed<ODT>(a.y, doff + int64_t(r) * a.W, o);
             }
         }
         __syncthreads();                      // every lane is done with stage s
@@ -195,30 +209,30 @@ __global__ void __launch_bounds__(BT_THREADS, WM_BT_MINB) gaussblur_tma_kernel(c
     }
 }
 
-template <int K, bool RAGGED>
-static int launch_blur_tma(const float* x, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W,
+template <int K, bool RAGGED, int IDT = WM_DT_F32, int ODT = WM_DT_F32>
+static int launch_blur_tma(const void* x, int64_t x_sp, int64_t x_sh, void* y, int N, int H, int W,
                            const float* taps_host, const wm_store_epilogue* ep, cudaStream_t st) {
     constexpr int R = K / 2, S = bt_stages<K>();
     CUtensorMap tm{};
     if (!RAGGED)
-        if (int rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, N, H, W, x_sp, x_sh, BT_BW, BT_TH + 2 * R)) {
+        if (int rc = tmap_planes(&tm, tile_tmap_type<IDT>(), tile_elem_size<IDT>(), x, N, H, W, x_sp, x_sh, bt_bw<IDT>(), BT_TH + 2 * R)) {
             set_error("wm_gaussblur: cuTensorMapEncodeTiled failed (%d)", rc);
             return WM_E_ARG;
         }
     BlurTArgs a{};
-    a.rag = RaggedSrc{x, x_sp, x_sh};
+    a.rag = RaggedSrc{reinterpret_cast<const float*>(x), x_sp, x_sh};
     a.y = y; a.N = N; a.H = H; a.W = W;
     a.tiles_x = (W + BT_TW - 1) / BT_TW; a.tiles_y = (H + BT_TH - 1) / BT_TH;
     a.total = int64_t(N) * a.tiles_x * a.tiles_y;
     for (int i = 0; i < K; ++i) a.taps[i] = taps_host[i];
     a.ep = make_store_ep(ep);
-    a.ep.from_input = a.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;
-    const size_t smem = sizeof(float) * size_t(S) * bt_stage_floats<K>();
-    cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    a.ep.from_input = a.ep.x == x && x_sh == W && x_sp == int64_t(H) * W;      // (a typed call takes no epilogue: ep.x is null)
+    const size_t smem = size_t(tile_elem_size<IDT>()) * size_t(S) * bt_stage_elems<K, IDT>();
+    cudaError_t e = cudaFuncSetAttribute(gaussblur_tma_kernel<K, RAGGED, IDT, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_gaussblur");
     const int64_t cap = int64_t(sm_count()) * WM_BT_MINB;
     const unsigned grid = (unsigned)(a.total < cap ? a.total : cap);
-    gaussblur_tma_kernel<K, RAGGED><<<grid, BT_THREADS, smem, st>>>(tm, a);
+    gaussblur_tma_kernel<K, RAGGED, IDT, ODT><<<grid, BT_THREADS, smem, st>>>(tm, a);
     WM_LAUNCH_CHECK("wm_gaussblur(tma)");
     return WM_OK;
 }
@@ -301,4 +315,33 @@ extern "C" int wm_gaussblur(const float* x, int64_t x_sp, int64_t x_sh, float* y
     gaussblur_kernel<<<dim3(tiles, N), BL_THREADS, smem, st>>>(a);
     WM_LAUNCH_CHECK("wm_gaussblur");
     return WM_OK;
+}
+
+// Typed planes (include/wm_attack.h): float16 / bfloat16 source read by the ring as it is, or the result stored in
+// that type.  Zero border, k = 3 / 5 / 7, rows on 16-byte boundaries - any other case is the caller's to convert.
+template <int IDT, int ODT>
+static int blur_typed(const void* x, int64_t x_sp, int64_t x_sh, void* y, int N, int H, int W, const float* taps, int k, cudaStream_t st) {
+    if (k == 3) return launch_blur_tma<3, false, IDT, ODT>(x, x_sp, x_sh, y, N, H, W, taps, nullptr, st);
+    if (k == 5) return launch_blur_tma<5, false, IDT, ODT>(x, x_sp, x_sh, y, N, H, W, taps, nullptr, st);
+    return launch_blur_tma<7, false, IDT, ODT>(x, x_sp, x_sh, y, N, H, W, taps, nullptr, st);
+}
+
+extern "C" int wm_gaussblur_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, void* y, int y_dtype, int N, int H, int W,
+                                  const float* taps_host, int k, void* stream) {
+    if (N == 0) return WM_OK;
+    WM_REQUIRE(x && y && taps_host, WM_E_NULL, "wm_gaussblur_typed: null pointer");
+    WM_REQUIRE(dtype_ok(x_dtype) && dtype_ok(y_dtype), WM_E_ARG, "wm_gaussblur_typed: unknown element type");
+    WM_REQUIRE(x_dtype == WM_DT_F32 || y_dtype == WM_DT_F32, WM_E_ARG, "wm_gaussblur_typed: one side is float32 (typed source OR typed result)");
+    WM_REQUIRE(k == 3 || k == 5 || k == 7, WM_E_ARG, "wm_gaussblur_typed: kernel size 3, 5 or 7 (got %d)", k);
+    WM_REQUIRE(N > 0 && H > 0 && W > 0, WM_E_SHAPE, "wm_gaussblur_typed: bad shape N=%d H=%d W=%d", N, H, W);
+    const size_t xs = dtype_size(x_dtype), ys = dtype_size(y_dtype);
+    WM_REQUIRE((W * ys) % (4 * ys) == 0 && W % 4 == 0 && aligned(y, 4 * ys) && tmap_ok(x, x_sp, x_sh, xs), WM_E_ALIGN,
+               "wm_gaussblur_typed: rows must start on 16-byte boundaries (W %% %d == 0, aligned planes); convert to float32 otherwise",
+               int(16 / xs));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == WM_DT_F16) return blur_typed<WM_DT_F16, WM_DT_F32>(x, x_sp, x_sh, y, N, H, W, taps_host, k, st);
+    if (x_dtype == WM_DT_BF16) return blur_typed<WM_DT_BF16, WM_DT_F32>(x, x_sp, x_sh, y, N, H, W, taps_host, k, st);
+    if (y_dtype == WM_DT_F16) return blur_typed<WM_DT_F32, WM_DT_F16>(x, x_sp, x_sh, y, N, H, W, taps_host, k, st);
+    if (y_dtype == WM_DT_BF16) return blur_typed<WM_DT_F32, WM_DT_BF16>(x, x_sp, x_sh, y, N, H, W, taps_host, k, st);
+    return blur_typed<WM_DT_F32, WM_DT_F32>(x, x_sp, x_sh, y, N, H, W, taps_host, k, st);
 }

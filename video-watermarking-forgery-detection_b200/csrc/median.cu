@@ -104,10 +104,21 @@ __device__ __forceinline__ float mid3_sum(float a, float b, float c, float lo, f
     return __int_as_float(s);
 }
 
+// stage stride in elements: whole 128-byte lines for 4-byte and for 2-byte elements
+// a TMA box must START on a 16-byte boundary of its row (a 2-byte box at an 8-byte offset is an illegal instruction),
+// so the halo of a 2-byte tile is 8 elements
+template <int DT> constexpr int mt_halo() { return DT == WM_DT_F32 ? MT_HALO : 8; }
+template <int DT> constexpr int mt_bw() { return MT_TW + 2 * mt_halo<DT>(); }
+template <int DT> constexpr int mt_stride() { return DT == WM_DT_F32 ? MT_STRIDE : ((mt_bw<DT>() * MT_BH + 63) / 64) * 64; }
+
 // RAGGED (rows not 16-byte aligned): ring fed by cp.async, scalar stores (tma.cuh: stage_box_cpasync).
-template <bool WANT_IDX, bool EP, bool RAGGED = false>
+// IDT: element type of the source planes (float16 / bfloat16 tiles are widened on the way to registers: exact, so the
+// median and its position are those of the float32 image); typed instantiations are TMA-only, no store epilogue.
+template <bool WANT_IDX, bool EP, bool RAGGED = false, int IDT = WM_DT_F32>
 __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MedTArgs a) {
-    extern __shared__ __align__(128) float bufs[];
+    static_assert(IDT == WM_DT_F32 || (!RAGGED && !EP), "typed planes: TMA rows, plain store");
+    constexpr int ES = tile_elem_size<IDT>(), SSTRIDE = mt_stride<IDT>(), HALO = mt_halo<IDT>(), BW = mt_bw<IDT>();
+    extern __shared__ __align__(128) unsigned char tiles[];
     __shared__ uint64_t full[MT_STAGES];
     const int tid = threadIdx.x;
     if (!RAGGED && tid == 0) {
@@ -122,11 +133,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         if (RAGGED) {       // every thread; an empty group keeps the per-thread group count in step with the ring
-            if (t < a.total) stage_box_cpasync<MT_THREADS>(bufs + s * MT_STRIDE, a.rag, n, a.H, a.W, tx * MT_TW - MT_HALO, ty * MT_TH - 1, MT_BW, MT_BH);
+            if (t < a.total) stage_box_cpasync<MT_THREADS>(reinterpret_cast<float*>(tiles) + s * MT_STRIDE, a.rag, n, a.H, a.W, tx * MT_TW - HALO, ty * MT_TH - 1, BW, MT_BH);
             else asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
-            mbar_expect_tx(&full[s], MT_BW * MT_BH * sizeof(float));
-            tma_load_3d(bufs + s * MT_STRIDE, &tmap, tx * MT_TW - MT_HALO, ty * MT_TH - 1, n, &full[s]);
+            mbar_expect_tx(&full[s], BW * MT_BH * ES);
+            tma_load_3d(tiles + size_t(s) * SSTRIDE * ES, &tmap, tx * MT_TW - HALO, ty * MT_TH - 1, n, &full[s]);
         }
     };
     if (RAGGED || tid == 0) {
@@ -145,13 +156,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) median3_tma_kernel(const __grid
         const int n = int(t / per_plane), rem = int(t - int64_t(n) * per_plane);
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int gx = tx * MT_TW + 4 * cg, gy0 = ty * MT_TH + strip * MT_ROWS;
-        const float* col = bufs + s * MT_STRIDE + (strip * MT_ROWS) * MT_BW + MT_HALO + 4 * cg;
+        const unsigned char* stage = tiles + size_t(s) * SSTRIDE * ES;
+        const int col = (strip * MT_ROWS) * BW + HALO + 4 * cg;           // element index of the lane's first column
         float raw[3][6], lo[3][4], mi[3][4], hi[3][4];
         auto load_row = [&](int row, int slot) {
-            const float* p = col + row * MT_BW;
-            const float4 c = *reinterpret_cast<const float4*>(p);
-            raw[slot][0] = p[-1]; raw[slot][1] = c.x; raw[slot][2] = c.y; raw[slot][3] = c.z; raw[slot][4] = c.w;
-            raw[slot][5] = p[4];
+            const int p = col + row * BW;
+            const float4 c = tile_ld4<IDT>(stage, p);
+            raw[slot][0] = tile_ld1<IDT>(stage, p - 1); raw[slot][1] = c.x; raw[slot][2] = c.y; raw[slot][3] = c.z; raw[slot][4] = c.w;
+            raw[slot][5] = tile_ld1<IDT>(stage, p + 4);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 const float u = raw[slot][c4], v = raw[slot][c4 + 1], w = raw[slot][c4 + 2];
@@ -246,6 +258,11 @@ __host__ __device__ __forceinline__ int m5_row0(int ty, int H) {
     return r < last ? r : last;
 }
 
+template <int DT> constexpr int m5_halo() { return DT == WM_DT_F32 ? M5_HALO : 8; }
+template <int DT> constexpr int m5_bw() { return M5_TW + 2 * m5_halo<DT>(); }
+template <int DT> constexpr int m5_stride() { return 2 * m5_bw<DT>() * M5_BH; }
+static_assert((m5_stride<WM_DT_F16>() * 2) % 128 == 0, "stage alignment of 2-byte tiles");
+
 struct Med5Args {
     float* y; uint8_t* idx; int N, H, W, tiles_x, tiles_y; int64_t total;
     int one, neg1;
@@ -254,19 +271,21 @@ struct Med5Args {
     RaggedSrc rag;      // RAGGED instantiations: source planes
 };
 
-// One 128 x 36 tile of one plane: `col` = the lane's window column in the staged box (row 0 = image row gy0 - 2).
-template <bool WANT_IDX, bool EP>
-__device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col, int64_t obase, int64_t ibase, int rows_ok) {
+// One 128 x 36 tile of one plane: `col` = element index of the lane's window column in the staged box `stage`
+// (row 0 = image row gy0 - 2; elements of type IDT).
+template <bool WANT_IDX, bool EP, int IDT>
+__device__ __forceinline__ void median5_tile(const Med5Args& a, const void* stage, int col, int64_t obase, int64_t ibase, int rows_ok) {
     // with the arg-median search on the ALU pipe too, every comparator moves its max to the FMA pipe; without it the
     // last network keeps plain FMNMX pairs (measured: 338 -> 261 us with, 231 -> 172 us without the plane at 64x3x504x512)
+    constexpr int BW = m5_bw<IDT>();
     const auto ce_s = ce_pick<true>::make(a.one, a.neg1);
     const auto ce_c = ce_pick<WANT_IDX>::make(a.one, a.neg1);
     float srt[6][5], raw[WANT_IDX ? 6 : 1][5];
     auto load_row = [&](int row, int slot) {
-        const float* p = col + row * M5_BW;
+        const int p = col + row * BW;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            srt[slot][k] = p[k];
+            srt[slot][k] = tile_ld1<IDT>(stage, p + k);
             if (WANT_IDX) raw[slot][k] = srt[slot][k];
         }
         sort5(srt[slot], ce_s);
@@ -316,7 +335,7 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col
                     pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
                 }
                 if (r + o < rows_ok) {
-                    yb[off] = EP ? ep_apply(med, a.ep.from_input ? col[(r + o + 2) * M5_BW + 2] : a.ep.x[obase + off], a.ep) : med;
+                    yb[off] = EP ? ep_apply(med, a.ep.from_input ? tile_ld1<IDT>(stage, col + (r + o + 2) * BW + 2) : a.ep.x[obase + off], a.ep) : med;
                     if (WANT_IDX) ib[ioff] = (uint8_t)pos;
                 }
                 off += a.W; ioff += int(a.idx_sh);
@@ -325,9 +344,11 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const float* col
     }
 }
 
-template <bool WANT_IDX, bool EP, bool RAGGED = false>
+template <bool WANT_IDX, bool EP, bool RAGGED = false, int IDT = WM_DT_F32>
 __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Med5Args a) {
-    extern __shared__ __align__(128) float bufs[];
+    static_assert(IDT == WM_DT_F32 || (!RAGGED && !EP), "typed planes: TMA rows, plain store");
+    constexpr int ES = tile_elem_size<IDT>(), HALO = m5_halo<IDT>(), BW = m5_bw<IDT>(), STRIDE = m5_stride<IDT>();
+    extern __shared__ __align__(128) unsigned char tiles[];
     __shared__ uint64_t full[M5_STAGES];
     const int tid = threadIdx.x;
     if (!RAGGED && tid == 0) {
@@ -346,11 +367,11 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const int n = 2 * m + hf;
-                    float* dst = bufs + s * M5_STRIDE + hf * (M5_BW * M5_BH);
+                    float* dst = reinterpret_cast<float*>(tiles) + s * STRIDE + hf * (BW * M5_BH);
                     if (n < a.N) {
                         const float* plane = a.rag.x + int64_t(n) * a.rag.sp;
-                        for (int i = threadIdx.x; i < M5_BW * M5_BH; i += M5_THREADS) {
-                            const int ly = i / M5_BW, lx = i - ly * M5_BW, gy = m5_row0(ty, a.H) - 2 + ly, gx = tx * M5_TW - M5_HALO + lx;
+                        for (int i = threadIdx.x; i < BW * M5_BH; i += M5_THREADS) {
+                            const int ly = i / BW, lx = i - ly * BW, gy = m5_row0(ty, a.H) - 2 + ly, gx = tx * M5_TW - HALO + lx;
                             const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
                             const float* src = ok ? plane + int64_t(gy) * a.rag.sh + gx : plane;
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + i)), "l"(src), "r"(ok ? 4 : 0) : "memory");
@@ -360,8 +381,8 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
-            mbar_expect_tx(&full[s], M5_STRIDE * sizeof(float));
-            tma_load_3d(bufs + s * M5_STRIDE, &tmap, tx * M5_TW - M5_HALO, m5_row0(ty, a.H) - 2, 2 * m, &full[s]);
+            mbar_expect_tx(&full[s], STRIDE * ES);
+            tma_load_3d(tiles + size_t(s) * STRIDE * ES, &tmap, tx * M5_TW - HALO, m5_row0(ty, a.H) - 2, 2 * m, &full[s]);
         }
     };
     if (RAGGED || tid == 0) {
@@ -381,10 +402,10 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int n = 2 * m + half, gx = tx * M5_TW + c, gy0 = m5_row0(ty, a.H);
         const int rows_tile = min(M5_ROWS, a.H - gy0);
-        const float* col = bufs + s * M5_STRIDE + half * (M5_BW * M5_BH) + M5_HALO - 2 + c;
+        const int col = half * (BW * M5_BH) + HALO - 2 + c;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
         const int rows_ok = (gx < a.W && n < a.N) ? rows_tile : 0;          // this lane stores output rows r < rows_ok
-        median5_tile<WANT_IDX, EP>(a, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
+        median5_tile<WANT_IDX, EP, IDT>(a, tiles + size_t(s) * STRIDE * ES, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
         __syncthreads();
         if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(M5_STAGES) * gridDim.x;
@@ -419,13 +440,14 @@ template <int K> struct MBCfg {
 };
 
 struct MedBArgs {
-    float* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
+    void* gx; int N, H, W, tiles_x, tiles_y; int64_t total;
     RaggedSrc rag;      // RAGGED: the cotangent planes (rows not 16-byte aligned); the idx plane always has a tensor map
 };
 
 // RAGGED: the (gy) ring is filled by cp.async, the idx ring still by TMA (the forward wrote the arg-median plane with
 // a 16-byte row stride), and gx leaves by scalar stores.
-template <int K, bool RAGGED = false>
+// ODT: element type of gx (float16 / bfloat16: the gradient leaves in the autocast type, rounded to nearest even).
+template <int K, bool RAGGED = false, int ODT = WM_DT_F32>
 __global__ void __launch_bounds__(MT_THREADS, MBCfg<K>::MINB) median_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                                        const __grid_constant__ CUtensorMap tm_i,
                                                                        const MedBArgs a) {
@@ -506,7 +528,8 @@ __global__ void __launch_bounds__(MT_THREADS, MBCfg<K>::MINB) median_bwd_tma_ker
 #pragma unroll
         for (int j = 0; j < K - 1; ++j) load_row(j, j);
         const bool col_ok = gx < a.W;
-        float* dst = a.gx + (int64_t(n) * a.H + gy0) * a.W + gx;
+        const int64_t doff = (int64_t(n) * a.H + gy0) * a.W + gx;
+        float* dst = reinterpret_cast<float*>(a.gx) + doff;
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             load_row(r + K - 1, (r + K - 1) % K);
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(MT_THREADS, MBCfg<K>::MINB) median_bwd_tma_ker
             }
             if (col_ok && gy0 + r < a.H) {
                 if (RAGGED) st4_ragged(dst + int64_t(r) * a.W, o, gx, a.W);
-                else stg128(dst + int64_t(r) * a.W, o);
+                else stg4_typed<ODT>(a.gx, doff + int64_t(r) * a.W, o);
             }
         }
         __syncthreads();
@@ -559,8 +582,8 @@ __global__ void __launch_bounds__(MT_THREADS, MBCfg<K>::MINB) median_bwd_tma_ker
     }
 }
 
-template <int K, bool RAGGED>
-static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, int64_t idx_sh, float* gx, int N, int H, int W, cudaStream_t st) {
+template <int K, bool RAGGED, int ODT = WM_DT_F32>
+static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, int64_t idx_sh, void* gx, int N, int H, int W, cudaStream_t st) {
     CUtensorMap tg{}, ti;
     int rc = RAGGED ? 0 : tmap_planes(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gy, N, H, W, int64_t(H) * W, W, MT_BW, MBCfg<K>::BH);
     if (!rc) rc = tmap_planes(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx, N, H, W, int64_t(H) * idx_sh, idx_sh, MB_IBW, MBCfg<K>::BH);
@@ -568,10 +591,10 @@ static int launch_median_bwd_tma(const float* gy, const uint8_t* idx, int64_t id
     MedBArgs ba{gx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MBCfg<K>::TH - 1) / MBCfg<K>::TH, 0, RaggedSrc{gy, int64_t(H) * W, W}};
     ba.total = int64_t(N) * ba.tiles_x * ba.tiles_y;
     const size_t smem = size_t(MBCfg<K>::STAGES) * (sizeof(float) * MBCfg<K>::GS + MBCfg<K>::IS);
-    cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(median_bwd_tma_kernel<K, RAGGED, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "wm_median_bwd");
     const int64_t cap = int64_t(sm_count()) * MBCfg<K>::MINB;
-    median_bwd_tma_kernel<K, RAGGED><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
+    median_bwd_tma_kernel<K, RAGGED, ODT><<<(unsigned)(ba.total < cap ? ba.total : cap), MT_THREADS, smem, st>>>(tg, ti, ba);
     WM_LAUNCH_CHECK("wm_median_bwd(tma)");
     return WM_OK;
 }
@@ -605,6 +628,29 @@ __global__ void __launch_bounds__(256) median_bwd_kernel(const float* __restrict
 }  // namespace wm
 
 using namespace wm;
+
+template <int IDT>
+static int launch_median3_typed(const CUtensorMap& tm, MedTArgs& ta, cudaStream_t st) {
+    const size_t smem = size_t(tile_elem_size<IDT>()) * MT_STAGES * mt_stride<IDT>();
+    auto kern = ta.idx ? median3_tma_kernel<true, false, false, IDT> : median3_tma_kernel<false, false, false, IDT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd_typed");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    kern<<<(unsigned)(ta.total < cap ? ta.total : cap), MT_THREADS, smem, st>>>(tm, ta);
+    WM_LAUNCH_CHECK("wm_median_fwd_typed(3x3)");
+    return WM_OK;
+}
+template <int IDT>
+static int launch_median5_typed(const CUtensorMap& tm, Med5Args& ta, cudaStream_t st) {
+    const size_t smem = size_t(tile_elem_size<IDT>()) * M5_STAGES * m5_stride<IDT>();
+    auto kern = ta.idx ? median5_tma_kernel<true, false, false, IDT> : median5_tma_kernel<false, false, false, IDT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "wm_median_fwd_typed");
+    const int64_t cap = int64_t(sm_count()) * 2;
+    kern<<<(unsigned)(ta.total < cap ? ta.total : cap), M5_THREADS, smem, st>>>(tm, ta);
+    WM_LAUNCH_CHECK("wm_median_fwd_typed(5x5)");
+    return WM_OK;
+}
 
 template <bool RAGGED>
 static int launch_median3(const CUtensorMap& tm, MedTArgs& ta, cudaStream_t st) {
@@ -683,4 +729,60 @@ extern "C" int wm_median_bwd(const float* gy, const uint8_t* idx, int64_t idx_sh
     else median_bwd_kernel<5><<<grid, 256, 0, st>>>(gy, idx, idx_sh, gx, N, H, W);
     WM_LAUNCH_CHECK("wm_median_bwd");
     return WM_OK;
+}
+
+// Typed planes (include/wm_attack.h): the forward reads float16 / bfloat16 source planes through the same TMA ring
+// (exact widening: value and position are those of the float32 image), the backward stores gx in that type.
+template <int IDT>
+static int median_fwd_typed(const void* x, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh, int N, int H, int W, int k,
+                            cudaStream_t st) {
+    CUtensorMap tm{};
+    if (int rc = tmap_planes(&tm, tile_tmap_type<IDT>(), tile_elem_size<IDT>(), x, N, H, W, x_sp, x_sh, k == 3 ? mt_bw<IDT>() : m5_bw<IDT>(),
+                             k == 3 ? MT_BH : M5_BH, k == 3 ? 1 : 2)) {
+        set_error("wm_median_fwd_typed: cuTensorMapEncodeTiled failed (%d)", rc);
+        return WM_E_ARG;
+    }
+    const StoreEp sep{nullptr, 0, 0, 0};
+    if (k == 3) {
+        MedTArgs ta{y, idx, N, H, W, (W + MT_TW - 1) / MT_TW, (H + MT_TH - 1) / MT_TH, 0, sep, 1, -1, idx_sh, RaggedSrc{nullptr, 0, 0}};
+        ta.total = int64_t(N) * ta.tiles_x * ta.tiles_y;
+        return launch_median3_typed<IDT>(tm, ta, st);
+    }
+    Med5Args ta{y, idx, N, H, W, (W + M5_TW - 1) / M5_TW, (H + M5_ROWS - 1) / M5_ROWS, 0, 1, -1, sep, idx_sh, RaggedSrc{nullptr, 0, 0}};
+    ta.total = int64_t((N + 1) / 2) * ta.tiles_x * ta.tiles_y;
+    return launch_median5_typed<IDT>(tm, ta, st);
+}
+
+extern "C" int wm_median_fwd_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, float* y, uint8_t* idx, int64_t idx_sh,
+                                   int N, int H, int W, int k, void* stream) {
+    if (N == 0) return WM_OK;
+    if (x_dtype == WM_DT_F32) return wm_median_fwd(reinterpret_cast<const float*>(x), x_sp, x_sh, y, idx, idx_sh, N, H, W, k, nullptr, stream);
+    WM_REQUIRE(x && y, WM_E_NULL, "wm_median_fwd_typed: null pointer");
+    WM_REQUIRE(x_dtype == WM_DT_F16 || x_dtype == WM_DT_BF16, WM_E_ARG, "wm_median_fwd_typed: unknown element type %d", x_dtype);
+    WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_fwd_typed: kernel size must be 3 or 5 (got %d)", k);
+    WM_REQUIRE(N > 0 && H > 0 && W > 0, WM_E_SHAPE, "wm_median_fwd_typed: bad shape N=%d H=%d W=%d", N, H, W);
+    WM_REQUIRE(!idx || idx_sh >= W, WM_E_ARG, "wm_median_fwd_typed: the arg-median plane's row stride (%lld) must be >= W", (long long)idx_sh);
+    WM_REQUIRE(W % 4 == 0 && aligned(y, 16) && tmap_ok(x, x_sp, x_sh, 2) && (k == 5 || !idx || (aligned(idx, 4) && idx_sh % 4 == 0)), WM_E_ALIGN,
+               "wm_median_fwd_typed: 2-byte planes need rows on 16-byte boundaries (W %% 8 == 0, aligned strides); convert to float32 otherwise");
+    cudaStream_t st = (cudaStream_t)stream;
+    return x_dtype == WM_DT_F16 ? median_fwd_typed<WM_DT_F16>(x, x_sp, x_sh, y, idx, idx_sh, N, H, W, k, st)
+                                : median_fwd_typed<WM_DT_BF16>(x, x_sp, x_sh, y, idx, idx_sh, N, H, W, k, st);
+}
+
+extern "C" int wm_median_bwd_typed(const float* gy, const uint8_t* idx, int64_t idx_sh, void* gx, int gx_dtype, int N, int H, int W, int k,
+                                   void* stream) {
+    if (N == 0) return WM_OK;
+    if (gx_dtype == WM_DT_F32) return wm_median_bwd(gy, idx, idx_sh, reinterpret_cast<float*>(gx), N, H, W, k, stream);
+    WM_REQUIRE(gy && idx && gx, WM_E_NULL, "wm_median_bwd_typed: null pointer");
+    WM_REQUIRE(gx_dtype == WM_DT_F16 || gx_dtype == WM_DT_BF16, WM_E_ARG, "wm_median_bwd_typed: unknown element type %d", gx_dtype);
+    WM_REQUIRE(k == 3 || k == 5, WM_E_ARG, "wm_median_bwd_typed: kernel size must be 3 or 5 (got %d)", k);
+    WM_REQUIRE(N > 0 && H > 0 && W > 0 && idx_sh >= W, WM_E_SHAPE, "wm_median_bwd_typed: bad shape / idx stride");
+    WM_REQUIRE(W % 4 == 0 && aligned(gx, 8) && tmap_ok(gy, int64_t(H) * W, W, 4) && tmap_ok(idx, int64_t(H) * idx_sh, idx_sh, 1), WM_E_ALIGN,
+               "wm_median_bwd_typed: needs W %% 4 == 0, aligned planes and the forward's 16-byte idx rows; use wm_median_bwd + a cast otherwise");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gx_dtype == WM_DT_F16)
+        return k == 3 ? launch_median_bwd_tma<3, false, WM_DT_F16>(gy, idx, idx_sh, gx, N, H, W, st)
+                      : launch_median_bwd_tma<5, false, WM_DT_F16>(gy, idx, idx_sh, gx, N, H, W, st);
+    return k == 3 ? launch_median_bwd_tma<3, false, WM_DT_BF16>(gy, idx, idx_sh, gx, N, H, W, st)
+                  : launch_median_bwd_tma<5, false, WM_DT_BF16>(gy, idx, idx_sh, gx, N, H, W, st);
 }

@@ -125,8 +125,8 @@ __global__ void rb_adj_tables_kernel(int n, int BT, const int* __restrict__ flo,
 // main kernel
 // ---------------------------------------------------------------------------------------------
 struct RBArgs {
-    const float* src; int64_t s_sp, s_sh;         // source planes (backward: dense cotangent)
-    float* dst;                                   // dense [N, H, W]
+    const void* src; int64_t s_sp, s_sh;          // source planes (backward: dense float32 cotangent); forward: element type DT
+    void* dst;                                    // dense [N, H, W]; backward: element type DT
     uint32_t* mask;                               // [N, H, tiles_x, 4] ballot words (see header)
     const int* lox; const float* wx;              // column-axis tables of this direction
     const int* loy; const float* wy;              // row-axis tables
@@ -143,18 +143,29 @@ template <int BT> struct RBGeom {
     static constexpr int BTV = BT + 2;                              // window shared by the 4 rows of a quad
     static constexpr size_t smem = sizeof(float) * (size_t(IHA) * IW + size_t(IHA) * RB_TW + size_t(NQ) * 4 * BTV) +
                                    sizeof(int) * NQ + sizeof(uint32_t) * IH * 12 + 128;
+    // staged columns of a 2-byte source tile: a TMA box must start on a 16-byte boundary of its row (a 2-byte box at an
+    // 8-byte offset is an illegal instruction), so its first column is rounded down to a multiple of 8 (up to 4 columns
+    // further left than the float32 tile) and its rows are whole 16-byte groups: a superset of the float32 tile's
+    // columns, so the proof of fit holds.  IW2 * 2 bytes <= IW * 4: the tile lives in the same region.
+    static constexpr int IW2 = ((IW + 4 + 7) / 8) * 8;
 };
 
 // DIR 0: forward (clamp, mask out)   DIR 1: adjoint (cotangent masked in shared memory, no clamp)
 // RAGGED: rows that are not 16-byte aligned (W % 4 != 0, odd strides) have no tensor map: the source tile is staged by
 // 4-byte cp.async from every thread (zero fill outside the plane) and the output leaves by scalar stores; the mask
 // words (rows of whole 16-byte groups for any W) stay on TMA.
-template <int BT, int DIR, bool RAGGED = false>
+// DT: float16 / bfloat16 at the boundary - the forward's SOURCE planes (staged as they are, widened in the H pass) or
+// the adjoint's RESULT (stored rounded to nearest even); TMA rows only, no store epilogue.
+template <int BT, int DIR, bool RAGGED = false, int DT = WM_DT_F32>
 __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_mask,
                                                                   const RBArgs a) {
     using G = RBGeom<BT>;
+    static_assert(DT == WM_DT_F32 || !RAGGED, "typed planes need 16-byte rows");
+    constexpr int IDT = DIR == 0 ? DT : WM_DT_F32, ODT = DIR == 1 ? DT : WM_DT_F32;
+    constexpr int IWS = IDT == WM_DT_F32 ? G::IW : G::IW2;           // row pitch of the staged source tile (elements)
+    constexpr bool PLAIN = DT == WM_DT_F32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* in = reinterpret_cast<float*>(smem_raw);                  // [IHA][IW] (TMA fills IH rows)
+    float* in = reinterpret_cast<float*>(smem_raw);                  // [IHA][IW] (TMA fills IH rows; IDT elements, pitch IWS)
     float* tmp = in + G::IHA * G::IW;                                // [IHA][TW]
     uint32_t* mb = reinterpret_cast<uint32_t*>(tmp + G::IHA * RB_TW);   // [IH][12] mask words of the staged rows (adjoint)
     float* wyq = reinterpret_cast<float*>(mb + G::IH * 12);          // [NQ][BTV][4] weights of a row quad on its shared window
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 
     // staged region: columns [xs, xs + IW) (xs may be negative: zero filled), rows [ys, ys + IH).
     // The 8-column margin absorbs the regularised window starts (flat band starts at a clamped border).
-    const int xs = (__ldg(a.lox + ox0) & ~3) - 8;
+    const int xs = (__ldg(a.lox + ox0) & (IDT == WM_DT_F32 ? ~3 : ~7)) - 8;
     const int ys = __ldg(a.loy + oy0);
     // rows the V pass can touch (rows past the image bottom are staged as zeros: their weights are 0)
     const int ih = min(max(__ldg(a.loy + oy0 + th - 1) + BT, __ldg(a.loy + oy0 + ((th - 1) & ~3)) + BT + 2) - ys, G::IH);
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         }
         if (lost) atomicExch(a.overflow, 1);
     }
-    const int hbase = min(max(hs - xs, 0), G::IW - BTW) & ~1;
+    const int hbase = min(max(hs - xs, 0), IWS - BTW) & ~1;
     if (a.overflow && hv0 && hbase != hs - xs) atomicExch(a.overflow, 1);
 
     // V pass tables: rows 4p .. 4p+3 share the BTV-row window that starts at the first row's band start
@@ -229,13 +240,13 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
     const int mt0 = max(xs, 0) >> 7;                                 // first 128-column mask tile of the staged region
     auto request = [&](int plane) {        // TMA: thread 0 only.  RAGGED: every thread (its share of the cp.async copies)
         if (RAGGED) {
-            stage_box_cpasync<RB_THREADS>(in, RaggedSrc{a.src, a.s_sp, a.s_sh}, plane, a.H, a.W, xs, ys, G::IW, G::IH);
+            stage_box_cpasync<RB_THREADS>(in, RaggedSrc{reinterpret_cast<const float*>(a.src), a.s_sp, a.s_sh}, plane, a.H, a.W, xs, ys, G::IW, G::IH);
             if (masked && tid == 0) {
                 mbar_expect_tx(&full, 12 * G::IH * sizeof(uint32_t));
                 tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
             }
         } else {
-            mbar_expect_tx(&full, G::IW * G::IH * sizeof(float) + (masked ? 12 * G::IH * sizeof(uint32_t) : 0));
+            mbar_expect_tx(&full, IWS * G::IH * tile_elem_size<IDT>() + (masked ? 12 * G::IH * sizeof(uint32_t) : 0));
             tma_load_3d(in, &tmap, xs, ys, plane, &full);
             if (masked) tma_load_3d(mb, &tmap_mask, 4 * mt0, ys, plane, &full);
         }
@@ -267,22 +278,22 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
 
         // ---- H pass: tmp[r][oa .. oa+1] = sum_t {w0, w1}[t] * in[r][hbase + t] ----------------------
         {
-            const float* p = in + hr * G::IW + hbase;
+            int p = hr * IWS + hbase;                      // element index in the staged tile
             float* q = tmp + hr * RB_TW + oa;
             for (int r = hr; r < ih; r += 8) {            // rows r and r + 4 (rows past ih land in spare rows)
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const float* pk = p + 4 * k * G::IW;
+                    const int pk = p + 4 * k * IWS;
                     float2 a0 = make_float2(0.f, 0.f), a1 = a0;        // (even taps, odd taps) partial sums
 #pragma unroll
                     for (int t = 0; t < BTW; t += 2) {
-                        const float2 v = *reinterpret_cast<const float2*>(pk + t);
+                        const float2 v = tile_ld2<IDT>(in, pk + t);
                         a0 = ffma2(make_float2(w0[t], w0[t + 1]), v, a0);
                         a1 = ffma2(make_float2(w1[t], w1[t + 1]), v, a1);
                     }
                     *reinterpret_cast<float2*>(q + 4 * k * RB_TW) = make_float2(a0.x + a0.y, a1.x + a1.y);
                 }
-                p += 8 * G::IW; q += 8 * RB_TW;
+                p += 8 * IWS; q += 8 * RB_TW;
             }
         }
         __syncthreads();
@@ -294,11 +305,12 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
             const bool okc = 4 * lane < tw;
             const bool want_mask = DIR == 0 && a.mask != nullptr;
             // running pointers of this warp's row quads (q = warp, warp + 8, ...)
-            float* drow = a.dst + (int64_t(n) * a.H + oy0 + 4 * warp) * a.W + ox0 + 4 * lane;
+            int64_t doff = (int64_t(n) * a.H + oy0 + 4 * warp) * a.W + ox0 + 4 * lane;     // element offset of this lane's first output
+            float* const dst32 = reinterpret_cast<float*>(a.dst);
             uint32_t* mrow = a.mask + ((int64_t(n) * a.H + oy0 + 4 * warp) * a.tiles_x + tx) * 4 + (lane & 3);
             const int drow_step = 4 * (RB_THREADS / 32) * a.W, mrow_step = 4 * (RB_THREADS / 32) * a.tiles_x * 4;
             const int mrow_k = a.tiles_x * 4;
-            for (int qd = warp; 4 * qd < th; qd += RB_THREADS / 32, drow += drow_step, mrow += mrow_step) {
+            for (int qd = warp; 4 * qd < th; qd += RB_THREADS / 32, doff += drow_step, mrow += mrow_step) {
                 const float4* wq = reinterpret_cast<const float4*>(wyq + qd * BTV * 4);     // [t] -> weights of the 4 rows
                 const float* p = tmp + yloq[qd] * RB_TW + 4 * lane;
                 float2 lo[4], hi[4];                                // columns (0,1), (2,3) of the 4 rows
@@ -307,10 +319,10 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                 // store epilogue: x at the output positions is requested now (L2 hits: the tile was just
                 // staged from the same lines) so that its latency hides under the window loop
                 float4 xe[4];
-                if (!RAGGED && DIR == 0 && a.ep.x) {
+                if (PLAIN && !RAGGED && DIR == 0 && a.ep.x) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        xe[k] = (okc && 4 * qd + k < th) ? ldg128_nc(a.ep.x + (drow - a.dst) + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xe[k] = (okc && 4 * qd + k < th) ? ldg128_nc(a.ep.x + doff + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int t = 0; t < BTV; ++t) {
@@ -330,8 +342,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
                         const float4 c = clamp01_nan4(acc);
-                        if (RAGGED) { if (okc && okr) st4_ragged(drow + k * a.W, c, ox0 + 4 * lane, a.W); }
-                        else if (okc && okr) stg128(drow + k * a.W, a.ep.x ? ep_apply4v(c, xe[k], a.ep) : c);
+                        if (RAGGED) { if (okc && okr) st4_ragged(dst32 + doff + k * a.W, c, ox0 + 4 * lane, a.W); }
+                        else if (okc && okr) stg128(dst32 + doff + k * a.W, (PLAIN && a.ep.x) ? ep_apply4v(c, xe[k], a.ep) : c);
                         if (want_mask) {   // 0 <= v <= 1  <=>  saturate(v) == v  (false for NaN)
                             const unsigned b0 = __ballot_sync(0xffffffffu, okc && c.x == acc.x);
                             const unsigned b1 = __ballot_sync(0xffffffffu, okc && c.y == acc.y);
@@ -342,8 +354,8 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                             if (lane < 4 && okr) mrow[k * mrow_k] = w;
                         }
                     } else if (okc && okr) {
-                        if (RAGGED) st4_ragged(drow + k * a.W, acc, ox0 + 4 * lane, a.W);
-                        else stg128(drow + k * a.W, acc);
+                        if (RAGGED) st4_ragged(dst32 + doff + k * a.W, acc, ox0 + 4 * lane, a.W);
+                        else stg4_typed<ODT>(a.dst, doff + k * a.W, acc);
                     }
                 }
             }
@@ -428,16 +440,16 @@ static inline int rb_band(int H, int W, int Hm, int Wm) {
 
 static inline RBAxis rb_axis(int n, int nm) { return RBAxis{n, nm, (float)n / (float)nm, (float)nm / (float)n}; }
 
-template <int BT, int DIR, bool RAGGED>
+template <int BT, int DIR, bool RAGGED, int DT = WM_DT_F32>
 static int rb_launch(const RBArgs& a, const CUtensorMap& tm, const CUtensorMap& tmm, cudaStream_t st, const char* who) {
     const size_t smem = RBGeom<BT>::smem;
-    cudaError_t e = cudaFuncSetAttribute(rb_banded_kernel<BT, DIR, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rb_banded_kernel<BT, DIR, RAGGED, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
     // persistent over planes: ~2 CTAs per SM in total, each tile position walks its share of planes
     const int pos = a.tiles_x * a.tiles_y;
     int gz = (2 * sm_count()) / pos;
     gz = gz < 1 ? 1 : (gz > a.N ? a.N : gz);
-    rb_banded_kernel<BT, DIR, RAGGED><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, tmm, a);
+    rb_banded_kernel<BT, DIR, RAGGED, DT><<<dim3(a.tiles_x, a.tiles_y, gz), RB_THREADS, smem, st>>>(tm, tmm, a);
     WM_LAUNCH_CHECK(who);
     return WM_OK;
 }
@@ -486,8 +498,9 @@ extern "C" int wm_resize_tables(float* tables, int H, int W, int Hm, int Wm, int
     return WM_OK;
 }
 
-static int rb_run(int dir, bool ragged, const float* src, int64_t s_sp, int64_t s_sh, float* dst, uint32_t* mask, const float* tables,
-                  int N, int H, int W, int Hm, int Wm, const wm_store_epilogue* ep, void* stream, const char* who) {
+// dt: element type of the forward's source planes / of the adjoint's result (WM_DT_F32: the plain kernels)
+static int rb_run(int dir, bool ragged, const void* src, int64_t s_sp, int64_t s_sh, void* dst, uint32_t* mask, const float* tables,
+                  int N, int H, int W, int Hm, int Wm, const wm_store_epilogue* ep, void* stream, const char* who, int dt = WM_DT_F32) {
     const int BT = rb_band(H, W, Hm, Wm);
     const float* fx = tables; const float* fy = fx + rb_axis_words(W, BT);
     const float* bx = fy + rb_axis_words(H, BT); const float* by = bx + rb_axis_words(W, BT);
@@ -502,11 +515,14 @@ static int rb_run(int dir, bool ragged, const float* src, int64_t s_sp, int64_t 
     CUtensorMap tm{}, tmm{};
     int rc = 0;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool typed_src = dir == 0 && dt != WM_DT_F32;
 #define RB_CASE(B)                                                                                                  \
     case B:                                                                                                         \
         if (!ragged)                                                                                                \
-            rc = tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh, RBGeom<B>::IW,      \
-                             RBGeom<B>::IH);                                                                        \
+            rc = typed_src ? tmap_planes(&tm, dt == WM_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, \
+                                         src, N, H, W, s_sp, s_sh, RBGeom<B>::IW2, RBGeom<B>::IH)                  \
+                           : tmap_planes(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, N, H, W, s_sp, s_sh, RBGeom<B>::IW, \
+                                         RBGeom<B>::IH);                                                            \
         if (!rc && dir == 1 && mask)                                                                                \
             rc = tmap_planes(&tmm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, mask, N, H, 4 * a.tiles_x,                    \
                              int64_t(H) * 4 * a.tiles_x, 4 * a.tiles_x, 12, RBGeom<B>::IH);                         \
@@ -515,6 +531,8 @@ static int rb_run(int dir, bool ragged, const float* src, int64_t s_sp, int64_t 
             return WM_E_ARG;                                                                                        \
         }                                                                                                           \
         if (ragged) return dir == 0 ? rb_launch<B, 0, true>(a, tm, tmm, st, who) : rb_launch<B, 1, true>(a, tm, tmm, st, who); \
+        if (dt == WM_DT_F16) return dir == 0 ? rb_launch<B, 0, false, WM_DT_F16>(a, tm, tmm, st, who) : rb_launch<B, 1, false, WM_DT_F16>(a, tm, tmm, st, who); \
+        if (dt == WM_DT_BF16) return dir == 0 ? rb_launch<B, 0, false, WM_DT_BF16>(a, tm, tmm, st, who) : rb_launch<B, 1, false, WM_DT_BF16>(a, tm, tmm, st, who); \
         return dir == 0 ? rb_launch<B, 0, false>(a, tm, tmm, st, who) : rb_launch<B, 1, false>(a, tm, tmm, st, who);
     switch (BT) {
         RB_CASE(8)
@@ -556,4 +574,35 @@ extern "C" int wm_resize_bwd(const float* gy, const uint32_t* maskbits, float* g
     WM_REQUIRE(!maskbits || aligned(maskbits, 16), WM_E_ALIGN, "wm_resize_bwd: maskbits must be 16-byte aligned");
     const bool ragged = !(W % 4 == 0 && aligned(gy, 16) && aligned(gx, 16));
     return rb_run(1, ragged, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, nullptr, stream, "wm_resize_bwd");
+}
+
+// Typed planes (include/wm_attack.h): float16 / bfloat16 source planes staged as they are (forward), or the adjoint's
+// result stored in that type.  Rows on 16-byte boundaries only; no store epilogue.
+extern "C" int wm_resize_fwd_typed(const void* x, int x_dtype, int64_t x_sp, int64_t x_sh, float* y, int N, int H, int W, int Hm, int Wm,
+                                   int mode, uint32_t* maskbits, const float* tables, void* stream) {
+    if (N == 0) return WM_OK;
+    if (x_dtype == WM_DT_F32)
+        return wm_resize_fwd(reinterpret_cast<const float*>(x), x_sp, x_sh, y, N, H, W, Hm, Wm, mode, maskbits, tables, nullptr, stream);
+    WM_REQUIRE(x && y && tables, WM_E_NULL, "wm_resize_fwd_typed: null pointer");
+    WM_REQUIRE(x_dtype == WM_DT_F16 || x_dtype == WM_DT_BF16, WM_E_ARG, "wm_resize_fwd_typed: unknown element type %d", x_dtype);
+    WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_fwd_typed: mode must be 0 (bilinear) or 1 (bicubic)");
+    WM_REQUIRE(rb_ok(H, W, Hm, Wm, N), WM_E_SHAPE, "wm_resize_fwd_typed: geometry H=%d W=%d mid=%dx%d N=%d is outside the fused range", H, W, Hm, Wm, N);
+    WM_REQUIRE(!maskbits || aligned(maskbits, 16), WM_E_ALIGN, "wm_resize_fwd_typed: maskbits must be 16-byte aligned");
+    WM_REQUIRE(W % 4 == 0 && tmap_ok(x, x_sp, x_sh, 2) && aligned(y, 16), WM_E_ALIGN,
+               "wm_resize_fwd_typed: 2-byte planes need rows on 16-byte boundaries (W %% 8 == 0, aligned strides); convert to float32 otherwise");
+    return rb_run(0, false, x, x_sp, x_sh, y, maskbits, tables, N, H, W, Hm, Wm, nullptr, stream, "wm_resize_fwd_typed", x_dtype);
+}
+
+extern "C" int wm_resize_bwd_typed(const float* gy, const uint32_t* maskbits, void* gx, int gx_dtype, int N, int H, int W, int Hm, int Wm,
+                                   int mode, const float* tables, void* stream) {
+    if (N == 0) return WM_OK;
+    if (gx_dtype == WM_DT_F32) return wm_resize_bwd(gy, maskbits, reinterpret_cast<float*>(gx), N, H, W, Hm, Wm, mode, tables, stream);
+    WM_REQUIRE(gy && gx && tables, WM_E_NULL, "wm_resize_bwd_typed: null pointer");
+    WM_REQUIRE(gx_dtype == WM_DT_F16 || gx_dtype == WM_DT_BF16, WM_E_ARG, "wm_resize_bwd_typed: unknown element type %d", gx_dtype);
+    WM_REQUIRE(mode == 0 || mode == 1, WM_E_ARG, "wm_resize_bwd_typed: mode must be 0 (bilinear) or 1 (bicubic)");
+    WM_REQUIRE(rb_ok(H, W, Hm, Wm, N), WM_E_SHAPE, "wm_resize_bwd_typed: geometry H=%d W=%d mid=%dx%d N=%d is outside the fused range", H, W, Hm, Wm, N);
+    WM_REQUIRE(!maskbits || aligned(maskbits, 16), WM_E_ALIGN, "wm_resize_bwd_typed: maskbits must be 16-byte aligned");
+    WM_REQUIRE(W % 4 == 0 && aligned(gy, 16) && aligned(gx, 8), WM_E_ALIGN, "wm_resize_bwd_typed: needs W %% 4 == 0 and aligned planes");
+    return rb_run(1, false, gy, int64_t(H) * W, W, gx, const_cast<uint32_t*>(maskbits), tables, N, H, W, Hm, Wm, nullptr, stream,
+                  "wm_resize_bwd_typed", gx_dtype);
 }

@@ -131,4 +131,49 @@ __device__ __forceinline__ void stg128(float* p, const float4 v) {
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- shared-memory tiles staged in the caller's element type (DT = WM_DT_*, compile time) ---------------------
+// A TMA box of float16 / bfloat16 rows lands as it is; the stencil widens on the way to registers (exact), so an
+// autocast trainer's half tensors need no .float() pass.  i = element index in the tile.
+template <int DT> __device__ __forceinline__ float tile_widen(uint32_t h16) {
+    if (DT == WM_DT_BF16) return __uint_as_float(h16 << 16);
+    float f; asm("{\n .reg .b16 t;\n cvt.u16.u32 t, %1;\n cvt.f32.f16 %0, t;\n}" : "=f"(f) : "r"(h16)); return f;
+}
+template <int DT> __device__ __forceinline__ float2 tile_widen2(uint32_t w) {
+    if (DT == WM_DT_BF16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    float lo, hi;
+    asm("{\n .reg .b16 l, h;\n mov.b32 {l, h}, %2;\n cvt.f32.f16 %0, l;\n cvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(w));
+    return make_float2(lo, hi);
+}
+template <int DT> __device__ __forceinline__ float tile_ld1(const void* tile, int i) {
+    if (DT == WM_DT_F32) return reinterpret_cast<const float*>(tile)[i];
+    return tile_widen<DT>(reinterpret_cast<const uint16_t*>(tile)[i]);
+}
+template <int DT> __device__ __forceinline__ float2 tile_ld2(const void* tile, int i) {       // i % 2 == 0
+    if (DT == WM_DT_F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tile) + i);
+    return tile_widen2<DT>(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(tile) + i));
+}
+template <int DT> __device__ __forceinline__ float4 tile_ld4(const void* tile, int i) {       // i % 4 == 0
+    if (DT == WM_DT_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tile) + i);
+    const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(tile) + i);
+    const float2 a = tile_widen2<DT>(w.x), b = tile_widen2<DT>(w.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <int DT> constexpr int tile_elem_size() { return DT == WM_DT_F32 ? 4 : 2; }
+template <int DT> constexpr CUtensorMapDataType tile_tmap_type() {
+    return DT == WM_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : DT == WM_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+// 4 values to element offset `off` (off % 4 == 0) of a float32 / float16 / bfloat16 array, round-to-nearest-even
+template <int DT> __device__ __forceinline__ void stg4_typed(void* base, int64_t off, const float4 v) {
+    if (DT == WM_DT_F32) { stg128(reinterpret_cast<float*>(base) + off, v); return; }
+    uint32_t lo, hi;
+    if (DT == WM_DT_BF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    }
+    asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(reinterpret_cast<uint16_t*>(base) + off), "r"(lo), "r"(hi) : "memory");
+}
+
 }  // namespace wm

@@ -62,6 +62,9 @@ SIGNATURES = {
     "wm_gaussblur": [c_f32p, i64, i64, c_f32p, i32, i32, i32, C.POINTER(f32), i32, i32, i32, epp, vp],
     "wm_median_fwd": [c_f32p, i64, i64, c_f32p, c_u8p, i64, i32, i32, i32, i32, epp, vp],
     "wm_median_bwd": [c_f32p, c_u8p, i64, c_f32p, i32, i32, i32, i32, vp],
+    "wm_gaussblur_typed": [vp, i32, i64, i64, vp, i32, i32, i32, i32, C.POINTER(f32), i32, vp],
+    "wm_median_fwd_typed": [vp, i32, i64, i64, c_f32p, c_u8p, i64, i32, i32, i32, i32, vp],
+    "wm_median_bwd_typed": [c_f32p, c_u8p, i64, vp, i32, i32, i32, i32, i32, vp],
     "wm_gaussnoise_fwd": [vp, i32, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, epp, vp],
     "wm_gaussnoise_bwd": [c_f32p, c_f32p, c_f32p, i64, f32, f32, i32, u64, u64, c_f32p, vp],
     "wm_gaussnoise_fwd_mask": [vp, i32, c_f32p, vp, i64, f32, f32, u64, u64, c_f32p, vp],
@@ -90,6 +93,8 @@ SIGNATURES = {
     "wm_resize_tables": [c_f32p, i32, i32, i32, i32, i32, vp],
     "wm_resize_fwd": [c_f32p, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, epp, vp],
     "wm_resize_bwd": [c_f32p, vp, c_f32p, i32, i32, i32, i32, i32, i32, c_f32p, vp],
+    "wm_resize_fwd_typed": [vp, i32, i64, i64, c_f32p, i32, i32, i32, i32, i32, i32, vp, c_f32p, vp],
+    "wm_resize_bwd_typed": [c_f32p, vp, vp, i32, i32, i32, i32, i32, i32, i32, c_f32p, vp],
     "wm_cropresize_fwd": [c_f32p, i64, i64, i32, i32, i32, i32, i32, i32, c_f32p, i32, i32, i32, i32, vp, vp],
     "wm_cropresize_bwd": [c_f32p, c_f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
     "wm_jpegcodec": [vp, i64, i64, i64, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],

@@ -91,6 +91,21 @@ def _planes(t: torch.Tensor, who: str) -> Tuple[torch.Tensor, int, int]:
     return t, sc, sh
 
 
+def _typed_planes(t: torch.Tensor, who: str) -> Tuple[torch.Tensor, int, int, int]:
+    """(tensor, plane stride, row stride, WM_DT_* code).  A float16 / bfloat16 image whose rows sit on 16-byte boundaries
+    (W % 8 == 0, strides multiples of 8 elements) is handed to the *_typed entry points AS IT IS - the TMA ring stages the
+    2-byte planes and the kernel widens them - instead of paying a .float() pass; anything else is float32 planes."""
+    _check_cuda(t, who)
+    if t.dim() == 4 and t.dtype in (torch.float16, torch.bfloat16):
+        b, c, h, w = t.shape
+        sb, sc, sh, sw = t.stride()
+        if (sw == 1 and w % 8 == 0 and sh % 8 == 0 and sc % 8 == 0 and sh >= w and sc >= 0 and (b == 1 or sb == c * sc)
+                and t.data_ptr() % 16 == 0):
+            return t, sc, sh, _DT_CODE[t.dtype]
+    t, sp, sh = _planes(t, who)
+    return t, sp, sh, DT_F32
+
+
 def _flat(t: torch.Tensor, who: str) -> torch.Tensor:
     _check_cuda(t, who)
     return _f32(t).contiguous()
@@ -397,19 +412,29 @@ def _taps_array(taps: Sequence[float]):
 class _BlurFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, taps, border):
-        x, sp, sh = _planes(x, "gaussian blur")
+        xdtype = x.dtype
+        ring = border == 0 and len(taps) in (3, 5, 7)         # the TMA ring kernels: the only ones with typed planes
+        x, sp, sh, dt = _typed_planes(x, "gaussian blur") if ring else (*_planes(x, "gaussian blur"), DT_F32)
         b, c, h, w = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         arr = _taps_array(taps)
-        _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, y.data_ptr(), b * c, h, w, arr, len(taps), border, 0, None, _stream())
-        ctx.meta = (tuple(taps), border)
+        if dt != DT_F32:       # float16 / bfloat16 planes staged as they are
+            _lib.call("wm_gaussblur_typed", x.data_ptr(), dt, sp, sh, y.data_ptr(), DT_F32, b * c, h, w, arr, len(taps), _stream())
+        else:
+            _lib.call("wm_gaussblur", x.data_ptr(), sp, sh, y.data_ptr(), b * c, h, w, arr, len(taps), border, 0, None, _stream())
+        ctx.meta = (tuple(taps), border, xdtype if ring else torch.float32)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        taps, border = ctx.meta
+        taps, border, xdtype = ctx.meta
         gy, sp, sh = _planes(gy, "gaussian blur backward")
         b, c, h, w = gy.shape
+        if xdtype in (torch.float16, torch.bfloat16) and w % 4 == 0 and sh % 4 == 0 and sp % 4 == 0 and gy.data_ptr() % 16 == 0:
+            gx = torch.empty((b, c, h, w), device=gy.device, dtype=xdtype)      # the gradient leaves in the image's type
+            _lib.call("wm_gaussblur_typed", gy.data_ptr(), DT_F32, sp, sh, gx.data_ptr(), _DT_CODE[xdtype], b * c, h, w,
+                      _taps_array(taps), len(taps), _stream())
+            return gx, None, None
         gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
         _lib.call("wm_gaussblur", gy.data_ptr(), sp, sh, gx.data_ptr(), b * c, h, w, _taps_array(taps), len(taps),
                   border, 1, None, _stream())
@@ -433,12 +458,17 @@ class _MedianFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k):
         need_idx = bool(ctx.needs_input_grad[0])
-        x, sp, sh = _planes(x, "median blur")
+        ctx.xdtype = x.dtype
+        x, sp, sh, dt = _typed_planes(x, "median blur")
         b, c, h, w = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         idx = _idx_plane(b, c, h, w, x.device) if need_idx else None
-        _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), idx.shape[-1] if need_idx else 0,
-                  b * c, h, w, k, None, _stream())
+        if dt != DT_F32:       # float16 / bfloat16 planes staged as they are (exact widening: same median, same position)
+            _lib.call("wm_median_fwd_typed", x.data_ptr(), dt, sp, sh, y.data_ptr(), _ptr(idx), idx.shape[-1] if need_idx else 0,
+                      b * c, h, w, k, _stream())
+        else:
+            _lib.call("wm_median_fwd", x.data_ptr(), sp, sh, y.data_ptr(), _ptr(idx), idx.shape[-1] if need_idx else 0,
+                      b * c, h, w, k, None, _stream())
         ctx.k = k
         if need_idx:
             ctx.save_for_backward(idx)
@@ -449,6 +479,11 @@ class _MedianFn(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         gy = _flat(gy, "median blur backward")
         b, c, h, w = gy.shape
+        if ctx.xdtype in (torch.float16, torch.bfloat16) and w % 4 == 0:
+            gx = torch.empty((b, c, h, w), device=gy.device, dtype=ctx.xdtype)  # the gradient leaves in the image's type
+            _lib.call("wm_median_bwd_typed", gy.data_ptr(), idx.data_ptr(), idx.shape[-1], gx.data_ptr(), _DT_CODE[ctx.xdtype],
+                      b * c, h, w, ctx.k, _stream())
+            return gx, None
         gx = torch.empty_like(gy)
         _lib.call("wm_median_bwd", gy.data_ptr(), idx.data_ptr(), idx.shape[-1], gx.data_ptr(), b * c, h, w, ctx.k, _stream())
         return gx, None
@@ -812,15 +847,21 @@ class _ResizeFusedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mid_hw, mode):
         need_grad = bool(ctx.needs_input_grad[0])
-        x, sp, sh = _planes(x, "resize")
+        xdtype = x.dtype
+        x, sp, sh, dt = _typed_planes(x, "resize")
         b, c, h, w = x.shape
         n = b * c
         tables = _resize_tables(x.device, h, w, mid_hw, mode)       # proven by resize_roundtrip before dispatching here
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         mask = torch.empty((n, h, 4 * ((w + 127) // 128)), device=x.device, dtype=torch.int32) if need_grad else None
-        _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
-                  _ptr(mask), tables.data_ptr(), None, _stream())
+        if dt != DT_F32:       # float16 / bfloat16 planes staged as they are
+            _lib.call("wm_resize_fwd_typed", x.data_ptr(), dt, sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
+                      _ptr(mask), tables.data_ptr(), _stream())
+        else:
+            _lib.call("wm_resize_fwd", x.data_ptr(), sp, sh, y.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
+                      _ptr(mask), tables.data_ptr(), None, _stream())
         ctx.meta = (tuple(mid_hw), mode, (b, c, h, w))
+        ctx.xdtype = xdtype
         if need_grad:
             ctx.save_for_backward(mask, tables)
         return y
@@ -831,6 +872,11 @@ class _ResizeFusedFn(torch.autograd.Function):
         mask, tables = ctx.saved_tensors
         gy = _flat(gy, "resize backward")
         n = b * c
+        if ctx.xdtype in (torch.float16, torch.bfloat16) and w % 4 == 0:
+            gx = torch.empty((b, c, h, w), device=gy.device, dtype=ctx.xdtype)  # the gradient leaves in the image's type
+            _lib.call("wm_resize_bwd_typed", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), _DT_CODE[ctx.xdtype], n, h, w,
+                      mid_hw[0], mid_hw[1], mode, tables.data_ptr(), _stream())
+            return gx, None, None
         gx = torch.empty((b, c, h, w), device=gy.device, dtype=torch.float32)
         _lib.call("wm_resize_bwd", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), n, h, w, mid_hw[0], mid_hw[1], mode,
                   tables.data_ptr(), _stream())
