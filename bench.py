@@ -252,6 +252,7 @@ def ours(args, rank, world, dev):
     e2e_u8 = run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=True)
     extras = {}
     for name, fn in (("config2_natural", lambda: config2_natural(args, dj, comb, g, world, dev, px_step)),
+                     ("config2_autocast", lambda: config2_autocast(args, dj, comb, g, world, dev, px_step)),
                      ("config1", lambda: config1_gpu(dev)), ("config3", lambda: config3(world, dev)),
                      ("config5", lambda: config5(rank, world, dev)),
                      ("train_step", lambda: train_step_leg(args, rank, world, dev))):
@@ -449,6 +450,22 @@ def config2_natural(args, dj, comb, g, world, dev, px_step):
     return {"workload": "the config-2 step on smooth frames quantised to k/255 (two 9x9 box blurs of uniform noise)",
             "ms_per_step": round(ms, 4), "value": round(world * px_step / ms / 1e3, 1), "unit": "Mpix/s",
             "fraction_of_3x3_windows_with_a_repeated_value": round(ties, 3)}
+
+
+def config2_autocast(args, dj, comb, g, world, dev, px_step):
+    """The headline step on a bfloat16 batch - the autocast boundary of the trainers (models/IRNcrop_model.py:340): every
+    layer stages / reads the 2-byte image as it is and stores its input gradient in that type (the *_typed entry points
+    and the typed DiffJPEG / 8x8 JPEG / noise kernels); the attack arithmetic stays float32.  An extra, not the headline:
+    the headline is the reference's float32 configuration."""
+    gen = torch.Generator(dev).manual_seed(11)
+    x = torch.rand(B, 3, H, W, device=dev, generator=gen).to(torch.bfloat16).requires_grad_(True)
+    for s in range(max(2, args.warmup // 2)):
+        run_step(dj, comb, x, g, s)
+    torch.cuda.synchronize()
+    assert x.grad is not None and x.grad.dtype == torch.bfloat16
+    ms = timed(lambda: [run_step(dj, comb, x, g, s) for s in range(4)], max(1, args.steps // 4), 0, world, dev) / 4
+    return {"workload": "the config-2 step on a bfloat16 batch (typed boundary: 2-byte image in, 2-byte gradient out, float32 arithmetic)",
+            "ms_per_step": round(ms, 4), "value": round(world * px_step / ms / 1e3, 1), "unit": "Mpix/s"}
 
 
 def wmattack_unique_fraction(x):
