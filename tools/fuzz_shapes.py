@@ -41,7 +41,7 @@ def ofb(fn, x, g):
 for case in range(n_cases):
     b = int(rng.randint(1, 4))
     h = int(rng.choice([1, 2, 3, 5, 8, 17, 31, 36, 37, 40, 64, 73, 100]))
-    w = int(rng.choice([1, 2, 3, 6, 9, 20, 33, 63, 64, 65, 127, 128, 130, 131, 200, 258]))
+    w = int(rng.choice([1, 2, 3, 6, 8, 9, 16, 20, 33, 63, 64, 65, 72, 127, 128, 130, 131, 136, 200, 258, 264]))
     x = torch.from_numpy(rng.rand(b, 3, h, w).astype(np.float32))
     if rng.rand() < 0.3:
         x = torch.round(x * 7) / 7                      # ties
@@ -68,6 +68,21 @@ for case in range(n_cases):
         mid = torch.nn.functional.interpolate(x, size=[int(r * h), int(r * w)], mode="bicubic")
         ref = torch.clamp(torch.nn.functional.interpolate(mid, size=[h, w], mode="bicubic"), 0, 1)
         note("resize", float((y - ref).abs().max()), 2e-5, ctx + (r,))
+    # autocast boundary: the same layers on a float16 / bfloat16 image (typed kernels when the rows sit on 16-byte
+    # boundaries, one cast otherwise) must equal the float32 kernels on the widened image, gradient rounded to that type
+    dt = torch.float16 if rng.rand() < 0.5 else torch.bfloat16
+    xh = x.to(dt)
+    half_layers = [("blur3", wmattack.GaussianBlur(3), {}), ("median3", wmattack.MiddleBlur(3), {}), ("median5", wmattack.MiddleBlur(5), {}),
+                   ("jpegmask", wmattack.JpegMask(50), {})]
+    if h >= 8 and w >= 8:
+        half_layers.append(("resize", wmattack.Resize(), {"resize_ratio": float(rng.choice([0.5, 0.75, 1.25, 1.5]))}))
+    for name, layer, kw in half_layers:
+        xa = xh.to(dev).requires_grad_(True); ya = layer(xa, **kw); ya.backward(g.to(dev))
+        xb = xh.float().to(dev).requires_grad_(True); yb = layer(xb, **kw); yb.backward(g.to(dev))
+        note(f"{name}.half", float((ya - yb).abs().max()), 0.0, ctx + (str(dt),))
+        note(f"{name}.half.grad", float((xa.grad.float() - xb.grad.to(dt).float()).abs().max()), 0.0, ctx + (str(dt),))
+        if xa.grad.dtype != dt:
+            print(f"FAIL {name}: gradient dtype {xa.grad.dtype} for a {dt} image"); sys.exit(1)
     # strided view: a column slice of a wider tensor (odd row stride)
     if w > 8:
         wide = torch.from_numpy(rng.rand(b, 3, h, w + 5).astype(np.float32)).to(dev)
