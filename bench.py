@@ -459,7 +459,7 @@ def config2_autocast(args, dj, comb, g, world, dev, px_step):
     the headline is the reference's float32 configuration."""
     gen = torch.Generator(dev).manual_seed(11)
     x = torch.rand(B, 3, H, W, device=dev, generator=gen).to(torch.bfloat16).requires_grad_(True)
-    for s in range(max(2, args.warmup // 2)):
+    for s in range(max(4, args.warmup)):                     # every Resize ratio once: the 2-byte gradient buffers of each size get cached
         run_step(dj, comb, x, g, s)
     torch.cuda.synchronize()
     assert x.grad is not None and x.grad.dtype == torch.bfloat16
