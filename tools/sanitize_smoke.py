@@ -48,5 +48,30 @@ for t in range(3):
     for m in (wmattack.GaussianBlur(), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5), wmattack.DiffJPEG(True, 48, 160, 50), wmattack.JpegSS(30)):
         run(m, xs)
     run(wmattack.Resize(), xs, resize_ratio=0.8)
+# autocast boundary: float16 / bfloat16 images through every layer (typed kernels on the 16-byte grid, one cast otherwise)
+for dt in (torch.float16, torch.bfloat16):
+    for shape in ((2, 3, 48, 64), (1, 3, 70, 136), (1, 3, 33, 20), (2, 3, 37, 264)):
+        x = torch.rand(*shape, device=dev).to(dt)
+        h, w = shape[2:]
+        layers = [wmattack.Jpeg(50), wmattack.JpegSS(50), wmattack.JpegMask(50), wmattack.JpegCompression(dev), wmattack.GaussianBlur(3), wmattack.GaussianBlur(7),
+                  wmattack.MiddleBlur(3), wmattack.MiddleBlur(5), wmattack.Gaussian(), wmattack.SaltPepper(0.05), wmattack.Crop()]
+        if h % 16 == 0 and w % 16 == 0:
+            layers.append(wmattack.DiffJPEG(True, h, w, quality=50))
+        for m in layers:
+            xx = x.clone().requires_grad_(True)
+            y = m(xx)
+            y = y[0] if isinstance(y, tuple) else y
+            y.backward(torch.rand_like(y))
+            assert torch.isfinite(y).all() and torch.isfinite(xx.grad.float()).all() and xx.grad.dtype == dt, (type(m).__name__, shape, dt)
+        for r in (0.5, 0.75, 1.3, 2.0):
+            xx = x.clone().requires_grad_(True)
+            y = wmattack.Resize()(xx, resize_ratio=r)
+            y.backward(torch.rand_like(y))
+            assert torch.isfinite(y).all() and xx.grad.dtype == dt
+    clip = torch.rand(2, 3, 3, 48, 160, device=dev).to(dt)
+    for t in range(3):
+        for m in (wmattack.GaussianBlur(), wmattack.MiddleBlur(3), wmattack.MiddleBlur(5), wmattack.JpegSS(30)):
+            run(m, clip[:, :, t])
+        run(wmattack.Resize(), clip[:, :, t], resize_ratio=0.8)
 torch.cuda.synchronize()
 print("sanitize smoke ok")
