@@ -484,6 +484,63 @@ def test_ring_layers_read_half_inputs_and_store_half_gradients(dt):
         assert torch.equal(layer(odd), layer(odd.float())) and xa.grad.dtype == dt
 
 
+@pytest.mark.parametrize("dt", (torch.bfloat16, torch.float16))
+def test_typed_ring_kernels_stay_inside_their_outputs(dt):
+    """compute-sanitizer is not available on the pool: guard bands instead.  Every output of the typed entry points
+    (float32 result, arg-median plane, 2-byte gradient) lives in the middle of a sentinel-filled buffer; tiles overhang
+    the image in both directions at these shapes; the bands must come back untouched."""
+    import ctypes as C
+    from wmattack import _lib
+    code = {torch.float16: 1, torch.bfloat16: 2}[dt]
+    guard = 4096
+
+    def guarded(numel, dtype, fill):
+        buf = torch.full((numel + 2 * guard,), fill, device=DEV, dtype=dtype)
+        return buf, buf[guard:guard + numel]
+
+    def intact(buf, fill, what):
+        assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all()), what
+
+    taps = (C.c_float * 3)(0.25, 0.5, 0.25)
+    for n, h, w in ((3, 37, 136), (1, 130, 8), (2, 70, 264)):
+        x = (torch.rand(n, h, w, device=DEV) * 1.2 - 0.1).to(dt)
+        gy = torch.rand(n, h, w, device=DEV)
+        st = torch.cuda.current_stream().cuda_stream
+        # blur: typed source -> float32 result; float32 source -> typed result
+        ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+        _lib.call("wm_gaussblur_typed", x.data_ptr(), code, h * w, w, y.data_ptr(), 0, n, h, w, taps, 3, st)
+        intact(ybuf, 7.0, "blur y")
+        gbuf, gx = guarded(n * h * w, dt, 7.0)
+        _lib.call("wm_gaussblur_typed", gy.data_ptr(), 0, h * w, w, gx.data_ptr(), code, n, h, w, taps, 3, st)
+        intact(gbuf, 7.0, "blur gx")
+        assert torch.equal(gx.view(n, h, w), wmattack.functional.gaussian_blur(gy[None], (0.25, 0.5, 0.25))[0].to(dt))
+        # median: typed source -> float32 result + arg-median plane; float32 cotangent -> typed gradient
+        for k in (3, 5):
+            idx_sh = -(-w // 16) * 16
+            ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+            ibuf, idx = guarded(n * h * idx_sh, torch.uint8, 99)
+            _lib.call("wm_median_fwd_typed", x.data_ptr(), code, h * w, w, y.data_ptr(), idx.data_ptr(), idx_sh, n, h, w, k, st)
+            intact(ybuf, 7.0, f"median{k} y"); intact(ibuf, 99, f"median{k} idx")
+            assert bool((idx.view(n, h, idx_sh)[:, :, :w] < k * k).all())
+            gbuf, gx = guarded(n * h * w, dt, 7.0)
+            _lib.call("wm_median_bwd_typed", gy.data_ptr(), idx.data_ptr(), idx_sh, gx.data_ptr(), code, n, h, w, k, st)
+            intact(gbuf, 7.0, f"median{k} gx")
+        # fused resize: typed source -> float32 result + clamp mask; float32 cotangent -> typed gradient
+        if h >= 16 and w >= 16:
+            hm, wm = int(0.75 * h), int(0.75 * w)
+            tables = wmattack.functional._resize_tables(torch.device(DEV), h, w, (hm, wm), 1)
+            if tables is not None:
+                ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+                mwords = n * h * 4 * ((w + 127) // 128)
+                mbuf, mask = guarded(mwords, torch.int32, 12345)
+                _lib.call("wm_resize_fwd_typed", x.data_ptr(), code, h * w, w, y.data_ptr(), n, h, w, hm, wm, 1, mask.data_ptr(), tables.data_ptr(), st)
+                intact(ybuf, 7.0, "resize y"); intact(mbuf, 12345, "resize mask")
+                gbuf, gx = guarded(n * h * w, dt, 7.0)
+                _lib.call("wm_resize_bwd_typed", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), code, n, h, w, hm, wm, 1, tables.data_ptr(), st)
+                intact(gbuf, 7.0, "resize gx")
+    torch.cuda.synchronize()
+
+
 def test_typed_ring_entry_points_reject_unaligned_rows():
     import ctypes as C
     from wmattack import _lib
