@@ -541,6 +541,62 @@ def test_typed_ring_kernels_stay_inside_their_outputs(dt):
     torch.cuda.synchronize()
 
 
+def test_float32_kernels_stay_inside_their_outputs_at_ragged_and_overhanging_shapes():
+    """Guard bands around every output of the float32 entry points at shapes where tiles overhang the image and rows are
+    off the 16-byte grid (predicated scalar stores, cp.async-fed rings): nothing outside the output may change."""
+    import ctypes as C
+    from wmattack import _lib
+    guard = 4096
+
+    def guarded(numel, dtype, fill):
+        buf = torch.full((numel + 2 * guard,), fill, device=DEV, dtype=dtype)
+        return buf, buf[guard:guard + numel]
+
+    def intact(buf, fill, what):
+        assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all()), what
+
+    taps = (C.c_float * 3)(0.25, 0.5, 0.25)
+    jp = wmattack.JpegMask(50)._params
+    for n, h, w in ((3, 37, 131), (3, 70, 510), (3, 37, 132), (6, 5, 3), (3, 130, 8)):
+        x = torch.rand(n, h, w, device=DEV)
+        gy = torch.rand(n, h, w, device=DEV)
+        st = torch.cuda.current_stream().cuda_stream
+        ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+        _lib.call("wm_gaussblur", x.data_ptr(), h * w, w, y.data_ptr(), n, h, w, taps, 3, 0, 0, None, st)
+        intact(ybuf, 7.0, f"blur {n, h, w}")
+        for k in (3, 5):
+            idx_sh = -(-w // 16) * 16
+            ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+            ibuf, idx = guarded(n * h * idx_sh, torch.uint8, 99)
+            _lib.call("wm_median_fwd", x.data_ptr(), h * w, w, y.data_ptr(), idx.data_ptr(), idx_sh, n, h, w, k, None, st)
+            intact(ybuf, 7.0, f"median{k} y {n, h, w}"); intact(ibuf, 99, f"median{k} idx {n, h, w}")
+            gbuf, gx = guarded(n * h * w, torch.float32, 7.0)
+            _lib.call("wm_median_bwd", gy.data_ptr(), idx.data_ptr(), idx_sh, gx.data_ptr(), n, h, w, k, st)
+            intact(gbuf, 7.0, f"median{k} gx {n, h, w}")
+        if h >= 16 and w >= 16:
+            for ratio in (0.75, 1.5):
+                hm, wm = int(ratio * h), int(ratio * w)
+                tables = wmattack.functional._resize_tables(torch.device(DEV), h, w, (hm, wm), 1)
+                if tables is None:
+                    continue
+                ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+                mbuf, mask = guarded(n * h * 4 * ((w + 127) // 128), torch.int32, 12345)
+                _lib.call("wm_resize_fwd", x.data_ptr(), h * w, w, y.data_ptr(), n, h, w, hm, wm, 1, mask.data_ptr(), tables.data_ptr(), None, st)
+                intact(ybuf, 7.0, f"resize y {n, h, w, ratio}"); intact(mbuf, 12345, f"resize mask {n, h, w, ratio}")
+                gbuf, gx = guarded(n * h * w, torch.float32, 7.0)
+                _lib.call("wm_resize_bwd", gy.data_ptr(), mask.data_ptr(), gx.data_ptr(), n, h, w, hm, wm, 1, tables.data_ptr(), st)
+                intact(gbuf, 7.0, f"resize gx {n, h, w, ratio}")
+        if n % 3 == 0:          # the 8x8 JPEG family on [B,3,H,W]: ragged widths take the scalar row path
+            b = n // 3
+            ybuf, y = guarded(n * h * w, torch.float32, 7.0)
+            _lib.call("wm_jpeg8_fwd", x.data_ptr(), 0, 3 * h * w, h * w, w, y.data_ptr(), b, h, w, C.byref(jp), None, st)
+            intact(ybuf, 7.0, f"jpeg8 y {n, h, w}")
+            gbuf, gx = guarded(n * h * w, torch.float32, 7.0)
+            _lib.call("wm_jpeg8_bwd", x.data_ptr(), 3 * h * w, h * w, w, gy.data_ptr(), 3 * h * w, h * w, w, gx.data_ptr(), 0, b, h, w, C.byref(jp), st)
+            intact(gbuf, 7.0, f"jpeg8 gx {n, h, w}")
+    torch.cuda.synchronize()
+
+
 def test_typed_ring_entry_points_reject_unaligned_rows():
     import ctypes as C
     from wmattack import _lib
