@@ -258,6 +258,10 @@ __global__ void __launch_bounds__(J8_THREADS, 3) jpeg8_fwd_kernel(const J8Args a
 // touch 8 different blocks with the same chunk index: conflict-free LDS.128 / STS.128.
 // ---------------------------------------------------------------------------------------------
 constexpr int J8P_THREADS = 128, J8P_BLOCKS = 64, J8P_CHUNKS = 48;
+#ifndef WM_J8_LOAD_UNROLL
+#define WM_J8_LOAD_UNROLL 2
+#endif
+constexpr int J8P_LOAD_UNROLL = WM_J8_LOAD_UNROLL;      // rows of the load + row-DCT phase in flight per thread
 
 // DMODE 0: plain forward.  1: JpegSS forward that also saves ss'(q) of every coefficient (12 B/px,
 // [B,3,Hp,W] in coefficient-image order).  2: JpegSS backward from that state: the cotangent runs
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(J8P_THREADS, 4) jpeg8_pair_kernel(const J8Args
     const int ncol = min(8, a.W - col0);
 
     // ---- rows 4h .. 4h+3: colour transform + row DCT of the three channels -> scratch --------------
-#pragma unroll 2
+#pragma unroll J8P_LOAD_UNROLL
     for (int i = 0; i < 4; ++i) {
         const int r = 4 * h + i;
         const bool ok = active && (row0 + r) < a.H;
