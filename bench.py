@@ -160,14 +160,18 @@ def build_layers(dev):
     return dj, comb
 
 
-def run_step(dj, comb, x, g, step, events=None):
-    """One step; if `events` is given, records a CUDA event after every forward and backward.
+def run_step(dj, comb, x, g, step, events=None, only=None):
+    """One step; if `events` is given, records a CUDA event after every forward and backward (mark m: 0 = step start,
+    2*li+1 = after layer li's forward, 2*li+2 = after its backward) - or, with `only`, just the marks in that set.
     Returns the last layer's input gradient (the step's result for the e2e read-back)."""
+    m = [0]
+
     def mark():
-        if events is not None:
+        if events is not None and (only is None or m[0] in only):
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             events.append(e)
+        m[0] += 1
     mark()
     for li in range(NL):
         x.grad = None
@@ -205,12 +209,19 @@ def ours(args, rank, world, dev):
         run_step(dj, comb, x, g, s)
     barrier(world)
     torch.cuda.synchronize()
-    events = []
+    # The timed region brackets ONE kernel with events - the dominant one (the 5x5 median forward), whose live duration the
+    # roofline object needs.  An event between EVERY pair of kernels costs ~3 us of pipeline bubble each (measured:
+    # 1.487 vs 1.446 ms per step, tools/exp/event_gap_probe.py), so the full per-kernel table comes from a second pass of
+    # the same K steps run right after the timed region (`kernels_pass` in the JSON line says so).
+    DOM = "middleblur5.fwd"
+    dli = LAYERS.index(DOM.split(".")[0])
+    dom_marks = {2 * dli, 2 * dli + 1}
+    dom_events = []
     launches0 = _lib.launch_count
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(args.steps):
-        run_step(dj, comb, x, g, s, events)
+        run_step(dj, comb, x, g, s, dom_events, dom_marks)
     t1.record()
     torch.cuda.synchronize()
     barrier(world)
@@ -218,9 +229,18 @@ def ours(args, rank, world, dev):
     ms = t0.elapsed_time(t1)
     ms = allreduce_max(ms, world, dev)
     value = world * args.steps * px_step / (ms / 1e3) / 1e6
+    dom_ms = sum(dom_events[2 * s].elapsed_time(dom_events[2 * s + 1]) for s in range(args.steps)) / args.steps
 
-    # per-kernel durations from the events recorded inside the timed region (every layer is ONE kernel
-    # launch per direction, so each event interval is one kernel + its launch gap)
+    # second pass: the same K steps with an event after every forward and backward (every layer is ONE kernel launch per
+    # direction, so each event interval is one kernel + its launch gap)
+    events = []
+    p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for s in range(args.steps):
+        run_step(dj, comb, x, g, s, events)
+    p1.record()
+    torch.cuda.synchronize()
+    pass_ms = p0.elapsed_time(p1) / args.steps
     per = {}
     n_ev = 2 * NL + 1
     for s in range(args.steps):
@@ -238,15 +258,24 @@ def ours(args, rank, world, dev):
         kernels[k] = {"ms": round(msk, 4), "GBps": round(byts / (msk / 1e3) / 1e9, 1),
                       "frac": round(byts / (msk / 1e3) / 1e9 / peak, 3)}
     dom = max(avg, key=avg.get)
+    # the kernel bracketed inside the timed region is the dominant one of the second pass too (if it ever were not,
+    # the roofline object falls back to the second pass's interval and says so)
+    live = dom == DOM
+    dom_live_ms = dom_ms if live else avg[dom]
     dname, dd = dom.split(".")
     dbytes = ALG_BYTES[dname][0 if dd == "fwd" else 1] * px
     step_bytes = sum(sum(ALG_BYTES[n]) for n in LAYERS) * px
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dbytes / (avg[dom] / 1e3) / 1e9, 1), "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": round(dbytes / (avg[dom] / 1e3) / 1e9 / peak, 4),
-                "traffic": load_ncu_traffic(dom), "share_of_step": round(avg[dom] / (ms / args.steps), 4),
-                "algorithmic_bytes_per_launch": dbytes,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dbytes / (dom_live_ms / 1e3) / 1e9, 1), "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": round(dbytes / (dom_live_ms / 1e3) / 1e9 / peak, 4),
+                "traffic": load_ncu_traffic(dom), "share_of_step": round(dom_live_ms / (ms / args.steps), 4),
+                "algorithmic_bytes_per_launch": dbytes, "kernel_ms": round(dom_live_ms, 4),
+                "measured": "CUDA events around this kernel inside the timed region" if live else "second pass (see kernels_pass)",
                 "whole_step": {"algorithmic_bytes": step_bytes, "GBps": round(step_bytes / (ms / args.steps / 1e3) / 1e9, 1),
                                "frac": round(step_bytes / (ms / args.steps / 1e3) / 1e9 / peak, 4)}}
+    kernels_pass = {"what": "the same K steps run once more right after the timed region with a CUDA event after EVERY forward and "
+                            "backward: the `kernels` table.  The timed region itself records events only around the dominant kernel "
+                            "(an event between every pair of kernels costs ~3 us of pipeline bubble each)",
+                    "ms_per_step": round(pass_ms, 4)}
 
     e2e = run_e2e(args, dj, comb, g, rank, world, dev, px_step)
     e2e_u8 = run_e2e(args, dj, comb, g, rank, world, dev, px_step, u8=True)
@@ -282,7 +311,7 @@ def ours(args, rank, world, dev):
         "config": config_block(world),
         "e2e": e2e, "e2e_u8": dict(e2e_u8, note="same step with 8-bit host frames: bytes uploaded and converted on the "
                                               "device (wm_u8_to_unit_float), result returned as bytes; extra to the contract's fp32 e2e"),
-        "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "kernels_pass": kernels_pass,
         "parity_note": "MiddleBlur/GF delegate to kornia upstream (not vendored/pinned/installed): their parity is "
                        "pinned only to the kornia 0.6.x algorithm restated in oracle/ — 'parity unpinned' rows",
         "clocks": clk.summary(),
