@@ -25,7 +25,7 @@ out = ["# Round-2 measurements (B200, 64x3x512x512 fp32, BASELINE config 2: 7 la
        f"e2e (pinned fp32 host batch in AND 201 MB result out, inside the timed region) = {d['e2e']['value']} Mpix/s, e2e_u8 (8-bit host frames) = {d['e2e_u8']['value']} Mpix/s; "
        f"the unmodified reference on the host cores = {d['cpu_baseline']['value']} Mpix/s on {d['cpu_baseline']['cores']} threads, run eagerly on the same B200 = "
        f"{d['reference_gpu_eager']['value']} Mpix/s.", "",
-       "## Per layer, CUDA-event time inside the timed region (fraction of the measured 6536.7 GB/s copy peak on ALGORITHMIC bytes)", "",
+       "## Per layer, CUDA-event time of the per-kernel pass (the same K steps right after the timed region, an event after every kernel; fraction of the measured 6536.7 GB/s copy peak on ALGORITHMIC bytes).  The timed region itself brackets only the dominant kernel: " + f"{d['roofline']['kernel']} = {d['roofline']['kernel_ms'] * 1e3:.1f} us live, {d['roofline']['frac']} of the roofline; the per-kernel pass runs at {d['kernels_pass']['ms_per_step']} ms per step (every event costs ~3 us)", "",
        "| layer.direction | us | alg. GB/s | frac |", "|---|---|---|---|"]
 for k, v in d["kernels"].items():
     out.append(f"| {k} | {v['ms'] * 1e3:.1f} | {v['GBps']:.0f} | {v['frac']:.3f} |")
