@@ -69,6 +69,19 @@ template <class CE> __device__ __forceinline__ void sort5(float (&v)[5], const C
     ce(v[0], v[1]); ce(v[3], v[4]); ce(v[2], v[4]); ce(v[2], v[3]); ce(v[0], v[3]);
     ce(v[0], v[2]); ce(v[1], v[4]); ce(v[1], v[3]); ce(v[1], v[2]);
 }
+// the same network with its first NPLAIN comparators as plain min/max pairs (2 ALU-pipe instructions) and the rest as
+// min + integer-sum max (1 ALU + 2 FMA-pipe instructions): a per-comparator balance between issue slots and the ALU pipe
+#ifndef WM_M5_SORT_PLAIN
+#define WM_M5_SORT_PLAIN 4
+#endif
+template <int NPLAIN, class CE> __device__ __forceinline__ void sort5_mixed(float (&v)[5], const CE ce) {
+    const CeMinMax pl{};
+    constexpr int A[9] = {0, 3, 2, 2, 0, 0, 1, 1, 1}, B[9] = {1, 4, 4, 3, 3, 2, 4, 3, 2};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (i < NPLAIN) pl(v[A[i]], v[B[i]]); else ce(v[A[i]], v[B[i]]);
+    }
+}
 template <bool INT> struct ce_pick { using type = CeMinMax; static __device__ __forceinline__ type make(int, int) { return type(); } };
 template <> struct ce_pick<true> { using type = CeIntSum; static __device__ __forceinline__ type make(int one, int neg1) { return type{one, neg1}; } };
 
@@ -288,7 +301,7 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const void* stag
             srt[slot][k] = tile_ld1<IDT>(stage, p + k);
             if (WANT_IDX) raw[slot][k] = srt[slot][k];
         }
-        sort5(srt[slot], ce_s);
+        if (WANT_IDX) sort5_mixed<WM_M5_SORT_PLAIN>(srt[slot], ce_s); else sort5(srt[slot], ce_s);
     };
 #pragma unroll
     for (int j = 0; j < 4; ++j) load_row(j, j);
