@@ -286,7 +286,9 @@ struct Med5Args {
 
 // One 128 x 36 tile of one plane: `col` = element index of the lane's window column in the staged box `stage`
 // (row 0 = image row gy0 - 2; elements of type IDT).
-template <bool WANT_IDX, bool EP, int IDT>
+// FULL: this lane stores all M5_ROWS rows of the tile (every lane inside the image when H >= M5_ROWS, thanks to the
+// shifted bottom tile): the per-output row test and its branch go away.
+template <bool WANT_IDX, bool EP, int IDT, bool FULL = false>
 __device__ __forceinline__ void median5_tile(const Med5Args& a, const void* stage, int col, int64_t obase, int64_t ibase, int rows_ok) {
     // with the arg-median search on the ALU pipe too, every comparator moves its max to the FMA pipe; without it the
     // last network keeps plain FMNMX pairs (measured: 338 -> 261 us with, 231 -> 172 us without the plane at 64x3x504x512)
@@ -347,7 +349,7 @@ __device__ __forceinline__ void median5_tile(const Med5Args& a, const void* stag
                         lo = fmaf(lo, 2.f, feq(raw[(2 * u + o + j / 5) % 6][j % 5], med));
                     pos = hi != 0.f ? first_match(hi, 15) : 15 + first_match(lo, 10);
                 }
-                if (r + o < rows_ok) {
+                if (FULL || r + o < rows_ok) {
                     yb[off] = EP ? ep_apply(med, a.ep.from_input ? tile_ld1<IDT>(stage, col + (r + o + 2) * BW + 2) : a.ep.x[obase + off], a.ep) : med;
                     if (WANT_IDX) ib[ioff] = (uint8_t)pos;
                 }
@@ -418,7 +420,12 @@ __global__ void __launch_bounds__(M5_THREADS, 2) median5_tma_kernel(const __grid
         const int col = half * (BW * M5_BH) + HALO - 2 + c;
         const int64_t obase = (int64_t(n) * a.H + gy0) * a.W + gx;
         const int rows_ok = (gx < a.W && n < a.N) ? rows_tile : 0;          // this lane stores output rows r < rows_ok
-        median5_tile<WANT_IDX, EP, IDT>(a, tiles + size_t(s) * STRIDE * ES, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
+        // lanes that store the whole tile column (all of them inside an image of >= M5_ROWS rows) take the instantiation
+        // without the per-output row test (-9 us at 64x3x512x512); lanes outside the image or the plane count do nothing
+        if (rows_ok == M5_ROWS)
+            median5_tile<WANT_IDX, EP, IDT, true>(a, tiles + size_t(s) * STRIDE * ES, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
+        else if (rows_ok > 0)
+            median5_tile<WANT_IDX, EP, IDT>(a, tiles + size_t(s) * STRIDE * ES, col, obase, (int64_t(n) * a.H + gy0) * a.idx_sh + gx, rows_ok);
         __syncthreads();
         if (RAGGED || tid == 0) {
             const int64_t t2 = t + int64_t(M5_STAGES) * gridDim.x;
