@@ -28,6 +28,12 @@
 namespace wm {
 
 constexpr int RB_TW = 128, RB_TH = 64, RB_THREADS = 256;
+#ifndef WM_RB_FULL_PATH
+#define WM_RB_FULL_PATH 1
+#endif
+constexpr bool RB_FULL_PATH = WM_RB_FULL_PATH;
+struct wm_true { static constexpr bool value = true; };
+struct wm_false { static constexpr bool value = false; };
 constexpr float RB_RATIO_MIN = 0.45f, RB_RATIO_MAX = 2.2f;
 
 __device__ __forceinline__ float rb_cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
@@ -301,8 +307,10 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
         if ((RAGGED || tid == 0) && n + gridDim.z < a.N) request(n + gridDim.z);
 
         // ---- V pass: rows 4p .. 4p+3 x 4 columns per lane from one shared window of tmp --------------
-        {
-            const bool okc = 4 * lane < tw;
+        // FULL (a whole 128 x 64 tile inside the image): no column / row tests around the stores
+        auto vpass = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const bool okc = FULL || 4 * lane < tw;
             const bool want_mask = DIR == 0 && a.mask != nullptr;
             // running pointers of this warp's row quads (q = warp, warp + 8, ...)
             int64_t doff = (int64_t(n) * a.H + oy0 + 4 * warp) * a.W + ox0 + 4 * lane;     // element offset of this lane's first output
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                 if (PLAIN && !RAGGED && DIR == 0 && a.ep.x) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        xe[k] = (okc && 4 * qd + k < th) ? ldg128_nc(a.ep.x + doff + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xe[k] = (okc && (FULL || 4 * qd + k < th)) ? ldg128_nc(a.ep.x + doff + k * a.W) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int t = 0; t < BTV; ++t) {
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const bool okr = 4 * qd + k < th;              // uniform
+                    const bool okr = FULL || 4 * qd + k < th;      // uniform
                     const float4 acc = make_float4(lo[k].x, lo[k].y, hi[k].x, hi[k].y);
                     if (DIR == 0) {
                         const float4 c = clamp01_nan4(acc);
@@ -359,7 +367,9 @@ __global__ void __launch_bounds__(RB_THREADS, 2) rb_banded_kernel(const __grid_c
                     }
                 }
             }
-        }
+        };
+        // (forward, TMA rows: -2..3 us per launch at 64x3x512x512; the adjoint's plain stores gain nothing)
+        if (RB_FULL_PATH && DIR == 0 && !RAGGED && tw == RB_TW && th == RB_TH) vpass(wm_true{}); else vpass(wm_false{});
         __syncthreads();          // tmp is rewritten by the next plane's H pass
     }
 }
